@@ -1,0 +1,104 @@
+/* b200seg.h -- C ABI of libb200seg.so: the sm_100a kernels behind the reference's model classes.
+ *
+ * The reference (SEAME-pt/Team02-ObjectDetection) has no FFI layer of its own: its hot path is
+ * reached through the torch.nn.Module protocol (src/unet.py:32-51, :137-147) and every operator
+ * below replaces one ATen dispatch that path makes.  The Python mirror of
+ * src/unet.py (team02-objectdetection_b200/b200seg/unet.py) binds these with ctypes; see
+ * INTEGRATION.md for the stub.
+ *
+ * Conventions:
+ *   - plain C: raw device pointers, ints, floats; no torch / C++ types.
+ *   - activations are NHWC ("channels innermost"), dtype B200SEG_F32 or B200SEG_BF16; the channel
+ *     count of an NHWC tensor must be a multiple of 16 bytes / sizeof(dtype) unless stated.
+ *   - every entry point takes the CUDA stream to launch on, never synchronises, never allocates,
+ *     keeps no pointer after it returns, and is CUDA-graph capturable.
+ *   - return 0 on success; <0 argument/shape error (nothing launched); >0 a cudaError_t from the
+ *     launch.  b200seg_last_error() returns a thread-local message for the last non-zero return.
+ *   - no CPU fallback: a host pointer is undefined behaviour, a missing GPU is an error.
+ */
+#ifndef B200SEG_H_
+#define B200SEG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* b200seg_stream_t;
+
+enum { B200SEG_F32 = 0, B200SEG_BF16 = 1 };
+enum { B200SEG_ACT_NONE = 0, B200SEG_ACT_RELU = 1, B200SEG_ACT_RELU6 = 2 };
+
+int b200seg_version(void);
+const char* b200seg_last_error(void);
+/* number of SMs / compute capability major*10+minor of the current device (sanity: 148 / 100). */
+int b200seg_device_info(int* sm_count, int* cc);
+
+/* ---------------------------------------------------------------------------------------------
+ * Direct 3x3 convolution for tiny Cin (the stem, torchvision mobilenetv2.py:125-127 called from
+ * unet.py:15/34; and UNet.inc's first conv, unet.py:58,127).  pad 1, stride 1 or 2.
+ *   x  : NCHW [B,Cin,H,W] (f32 or bf16)  -- the model's public input layout
+ *   w  : f32 [3][3][Cin][Cout] with the eval-mode BatchNorm scale already folded in
+ *   b  : f32 [Cout] folded shift (conv bias and BN), may be NULL
+ *   y  : NHWC [B,Ho,Wo,Cout]; Cout % 8 == 0, Cin <= 4
+ * replaces aten::convolution + native_batch_norm + hardtanh/relu. */
+int b200seg_conv3x3_smallcin(const void* x, int x_dtype, const float* w, const float* b, void* y,
+                             int y_dtype, int B, int Cin, int H, int W, int Cout, int stride, int act,
+                             b200seg_stream_t s);
+
+/* Depthwise 3x3 (+folded BN shift +act), NHWC, pad 1, stride 1|2 (mobilenetv2.py:42-51).
+ *   w : f32 [9][C] (tap-major, BN scale folded);  b : f32 [C] or NULL. */
+int b200seg_dwconv3x3(const void* x, const float* w, const float* b, void* y, int dtype, int B, int H,
+                      int W, int C, int stride, int act, b200seg_stream_t s);
+
+/* Dense convolution on the 5th-gen tensor cores: TMA -> smem ring -> tcgen05.mma -> TMEM ->
+ * epilogue(bias, act, +residual) -> TMA store.  bf16 in / fp32 accumulate / bf16 out.
+ * taps = 1 (pointwise, mobilenetv2.py:38,53; unet.py:113,116) or 9 (3x3 pad 1 stride 1, unet.py:58,61).
+ *   x   : NHWC bf16 [B,H,W,Cin]          Cin % 8 == 0
+ *   w   : bf16 [Cout][taps][Cin]         (K-major "OHWI"; BN scale folded)
+ *   b   : f32 [Cout] or NULL
+ *   res : NHWC bf16 [B,H,W,Cout] or NULL (added after act: the inverted-residual shortcut,
+ *         mobilenetv2.py:61-62)
+ *   y   : NHWC bf16 [B,H,W,Cout]         Cout % 8 == 0
+ *   flags: bit0 = store straight from registers instead of smem+TMA (debug / odd pitches) */
+int b200seg_conv_tc(const void* x, const void* w, const float* b, const void* res, void* y, int B, int H,
+                    int W, int Cin, int Cout, int taps, int act, int flags, b200seg_stream_t s);
+
+/* Same contract on the FP32 SIMT pipes (no tensor cores) for the fp32 parity configuration
+ * (BASELINE config 1: 1e-4 relative needs true fp32 products, SURVEY finding 10c).  dtype selects
+ * the storage type of x/res/y; w is f32 [Cout][taps][Cin]. */
+int b200seg_conv_simt(const void* x, const float* w, const float* b, const void* res, void* y, int dtype,
+                      int B, int H, int W, int Cin, int Cout, int taps, int act, b200seg_stream_t s);
+
+/* up.forward (unet.py:100-103): y[..., :Cs] = skip ; y[..., Cs:] = bilinear_x2(x, align_corners=False).
+ *   skip NHWC [B,2h,2w,Cs], x NHWC [B,h,w,Cu], y NHWC [B,2h,2w,Cs+Cu]. */
+int b200seg_upsample2x_concat(const void* skip, const void* x, void* y, int dtype, int B, int h, int w,
+                              int Cs, int Cu, b200seg_stream_t s);
+
+/* final_upsample (unet.py:30,49): bilinear x2 align_corners=True of NHWC logits [B,h,w,ldc]
+ * (first C channels valid) into NCHW [B,C,2h,2w] of out_dtype -- the model's public output. */
+int b200seg_upsample2x_ac_nchw(const void* logits, int dtype, int ldc, void* out, int out_dtype, int B,
+                               int h, int w, int C, b200seg_stream_t s);
+/* Same, fused with the per-pixel argmax inference.py:64 takes: writes uint8 [B,2h,2w]. */
+int b200seg_upsample2x_ac_argmax(const void* logits, int dtype, int ldc, uint8_t* mask, int B, int h,
+                                 int w, int C, b200seg_stream_t s);
+
+/* NHWC [B,H,W,ldc] (first C valid) -> NCHW [B,C,H,W] (UNet returns logits at input resolution). */
+int b200seg_nhwc_to_nchw(const void* x, int dtype, int ldc, void* out, int out_dtype, int B, int H, int W,
+                         int C, b200seg_stream_t s);
+
+/* MaxPool2d(2) NHWC (unet.py:85). */
+int b200seg_maxpool2x2(const void* x, void* y, int dtype, int B, int H, int W, int C, b200seg_stream_t s);
+
+/* nn.CrossEntropyLoss() forward fused with its gradient (main.py:99, train.py:37-38):
+ *   logits NCHW f32 [B,C,H,W], target int64 [B,H,W] in [0,C) (or ignore_index = -100)
+ *   loss_sum : f32[1], accumulates sum of -log softmax[target] (caller zeroes, divides by count)
+ *   dlogits  : NCHW f32 (softmax - onehot) * grad_scale, or NULL for forward only. */
+int b200seg_softmax_ce(const float* logits, const int64_t* target, float* loss_sum, float* dlogits,
+                       float grad_scale, int B, int C, int H, int W, b200seg_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SEG_H_ */

@@ -1,0 +1,247 @@
+"""Execution engine behind ``MobileNetV2UNet.forward`` / ``UNet.forward``.
+
+The nn.Module tree (b200seg.unet) only *holds* parameters.  This module turns it into a static
+list of fused steps -- conv(+BN)(+act)(+residual), depthwise conv(+BN+ReLU6), upsample+concat,
+final upsample -- packs the weights once per parameter version (BN folded in fp32, K-major bf16 for
+the tensor-core path) and launches the sm_100a kernels through the C ABI.
+
+Data layout in HBM: activations NHWC (channels innermost, 16-byte aligned rows) in the storage
+dtype (bf16 on the tensor-core path, f32 on the exact path); the public input/output stay NCHW as
+in the reference (unet.py:32-51): the stem kernel reads NCHW directly and the final upsample kernel
+writes NCHW directly, so no layout-conversion pass exists.
+
+Precision modes
+  "bf16": bf16 activations + tcgen05 convs (fp32 accumulate).  Chosen when the module is .bfloat16(),
+          under torch.autocast(bfloat16), or after ``model.set_precision("bf16")``.
+  "fp32": f32 activations + FP32-pipe convs: the 1e-4-relative configuration (BASELINE config 1).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import ACT_NONE, ACT_RELU, ACT_RELU6
+
+
+@dataclass
+class Step:
+    op: str                      # stem | dw | dense | upcat | pool | final | to_nchw
+    name: str                    # module path (debug / profiling labels)
+    src: str
+    dst: str
+    conv: Optional[nn.Conv2d] = None
+    bn: Optional[nn.BatchNorm2d] = None
+    act: int = ACT_NONE
+    stride: int = 1
+    taps: int = 1
+    res: Optional[str] = None    # residual source (dense) / skip source (upcat)
+    pad_cout: int = 0            # pad output channels (logits 10 -> 16)
+
+
+def _double_conv_steps(prefix: str, dc, src: str, dst: str) -> List[Step]:
+    seq = dc.conv
+    return [Step("dense", f"{prefix}.conv.0", src, dst + ".a", seq[0], seq[1], ACT_RELU, taps=9),
+            Step("dense", f"{prefix}.conv.3", dst + ".a", dst, seq[3], seq[4], ACT_RELU, taps=9)]
+
+
+def _outconv_steps(prefix: str, oc, src: str, dst: str) -> List[Step]:
+    seq = oc.conv
+    return [Step("dense", f"{prefix}.conv.0", src, dst + ".a", seq[0], seq[1], ACT_RELU, taps=1),
+            Step("dense", f"{prefix}.conv.3", dst + ".a", dst, seq[3], None, ACT_NONE, taps=1, pad_cout=16)]
+
+
+def build_steps_mbv2unet(model) -> List[Step]:
+    """Static schedule of MobileNetV2UNet.forward (unet.py:32-51)."""
+    f = model.backbone.features
+    st: List[Step] = [Step("stem", "backbone.features.0", "x", "f0", f[0][0], f[0][1], ACT_RELU6, stride=2, taps=9)]
+    for i in range(1, 18):
+        blk, seq, p = f[i], f[i].conv, f"backbone.features.{i}"
+        src, j = f"f{i - 1}", 0
+        if blk.expand_ratio != 1:
+            st.append(Step("dense", f"{p}.conv.0", src, f"f{i}.e", seq[0][0], seq[0][1], ACT_RELU6))
+            src, j = f"f{i}.e", 1
+        st.append(Step("dw", f"{p}.conv.{j}", src, f"f{i}.d", seq[j][0], seq[j][1], ACT_RELU6, stride=blk.stride, taps=9))
+        st.append(Step("dense", f"{p}.conv.{j + 1}", f"f{i}.d", f"f{i}", seq[j + 1], seq[j + 2], ACT_NONE,
+                       res=f"f{i - 1}" if blk.use_res_connect else None))
+    st.append(Step("dense", "backbone.features.18", "f17", "f18", f[18][0], f[18][1], ACT_RELU6))
+    cur = "f18"
+    for k, skip in ((1, "f10"), (2, "f6"), (3, "f3"), (4, "f1")):       # unet.py:41-44
+        st.append(Step("upcat", f"up{k}.up", cur, f"up{k}.cat", res=skip))
+        st += _double_conv_steps(f"up{k}.conv", getattr(model, f"up{k}").conv, f"up{k}.cat", f"up{k}")
+        cur = f"up{k}"
+    st += _outconv_steps("outc", model.outc, cur, "logits")
+    st.append(Step("final", "final_upsample", "logits", "out"))
+    return st
+
+
+def build_steps_unet(model) -> List[Step]:
+    """Static schedule of UNet.forward (unet.py:137-147)."""
+    seq = model.inc.conv.conv
+    st: List[Step] = [Step("stem", "inc.conv.conv.0", "x", "x1.a", seq[0], seq[1], ACT_RELU, stride=1, taps=9),
+                      Step("dense", "inc.conv.conv.3", "x1.a", "x1", seq[3], seq[4], ACT_RELU, taps=9)]
+    for k in (1, 2, 3):
+        st.append(Step("pool", f"down{k}.mpconv.0", f"x{k}", f"x{k}.p"))
+        st += _double_conv_steps(f"down{k}.mpconv.1", getattr(model, f"down{k}").mpconv[1], f"x{k}.p", f"x{k + 1}")
+    cur = "x4"
+    for k, skip in ((1, "x3"), (2, "x2"), (3, "x1")):
+        st.append(Step("upcat", f"up{k}.up", cur, f"up{k}.cat", res=skip))
+        st += _double_conv_steps(f"up{k}.conv", getattr(model, f"up{k}").conv, f"up{k}.cat", f"up{k}")
+        cur = f"up{k}"
+    st += _outconv_steps("sem_out", model.sem_out, cur, "logits")
+    st.append(Step("to_nchw", "output", "logits", "out"))
+    return st
+
+
+def fold_conv_bn(conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d]):
+    """Eval-mode BatchNorm folded into the convolution, in fp32:
+    w' = w * g/sqrt(rv+eps);  b' = beta + (b - rm) * g/sqrt(rv+eps)."""
+    w = conv.weight.detach().float()
+    b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(w.shape[0], device=w.device)
+    if bn is not None:
+        scale = bn.weight.detach().float() * torch.rsqrt(bn.running_var.detach().float() + bn.eps)
+        w = w * scale[:, None, None, None]
+        b = bn.bias.detach().float() + (b - bn.running_mean.detach().float()) * scale
+    return w, b
+
+
+class Engine:
+    def __init__(self, model, arch: str):
+        self.model = model
+        self.arch = arch
+        self.steps = build_steps_mbv2unet(model) if arch == "mbv2unet" else build_steps_unet(model)
+        self.precision: Optional[str] = None       # None = derive from module dtype / autocast
+        self.dense_impl: Optional[str] = None       # None = "tc" for bf16, "simt" for fp32 (tests may force)
+        self.tc_flags = 0
+        self._packed: Dict[str, dict] = {}
+        self._packed_key = None
+        self._bufs: Dict[tuple, Dict[str, torch.Tensor]] = {}
+        self.divisor = 32 if arch == "mbv2unet" else 8
+        self.out_ch = model.output_channels
+        if self.out_ch > 16:
+            raise NotImplementedError("b200seg: output_channels > 16 is not supported by the final-upsample kernel")
+
+    # ------------------------------------------------------------------ weights
+    def _version_key(self, mode: str):
+        v = 0
+        for t in self.model.parameters():
+            v += t._version
+        for t in self.model.buffers():
+            v += t._version
+        p0 = next(self.model.parameters())
+        return (mode, self.dense_impl, v, p0.device, p0.data_ptr())
+
+    def _pack_eval(self, mode: str):
+        key = self._version_key(mode)
+        if key == self._packed_key:
+            return self._packed
+        dense_impl = self.dense_impl or ("tc" if mode == "bf16" else "simt")
+        packed: Dict[str, dict] = {}
+        with torch.no_grad():
+            for s in self.steps:
+                if s.conv is None:
+                    continue
+                w, b = fold_conv_bn(s.conv, s.bn)
+                cout = w.shape[0]
+                if s.op == "stem":
+                    packed[s.name] = dict(w=w.permute(2, 3, 1, 0).contiguous(), b=b.contiguous())
+                elif s.op == "dw":
+                    packed[s.name] = dict(w=w.reshape(cout, 9).t().contiguous(), b=b.contiguous())
+                else:
+                    wk = w.permute(0, 2, 3, 1).reshape(cout, -1)        # [Cout][taps*Cin], K-major
+                    if s.pad_cout and cout < s.pad_cout:
+                        wk = torch.cat([wk, wk.new_zeros(s.pad_cout - cout, wk.shape[1])], 0)
+                        b = torch.cat([b, b.new_zeros(s.pad_cout - cout)], 0)
+                    wk = wk.to(torch.bfloat16) if dense_impl == "tc" else wk
+                    packed[s.name] = dict(w=wk.contiguous(), b=b.contiguous())
+        self._packed, self._packed_key = packed, key
+        return packed
+
+    # ------------------------------------------------------------------ helpers
+    def _mode(self, x: torch.Tensor) -> str:
+        if self.precision is not None:
+            return self.precision
+        p0 = next(self.model.parameters())
+        if p0.dtype == torch.bfloat16:
+            return "bf16"
+        if torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16:
+            return "bf16"
+        if p0.dtype != torch.float32:
+            raise TypeError(f"b200seg supports float32 and bfloat16 modules, got {p0.dtype}")
+        return "fp32"
+
+    def _check_input(self, x):
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError(f"expected input [B,3,H,W], got {tuple(x.shape)}")
+        B, _, H, W = x.shape
+        if B == 0:
+            raise ValueError("empty batch")
+        d = self.divisor
+        if H % d or W % d:
+            # the reference itself fails at torch.cat for such sizes (unet.py:103; SURVEY finding 8)
+            raise ValueError(f"H and W must be multiples of {d} (got {H}x{W}); pad the frame first")
+        p0 = next(self.model.parameters())
+        if p0.device != x.device:
+            raise RuntimeError(f"input on {x.device} but model on {p0.device}")
+
+    # ------------------------------------------------------------------ forward (eval)
+    @torch.no_grad()
+    def forward_eval(self, x: torch.Tensor, want_mask: bool = False, keep: Optional[dict] = None):
+        self._check_input(x)
+        mode = self._mode(x)
+        sdt = torch.bfloat16 if mode == "bf16" else torch.float32
+        dense_impl = self.dense_impl or ("tc" if mode == "bf16" else "simt")
+        if dense_impl == "tc" and mode != "bf16":
+            raise RuntimeError("tensor-core convs need bf16 storage")
+        pk = self._pack_eval(mode)
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError(f"input dtype {x.dtype} not supported")
+        x = x.contiguous()
+        out_dtype = x.dtype
+        env: Dict[str, torch.Tensor] = {"x": x}
+        for s in self.steps:
+            if s.op == "stem":
+                p = pk[s.name]
+                env[s.dst] = ops.conv3x3_smallcin(env[s.src], p["w"], p["b"], s.stride, s.act, sdt)
+            elif s.op == "dw":
+                p = pk[s.name]
+                env[s.dst] = ops.dwconv3x3(env[s.src], p["w"], p["b"], s.stride, s.act)
+            elif s.op == "dense":
+                p = pk[s.name]
+                res = env[s.res] if s.res else None
+                if dense_impl == "tc":
+                    env[s.dst] = ops.conv_tc(env[s.src], p["w"], p["b"], s.taps, s.act, res, flags=self.tc_flags)
+                else:
+                    env[s.dst] = ops.conv_simt(env[s.src], p["w"], p["b"], s.taps, s.act, res)
+            elif s.op == "upcat":
+                env[s.dst] = ops.upsample2x_concat(env[s.res], env[s.src])
+            elif s.op == "pool":
+                env[s.dst] = ops.maxpool2x2(env[s.src])
+            elif s.op == "final":
+                if want_mask:
+                    env[s.dst] = ops.upsample2x_ac_argmax(env[s.src], self.out_ch)
+                else:
+                    env[s.dst] = ops.upsample2x_ac_nchw(env[s.src], self.out_ch, out_dtype)
+            elif s.op == "to_nchw":
+                if want_mask:
+                    raise NotImplementedError("predict_mask is implemented for MobileNetV2UNet")
+                env[s.dst] = ops.nhwc_to_nchw(env[s.src], self.out_ch, out_dtype)
+            else:  # pragma: no cover
+                raise AssertionError(s.op)
+            if keep is None and s.src != "x":
+                pass  # torch's caching allocator recycles dead activations once env drops them
+        if keep is not None:
+            keep.update(env)
+        return env["out"]
+
+    # ------------------------------------------------------------------ dispatch
+    def forward(self, x: torch.Tensor, want_mask: bool = False):
+        if self.model.training:
+            if want_mask:
+                raise RuntimeError("predict_mask needs model.eval()")
+            from . import train_path
+            return train_path.forward_train(self, x)
+        return self.forward_eval(x, want_mask)

@@ -1,0 +1,440 @@
+// hbm_ops.cu -- the memory-bound operators: every kernel here moves each activation byte once,
+// with 16-byte vector accesses that are contiguous along the NHWC channel axis.
+//
+//   conv3x3_smallcin   stem / UNet.inc conv0   (NCHW in -> NHWC out, folded BN + act)
+//   dwconv3x3          depthwise 3x3 s1|s2     (folded BN + ReLU6)
+//   upsample2x_concat  bilinear x2 (align_corners=False) fused with cat([skip, up])
+//   upsample2x_ac_*    final bilinear x2 (align_corners=True) -> NCHW logits, or fused argmax mask
+//   nhwc_to_nchw, maxpool2x2
+#include "common.cuh"
+
+namespace b200 {
+
+static inline int grid_for(long long items, int threads) {
+  long long g = (items + threads - 1) / threads;
+  return (int)(g < 1 ? 1 : g);
+}
+
+// ------------------------------------------------------------------------------------------
+// conv3x3, tiny Cin (<=4), NCHW input -> NHWC output.  One thread = one output pixel x 8 channels.
+// Weights (f32 [9*Cin][Cout]) + bias staged in shared memory.
+// ------------------------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+conv3x3_smallcin_kernel(const TI* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                        TO* __restrict__ y, int B, int Cin, int H, int W, int Cout, int Ho, int Wo, int stride,
+                        int act) {
+  extern __shared__ float sw[];  // [9*Cin*Cout] + [Cout]
+  const int nw = 9 * Cin * Cout;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[nw + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int groups = Cout >> 3;
+  const long long total = (long long)B * Ho * Wo * groups;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % groups);
+    long long p = idx / groups;
+    const int wo = (int)(p % Wo); p /= Wo;
+    const int ho = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = sw[nw + g * 8 + j];
+    const int hi0 = ho * stride - 1, wi0 = wo * stride - 1;
+    for (int kh = 0; kh < 3; ++kh) {
+      const int hi = hi0 + kh;
+      if (hi < 0 || hi >= H) continue;
+      for (int kw = 0; kw < 3; ++kw) {
+        const int wi = wi0 + kw;
+        if (wi < 0 || wi >= W) continue;
+        for (int c = 0; c < Cin; ++c) {
+          const float xv = to_f32<TI>(x[(((long long)b * Cin + c) * H + hi) * W + wi]);
+          const float4* wp = reinterpret_cast<const float4*>(&sw[((kh * 3 + kw) * Cin + c) * Cout + g * 8]);
+          const float4 w0 = wp[0], w1 = wp[1];
+          acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
+          acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+          acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
+          acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+        }
+      }
+    }
+    TO* yp = y + (((long long)b * Ho + ho) * Wo + wo) * Cout + g * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = apply_act_rt(acc[j], act);
+    if (sizeof(TO) == 2) {
+      uint4 t;
+      t.x = pack_bf16x2(acc[0], acc[1]); t.y = pack_bf16x2(acc[2], acc[3]);
+      t.z = pack_bf16x2(acc[4], acc[5]); t.w = pack_bf16x2(acc[6], acc[7]);
+      *reinterpret_cast<uint4*>(yp) = t;
+    } else {
+      reinterpret_cast<float4*>(yp)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      reinterpret_cast<float4*>(yp)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// depthwise 3x3, NHWC.  One thread = TW consecutive output pixels along W x one 16-byte channel
+// vector; the 3 x (TW-1)*S+3 input window is walked row by row so each input vector is loaded
+// once per thread (sliding window in registers); neighbouring threads cover neighbouring channel
+// vectors, so every load/store instruction of a warp is one contiguous run of 16-byte words.
+// ------------------------------------------------------------------------------------------
+template <typename T, int S, int TW>
+__global__ void __launch_bounds__(256)
+dwconv3x3_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                 T* __restrict__ y, int B, int H, int W, int C, int Ho, int Wo, int act) {
+  using V = Vec16<T>;
+  constexpr int VN = V::N;
+  constexpr int NCOL = (TW - 1) * S + 3;
+  const int cv = C / VN;
+  const int strips = (Wo + TW - 1) / TW;
+  const long long total = (long long)B * Ho * strips * cv;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c0 = (int)(idx % cv) * VN;
+  long long p = idx / cv;
+  const int st = (int)(p % strips); p /= strips;
+  const int ho = (int)(p % Ho);
+  const int b = (int)(p / Ho);
+  const int wo0 = st * TW;
+
+  float acc[TW][VN];
+  {
+    float bv[VN];
+#pragma unroll
+    for (int j = 0; j < VN; ++j) bv[j] = bias ? __ldg(bias + c0 + j) : 0.f;
+#pragma unroll
+    for (int t = 0; t < TW; ++t)
+#pragma unroll
+      for (int j = 0; j < VN; ++j) acc[t][j] = bv[j];
+  }
+  const int wi0 = wo0 * S - 1;
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) {
+    const int hi = ho * S - 1 + kh;
+    if (hi < 0 || hi >= H) continue;
+    const T* row = x + (((long long)b * H + hi) * W) * C + c0;
+    V in[NCOL];
+#pragma unroll
+    for (int i = 0; i < NCOL; ++i) {
+      const int wi = wi0 + i;
+      if (wi >= 0 && wi < W) {
+        in[i].load(row + (long long)wi * C);
+      } else {
+#pragma unroll
+        for (int j = 0; j < VN; ++j) in[i].v[j] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      float wv[VN];
+      const float* wp = w + (kh * 3 + kw) * C + c0;
+#pragma unroll
+      for (int j = 0; j < VN; j += 4) {
+        const float4 t4 = __ldg(reinterpret_cast<const float4*>(wp + j));
+        wv[j] = t4.x; wv[j + 1] = t4.y; wv[j + 2] = t4.z; wv[j + 3] = t4.w;
+      }
+#pragma unroll
+      for (int t = 0; t < TW; ++t)
+#pragma unroll
+        for (int j = 0; j < VN; ++j) acc[t][j] = fmaf(in[t * S + kw].v[j], wv[j], acc[t][j]);
+    }
+  }
+  T* yrow = y + (((long long)b * Ho + ho) * Wo) * C + c0;
+#pragma unroll
+  for (int t = 0; t < TW; ++t) {
+    const int wo = wo0 + t;
+    if (wo < Wo) {
+      V o;
+#pragma unroll
+      for (int j = 0; j < VN; ++j) o.v[j] = apply_act_rt(acc[t][j], act);
+      o.store(yrow + (long long)wo * C);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// y[b,ho,wo,0:Cs] = skip ; y[b,ho,wo,Cs:] = bilinear x2 (align_corners=False) of x.
+// One thread = one 16-byte channel vector of one output pixel.
+// PyTorch source index: src = max(0, 0.5*(dst+0.5)-0.5); i0=floor(src); i1=min(i0+1,in-1).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+upsample2x_concat_kernel(const T* __restrict__ skip, const T* __restrict__ x, T* __restrict__ y, int B, int h,
+                         int w, int Cs, int Cu) {
+  using V = Vec16<T>;
+  constexpr int VN = V::N;
+  const int C = Cs + Cu, cv = C / VN, Ho = 2 * h, Wo = 2 * w;
+  const long long total = (long long)B * Ho * Wo * cv;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % cv) * VN;
+  long long p = idx / cv;
+  const int wo = (int)(p % Wo); p /= Wo;
+  const int ho = (int)(p % Ho);
+  const int b = (int)(p / Ho);
+  T* yp = y + (((long long)b * Ho + ho) * Wo + wo) * C + c;
+  if (c < Cs) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(skip + (((long long)b * Ho + ho) * Wo + wo) * Cs + c));
+    *reinterpret_cast<uint4*>(yp) = t;
+    return;
+  }
+  const int cu = c - Cs;
+  const float sy = fmaxf(0.5f * (ho + 0.5f) - 0.5f, 0.f), sx = fmaxf(0.5f * (wo + 0.5f) - 0.5f, 0.f);
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+  const float ly = sy - y0, lx = sx - x0;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  const T* xb = x + (long long)b * h * w * Cu + cu;
+  V a, bq, cq, d, o;
+  a.load(xb + ((long long)y0 * w + x0) * Cu);
+  bq.load(xb + ((long long)y0 * w + x1) * Cu);
+  cq.load(xb + ((long long)y1 * w + x0) * Cu);
+  d.load(xb + ((long long)y1 * w + x1) * Cu);
+#pragma unroll
+  for (int j = 0; j < VN; ++j) o.v[j] = hy * (hx * a.v[j] + lx * bq.v[j]) + ly * (hx * cq.v[j] + lx * d.v[j]);
+  o.store(yp);
+}
+
+// ------------------------------------------------------------------------------------------
+// final bilinear x2, align_corners=True, NHWC logits [B,h,w,ldc] -> NCHW [B,C,2h,2w] (or argmax).
+// One thread = PPT consecutive output pixels along W; stores are contiguous along W per plane.
+// src = dst * (in-1)/(out-1)  (PyTorch area_pixel_compute_scale with align_corners)
+// ------------------------------------------------------------------------------------------
+template <typename T, typename TO, int PPT, int CMAX, bool ARGMAX>
+__global__ void __launch_bounds__(256)
+upsample2x_ac_kernel(const T* __restrict__ lg, int ldc, TO* __restrict__ out, uint8_t* __restrict__ mask, int B,
+                     int h, int w, int C) {
+  const int Ho = 2 * h, Wo = 2 * w;
+  const int wq = Wo / PPT;
+  const long long total = (long long)B * Ho * wq;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int q = (int)(idx % wq);
+  long long p = idx / wq;
+  const int ho = (int)(p % Ho);
+  const int b = (int)(p / Ho);
+  const float sch = (Ho > 1) ? (float)(h - 1) / (float)(Ho - 1) : 0.f;
+  const float scw = (Wo > 1) ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
+  const float sy = sch * ho;
+  const int y0 = (int)sy;
+  const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
+  const float ly = sy - y0, hy = 1.f - ly;
+  const T* base = lg + (long long)b * h * w * ldc;
+  float res[PPT][CMAX];
+#pragma unroll
+  for (int t = 0; t < PPT; ++t) {
+    const int wo = q * PPT + t;
+    const float sx = scw * wo;
+    const int x0 = (int)sx;
+    const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
+    const float lx = sx - x0, hx = 1.f - lx;
+    const T* p00 = base + ((long long)y0 * w + x0) * ldc;
+    const T* p01 = base + ((long long)y0 * w + x1) * ldc;
+    const T* p10 = base + ((long long)y1 * w + x0) * ldc;
+    const T* p11 = base + ((long long)y1 * w + x1) * ldc;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      if (c < C) {
+        res[t][c] = hy * (hx * to_f32<T>(p00[c]) + lx * to_f32<T>(p01[c])) +
+                    ly * (hx * to_f32<T>(p10[c]) + lx * to_f32<T>(p11[c]));
+      } else {
+        res[t][c] = -INFINITY;
+      }
+    }
+  }
+  if (ARGMAX) {
+    uint32_t packed = 0;
+#pragma unroll
+    for (int t = 0; t < PPT; ++t) {
+      int best = 0;
+      float bv = res[t][0];
+#pragma unroll
+      for (int c = 1; c < CMAX; ++c)
+        if (res[t][c] > bv) { bv = res[t][c]; best = c; }   // first max wins, like torch.max
+      packed |= (uint32_t)best << (8 * t);
+    }
+    static_assert(!ARGMAX || PPT == 4, "argmax variant packs 4 pixels per 32-bit store");
+    *reinterpret_cast<uint32_t*>(mask + ((long long)b * Ho + ho) * Wo + q * PPT) = packed;
+  } else {
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      if (c < C) {
+        TO* op = out + (((long long)b * C + c) * Ho + ho) * Wo + q * PPT;
+#pragma unroll
+        for (int t = 0; t < PPT; ++t) op[t] = from_f32<TO>(res[t][c]);
+      }
+    }
+  }
+}
+
+template <typename T, typename TO>
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(const T* __restrict__ x, int ldc, TO* __restrict__ out, int B, int H, int W, int C) {
+  const long long total = (long long)B * H * W;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long hw = (long long)H * W;
+  const int b = (int)(idx / hw);
+  const long long pix = idx % hw;
+  const T* xp = x + idx * ldc;
+  for (int c = 0; c < C; ++c) out[((long long)b * C + c) * hw + pix] = from_f32<TO>(to_f32<T>(xp[c]));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool2x2_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C) {
+  using V = Vec16<T>;
+  constexpr int VN = V::N;
+  const int Ho = H / 2, Wo = W / 2, cv = C / VN;
+  const long long total = (long long)B * Ho * Wo * cv;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % cv) * VN;
+  long long p = idx / cv;
+  const int wo = (int)(p % Wo); p /= Wo;
+  const int ho = (int)(p % Ho);
+  const int b = (int)(p / Ho);
+  const T* xp = x + (((long long)b * H + 2 * ho) * W + 2 * wo) * C + c;
+  V a, bq, cq, d, o;
+  a.load(xp); bq.load(xp + C); cq.load(xp + (long long)W * C); d.load(xp + (long long)W * C + C);
+#pragma unroll
+  for (int j = 0; j < VN; ++j) o.v[j] = fmaxf(fmaxf(a.v[j], bq.v[j]), fmaxf(cq.v[j], d.v[j]));
+  o.store(y + (((long long)b * Ho + ho) * Wo + wo) * C + c);
+}
+
+}  // namespace b200
+
+using namespace b200;
+typedef __nv_bfloat16 bf16;
+
+extern "C" {
+
+int b200seg_conv3x3_smallcin(const void* x, int x_dtype, const float* w, const float* b, void* y, int y_dtype,
+                             int B, int Cin, int H, int W, int Cout, int stride, int act, b200seg_stream_t s) {
+  B200_REQUIRE(Cin >= 1 && Cin <= 4, "conv3x3_smallcin: Cin=%d not in 1..4", Cin);
+  B200_REQUIRE(Cout % 8 == 0 && Cout <= 256, "conv3x3_smallcin: Cout=%d must be a multiple of 8, <=256", Cout);
+  B200_REQUIRE(stride == 1 || stride == 2, "conv3x3_smallcin: stride=%d", stride);
+  B200_REQUIRE(B > 0 && H > 0 && W > 0, "conv3x3_smallcin: empty tensor");
+  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  const long long total = (long long)B * Ho * Wo * (Cout / 8);
+  const int threads = 256;
+  long long g = (total + threads - 1) / threads;
+  const long long cap = (long long)sm_count() * 8;
+  if (g > cap) g = cap;   // grid-stride: amortise the weight staging
+  const size_t smem = (size_t)(9 * Cin * Cout + Cout) * sizeof(float);
+  cudaStream_t st = (cudaStream_t)s;
+#define LAUNCH(TI, TO)                                                                                      \
+  conv3x3_smallcin_kernel<TI, TO><<<(int)g, threads, smem, st>>>((const TI*)x, w, b, (TO*)y, B, Cin, H, W, \
+                                                                 Cout, Ho, Wo, stride, act)
+  if (x_dtype == B200SEG_F32 && y_dtype == B200SEG_F32) LAUNCH(float, float);
+  else if (x_dtype == B200SEG_F32 && y_dtype == B200SEG_BF16) LAUNCH(float, bf16);
+  else if (x_dtype == B200SEG_BF16 && y_dtype == B200SEG_BF16) LAUNCH(bf16, bf16);
+  else if (x_dtype == B200SEG_BF16 && y_dtype == B200SEG_F32) LAUNCH(bf16, float);
+  else return set_error(-1, "conv3x3_smallcin: bad dtypes %d %d", x_dtype, y_dtype);
+#undef LAUNCH
+  return check_launch("conv3x3_smallcin");
+}
+
+int b200seg_dwconv3x3(const void* x, const float* w, const float* b, void* y, int dtype, int B, int H, int W,
+                      int C, int stride, int act, b200seg_stream_t s) {
+  const int vn = dtype == B200SEG_BF16 ? 8 : 4;
+  B200_REQUIRE(dtype == B200SEG_BF16 || dtype == B200SEG_F32, "dwconv3x3: bad dtype %d", dtype);
+  B200_REQUIRE(C % vn == 0, "dwconv3x3: C=%d must be a multiple of %d", C, vn);
+  B200_REQUIRE(stride == 1 || stride == 2, "dwconv3x3: stride=%d", stride);
+  B200_REQUIRE(B > 0 && H > 0 && W > 0, "dwconv3x3: empty tensor");
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  cudaStream_t st = (cudaStream_t)s;
+  const int threads = 256;
+#define LAUNCH(T, S, TW)                                                                              \
+  {                                                                                                   \
+    const long long total = (long long)B * Ho * ((Wo + TW - 1) / TW) * (C / vn);                       \
+    dwconv3x3_kernel<T, S, TW><<<grid_for(total, threads), threads, 0, st>>>((const T*)x, w, b, (T*)y, \
+                                                                             B, H, W, C, Ho, Wo, act); \
+  }
+  if (dtype == B200SEG_BF16) {
+    if (stride == 1) LAUNCH(bf16, 1, 4) else LAUNCH(bf16, 2, 2)
+  } else {
+    if (stride == 1) LAUNCH(float, 1, 4) else LAUNCH(float, 2, 2)
+  }
+#undef LAUNCH
+  return check_launch("dwconv3x3");
+}
+
+int b200seg_upsample2x_concat(const void* skip, const void* x, void* y, int dtype, int B, int h, int w, int Cs,
+                              int Cu, b200seg_stream_t s) {
+  const int vn = dtype == B200SEG_BF16 ? 8 : 4;
+  B200_REQUIRE(dtype == B200SEG_BF16 || dtype == B200SEG_F32, "upsample2x_concat: bad dtype %d", dtype);
+  B200_REQUIRE(Cs % vn == 0 && Cu % vn == 0 && Cu > 0 && Cs >= 0, "upsample2x_concat: Cs=%d Cu=%d must be multiples of %d", Cs, Cu, vn);
+  B200_REQUIRE(B > 0 && h > 0 && w > 0, "upsample2x_concat: empty tensor");
+  const long long total = (long long)B * 4 * h * w * ((Cs + Cu) / vn);
+  cudaStream_t st = (cudaStream_t)s;
+  if (dtype == B200SEG_BF16)
+    upsample2x_concat_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)skip, (const bf16*)x, (bf16*)y, B, h, w, Cs, Cu);
+  else
+    upsample2x_concat_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)skip, (const float*)x, (float*)y, B, h, w, Cs, Cu);
+  return check_launch("upsample2x_concat");
+}
+
+int b200seg_upsample2x_ac_nchw(const void* logits, int dtype, int ldc, void* out, int out_dtype, int B, int h,
+                               int w, int C, b200seg_stream_t s) {
+  B200_REQUIRE(C >= 1 && C <= 16 && ldc >= C, "upsample2x_ac_nchw: C=%d (<=16) ldc=%d", C, ldc);
+  B200_REQUIRE(B > 0 && h > 0 && w > 0, "upsample2x_ac_nchw: empty tensor");
+  cudaStream_t st = (cudaStream_t)s;
+  const long long total = (long long)B * 2 * h * (2 * w / 2);
+  const int g = grid_for(total, 256);
+#define LAUNCH(T, TO) upsample2x_ac_kernel<T, TO, 2, 16, false><<<g, 256, 0, st>>>((const T*)logits, ldc, (TO*)out, nullptr, B, h, w, C)
+  if (dtype == B200SEG_BF16 && out_dtype == B200SEG_BF16) LAUNCH(bf16, bf16);
+  else if (dtype == B200SEG_BF16 && out_dtype == B200SEG_F32) LAUNCH(bf16, float);
+  else if (dtype == B200SEG_F32 && out_dtype == B200SEG_F32) LAUNCH(float, float);
+  else if (dtype == B200SEG_F32 && out_dtype == B200SEG_BF16) LAUNCH(float, bf16);
+  else return set_error(-1, "upsample2x_ac_nchw: bad dtypes");
+#undef LAUNCH
+  return check_launch("upsample2x_ac_nchw");
+}
+
+int b200seg_upsample2x_ac_argmax(const void* logits, int dtype, int ldc, uint8_t* mask, int B, int h, int w, int C,
+                                 b200seg_stream_t s) {
+  B200_REQUIRE(C >= 1 && C <= 16 && ldc >= C, "upsample2x_ac_argmax: C=%d (<=16) ldc=%d", C, ldc);
+  B200_REQUIRE(B > 0 && h > 0 && w > 0 && (2 * w) % 4 == 0, "upsample2x_ac_argmax: bad shape");
+  cudaStream_t st = (cudaStream_t)s;
+  const long long total = (long long)B * 2 * h * (2 * w / 4);
+  const int g = grid_for(total, 256);
+  if (dtype == B200SEG_BF16)
+    upsample2x_ac_kernel<bf16, float, 4, 16, true><<<g, 256, 0, st>>>((const bf16*)logits, ldc, nullptr, mask, B, h, w, C);
+  else if (dtype == B200SEG_F32)
+    upsample2x_ac_kernel<float, float, 4, 16, true><<<g, 256, 0, st>>>((const float*)logits, ldc, nullptr, mask, B, h, w, C);
+  else return set_error(-1, "upsample2x_ac_argmax: bad dtype");
+  return check_launch("upsample2x_ac_argmax");
+}
+
+int b200seg_nhwc_to_nchw(const void* x, int dtype, int ldc, void* out, int out_dtype, int B, int H, int W, int C,
+                         b200seg_stream_t s) {
+  B200_REQUIRE(C >= 1 && ldc >= C && B > 0 && H > 0 && W > 0, "nhwc_to_nchw: bad shape");
+  cudaStream_t st = (cudaStream_t)s;
+  const int g = grid_for((long long)B * H * W, 256);
+#define LAUNCH(T, TO) nhwc_to_nchw_kernel<T, TO><<<g, 256, 0, st>>>((const T*)x, ldc, (TO*)out, B, H, W, C)
+  if (dtype == B200SEG_BF16 && out_dtype == B200SEG_BF16) LAUNCH(bf16, bf16);
+  else if (dtype == B200SEG_BF16 && out_dtype == B200SEG_F32) LAUNCH(bf16, float);
+  else if (dtype == B200SEG_F32 && out_dtype == B200SEG_F32) LAUNCH(float, float);
+  else if (dtype == B200SEG_F32 && out_dtype == B200SEG_BF16) LAUNCH(float, bf16);
+  else return set_error(-1, "nhwc_to_nchw: bad dtypes");
+#undef LAUNCH
+  return check_launch("nhwc_to_nchw");
+}
+
+int b200seg_maxpool2x2(const void* x, void* y, int dtype, int B, int H, int W, int C, b200seg_stream_t s) {
+  const int vn = dtype == B200SEG_BF16 ? 8 : 4;
+  B200_REQUIRE(dtype == B200SEG_BF16 || dtype == B200SEG_F32, "maxpool2x2: bad dtype");
+  B200_REQUIRE(C % vn == 0 && H % 2 == 0 && W % 2 == 0 && B > 0 && H > 0 && W > 0, "maxpool2x2: bad shape C=%d H=%d W=%d", C, H, W);
+  cudaStream_t st = (cudaStream_t)s;
+  const long long total = (long long)B * (H / 2) * (W / 2) * (C / vn);
+  if (dtype == B200SEG_BF16)
+    maxpool2x2_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)x, (bf16*)y, B, H, W, C);
+  else
+    maxpool2x2_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)x, (float*)y, B, H, W, C);
+  return check_launch("maxpool2x2");
+}
+
+}  // extern "C"
