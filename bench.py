@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 segmentation hot path (BASELINE.json `metric`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload infer|train] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+Default workload (N=1): BASELINE config[1] -- MobileNetV2UNet bf16 inference, batch 64 per GPU at
+3x256x512, 10 classes, random-init weights, synthetic frames; frames are sharded across ranks with no
+collective (weak scaling).  One "step" = one forward pass over one batch.
+
+One JSON line on rank 0:
+  value     images/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e       same metric through the public API with HOST (pinned) frames: H2D copy + forward +
+            fused argmax mask + D2H of the mask inside the timed region (the inference.py:159-166 loop)
+  roofline  the dominant kernel's achieved HBM GB/s (or TFLOP/s) vs MEASURED_PEAKS.json, measured
+            live with CUDA events on the launch stream
+  cpu_baseline  the oracle port of the reference path (fp32, PyTorch CPU) on this box's host cores
+--impl reference: times that CPU path alone (the reference is Python and is not present on the GPU
+box; the oracle port is its restatement, see oracle/unet_oracle.py).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "team02-objectdetection_b200"))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+H, W, NCLS = 256, 512, 10
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="infer", choices=["infer", "train"])
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default 64 infer / 32 train)")
+    ap.add_argument("--breakdown", action="store_true", help="print the per-kernel table to stderr")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tc_burst=d["bf16_tflops"], tc=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_leg(seconds=12.0, warmup=2, fixed_iters=None):
+    """The reference's CPU path (oracle port, fp32, batch 1 at 3x256x512, eval) on the host cores."""
+    from oracle import unet_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = O.synth_state_dict(O.mbv2unet_param_shapes(NCLS), seed=0)
+    x = O.synth_input(1, H, W, seed=0)
+    times = []
+    with torch.no_grad():
+        for _ in range(warmup):
+            O.mobilenetv2_unet_forward(sd, x)
+        t_end = time.perf_counter() + seconds
+        while (fixed_iters is None and time.perf_counter() < t_end) or (fixed_iters is not None and len(times) < fixed_iters):
+            t0 = time.perf_counter()
+            O.mobilenetv2_unet_forward(sd, x)
+            times.append(time.perf_counter() - t0)
+    tot = sum(times)
+    return dict(value=len(times) / tot, unit="images/s", cores=torch.get_num_threads(), kind="port",
+                sample=f"{len(times)} x (batch 1, 3x{H}x{W}, fp32 eval forward) oracle port of src/unet.py on PyTorch-CPU; "
+                       f"best {min(times) * 1e3:.1f} ms median {statistics.median(times) * 1e3:.1f} ms",
+                ms_per_image=tot / len(times) * 1e3)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    per_step = max(1, 1)
+    base = cpu_reference_leg(seconds=0, warmup=max(args.warmup, 1), fixed_iters=max(args.steps, 1) * per_step)
+    wall = time.perf_counter() - t0
+    line = {"impl": "reference", "metric": "MobileNetV2UNet inference images/s", "value": base["value"],
+            "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": base["ms_per_image"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"MobileNetV2UNet eval forward, 3x{H}x{W}, {NCLS} classes, random init; CPU sample: "
+                                   "batch 1 per step (reference inference.py is batch-1)", "device": "host CPU"},
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": wall}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import b200seg
+    from b200seg import _cabi
+    sms, cc = _cabi.device_info()
+
+    if args.workload == "train":
+        from bench_train import run_train          # training step benchmark lives in its own file
+        return run_train(args, dev, dist, world, rank, peaks())
+
+    B = args.batch or 64
+    torch.manual_seed(0)
+    model = b200seg.MobileNetV2UNet(output_channels=NCLS).to(dev).bfloat16().eval()
+    eng = model._get_engine()
+    g = torch.Generator(device="cpu").manual_seed(rank)
+    nrot = 4                                           # rotating inputs; activations (~7 GB/step) >> 126 MB L2 anyway
+    xs = [torch.randn(B, 3, H, W, generator=g).bfloat16().to(dev) for _ in range(nrot)]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- value leg: inputs resident in HBM ----------------
+    with torch.no_grad():
+        for i in range(args.warmup):
+            model(xs[i % nrot])
+        barrier()
+        clocks = ClockSampler(local)
+        if rank == 0:
+            clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            y = model(xs[i % nrot])
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clk = clocks.stop() if rank == 0 else None
+
+    # ---------------- e2e leg: host frames in, class mask out ----------------
+    xh = [torch.randn(B, 3, H, W, generator=g).bfloat16().pin_memory() for _ in range(2)]
+    mh = [torch.empty(B, H, W, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    xd = [torch.empty(B, 3, H, W, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+    copy_s, comp_s = torch.cuda.Stream(), torch.cuda.current_stream()
+
+    def e2e_steps(n):
+        # double-buffered: H2D of step i+1 overlaps the forward of step i; every copy is inside the timed region
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_free = [torch.cuda.Event() for _ in range(2)]
+        for i in range(n):
+            k = i & 1
+            with torch.cuda.stream(copy_s):
+                if i >= 2:
+                    copy_s.wait_event(ev_free[k])
+                xd[k].copy_(xh[k], non_blocking=True)
+                ev_in[k].record(copy_s)
+            comp_s.wait_event(ev_in[k])
+            mask = model.predict_mask(xd[k])
+            ev_free[k].record(comp_s)
+            mh[k].copy_(mask, non_blocking=True)
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        e2e_steps(max(3, args.warmup))
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        e2e_steps(args.steps)
+        t1.record()
+        barrier()
+        ms_e2e = t0.elapsed_time(t1)
+
+    # ---------------- per-kernel roofline (live, CUDA events on the launch stream) ----------------
+    pk = peaks()
+    acc = {}
+    with torch.no_grad():
+        for it in range(3 + 5):
+            prof = []
+            eng.forward_eval(xs[it % nrot], profile=prof)
+            torch.cuda.synchronize()
+            if it < 3:
+                continue
+            for s, a, b, nbytes, flops in prof:
+                r = acc.setdefault(s.name, dict(op=s.op, taps=s.taps, ms=0.0, bytes=nbytes, flops=flops, n=0))
+                r["ms"] += a.elapsed_time(b); r["n"] += 1
+    rows = []
+    for name, r in acc.items():
+        t = r["ms"] / r["n"] * 1e-3
+        gbs, tfs = r["bytes"] / t / 1e9, r["flops"] / t / 1e12
+        bound = "tensor" if (r["flops"] / max(r["bytes"], 1)) > pk["tc"] * 1e3 / pk["hbm"] else "hbm"
+        rows.append(dict(name=name, op=r["op"], us=t * 1e6, gbs=gbs, tfs=tfs, bound=bound, bytes=r["bytes"], flops=r["flops"],
+                         frac=(tfs / pk["tc_burst"]) if bound == "tensor" else gbs / pk["hbm"]))
+    rows.sort(key=lambda r: -r["us"])
+    tot_us = sum(r["us"] for r in rows)
+    if args.breakdown and rank == 0:
+        print(f"{'kernel':34s} {'op':6s} {'us':>9s} {'share':>6s} {'GB/s':>8s} {'TF/s':>8s} bound  frac", file=sys.stderr)
+        for r in rows:
+            print(f"{r['name']:34s} {r['op']:6s} {r['us']:9.1f} {r['us'] / tot_us:6.1%} {r['gbs']:8.0f} {r['tfs']:8.1f} "
+                  f"{r['bound']:6s} {r['frac']:.2f}", file=sys.stderr)
+        print(f"sum of kernels {tot_us:.0f} us; step {ms / args.steps * 1e3:.0f} us", file=sys.stderr)
+    top = rows[0]
+    roofline = {"kernel": top["name"], "bound": top["bound"],
+                "achieved": top["tfs"] if top["bound"] == "tensor" else top["gbs"],
+                "peak": pk["tc_burst"] if top["bound"] == "tensor" else pk["hbm"],
+                "unit": "TFLOP/s" if top["bound"] == "tensor" else "GB/s", "frac": top["frac"], "traffic": None,
+                "peak_source": pk["src"], "share_of_step": top["us"] / tot_us,
+                "algorithmic_per_launch": top["flops"] if top["bound"] == "tensor" else top["bytes"]}
+    tot_bytes = sum(r["bytes"] for r in rows)
+    step_roofline = {"bound": "hbm", "algorithmic_bytes_per_step": tot_bytes,
+                     "achieved": tot_bytes / (ms / args.steps * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                     "frac": tot_bytes / (ms / args.steps * 1e-3) / 1e9 / pk["hbm"]}
+
+    # ---------------- max over ranks ----------------
+    if dist is not None:
+        t = torch.tensor([ms, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_leg()
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    n_launch = len(eng.steps)
+    line = {"metric": "MobileNetV2UNet inference images/s", "value": B * world * args.steps / (ms * 1e-3),
+            "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"MobileNetV2UNet bf16 inference, batch {B}/GPU, 3x{H}x{W}, {NCLS} classes, random init "
+                                   "(BASELINE config[1]; frames sharded by rank, no collective)",
+                       "global_batch": B * world, "l2": "4 rotating input batches; ~7 GB of activations per step >> 126 MB L2",
+                       "sm_count": sms, "cc": cc},
+            "e2e": {"value": B * world * args.steps / (ms_e2e * 1e-3), "unit": "images/s",
+                    "h2d_bytes_per_step": B * 3 * H * W * 2, "d2h_bytes_per_step": B * H * W,
+                    "api": "model.predict_mask(frames): pinned bf16 NCHW frames -> uint8 class mask (fused final upsample + argmax), double-buffered copies"},
+            "gpu_launches": n_launch * args.steps, "launches_per_step": n_launch,
+            "roofline": roofline, "step_roofline": step_roofline, "clocks": clk}
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

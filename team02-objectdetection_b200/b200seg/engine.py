@@ -189,7 +189,10 @@ class Engine:
 
     # ------------------------------------------------------------------ forward (eval)
     @torch.no_grad()
-    def forward_eval(self, x: torch.Tensor, want_mask: bool = False, keep: Optional[dict] = None):
+    def forward_eval(self, x: torch.Tensor, want_mask: bool = False, keep: Optional[dict] = None,
+                     profile: Optional[list] = None):
+        """Eval-mode forward.  ``keep`` (dict) receives every intermediate NHWC tensor by schedule name;
+        ``profile`` (list) receives (step, start_event, end_event, bytes, flops) per launched kernel."""
         self._check_input(x)
         mode = self._mode(x)
         sdt = torch.bfloat16 if mode == "bf16" else torch.float32
@@ -203,6 +206,8 @@ class Engine:
         out_dtype = x.dtype
         env: Dict[str, torch.Tensor] = {"x": x}
         for s in self.steps:
+            if profile is not None:
+                ev0 = torch.cuda.Event(enable_timing=True); ev0.record()
             if s.op == "stem":
                 p = pk[s.name]
                 env[s.dst] = ops.conv3x3_smallcin(env[s.src], p["w"], p["b"], s.stride, s.act, sdt)
@@ -231,11 +236,35 @@ class Engine:
                 env[s.dst] = ops.nhwc_to_nchw(env[s.src], self.out_ch, out_dtype)
             else:  # pragma: no cover
                 raise AssertionError(s.op)
-            if keep is None and s.src != "x":
-                pass  # torch's caching allocator recycles dead activations once env drops them
+            if profile is not None:
+                ev1 = torch.cuda.Event(enable_timing=True); ev1.record()
+                nbytes, flops = self.step_cost(s, env, pk)
+                profile.append((s, ev0, ev1, nbytes, flops))
         if keep is not None:
             keep.update(env)
         return env["out"]
+
+    # ------------------------------------------------------------------ cost model
+    @staticmethod
+    def step_cost(s: Step, env, pk):
+        """Algorithmic HBM bytes and FLOPs of one fused step (SURVEY 8d traffic model): read every
+        input once, write the output once, weights once; FLOPs = 2*MAC."""
+        out = env[s.dst]
+        nbytes = out.numel() * out.element_size() + env[s.src].numel() * env[s.src].element_size()
+        flops = 0
+        if s.res:
+            nbytes += env[s.res].numel() * env[s.res].element_size()
+        if s.conv is not None:
+            p = pk[s.name]
+            nbytes += p["w"].numel() * p["w"].element_size() + p["b"].numel() * 4
+            if s.op == "dw":
+                flops = 2 * 9 * out.numel()
+            elif s.op == "stem":
+                flops = 2 * out.numel() * 27
+            else:
+                cout = s.conv.weight.shape[0]                      # real (unpadded) output channels
+                flops = 2 * (out.numel() // out.shape[-1]) * cout * s.taps * env[s.src].shape[-1]
+        return nbytes, flops
 
     # ------------------------------------------------------------------ dispatch
     def forward(self, x: torch.Tensor, want_mask: bool = False):

@@ -1,0 +1,201 @@
+"""T1: every CUDA kernel against the matching torch.nn.functional op (computed in
+float64 on the same GPU, i.e. no TF32 anywhere) on the reference's real layer shapes plus ragged
+ones.  All calls go through the C ABI (b200seg.ops -> ctypes -> libb200seg.so).
+
+Tolerances: f32 storage: 2e-5 of the output range.  bf16 storage: inputs/weights are rounded to
+bf16 first and the reference is computed from the rounded values, so the only error left is fp32
+accumulation order + one bf16 output rounding (2^-9 relative) -> 6e-3 of the output range.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from b200seg import ops  # noqa: E402
+
+DEV = "cuda"
+TOL = {torch.float32: 2e-5, torch.bfloat16: 6e-3}
+
+
+def _err(got, ref):
+    got, ref = got.double(), ref.double()
+    return float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+
+
+def _nhwc(t):  # NCHW -> NHWC contiguous
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def _nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+def _act(y, act):
+    return {0: y, 1: F.relu(y), 2: torch.clamp(y, 0, 6)}[act]
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+@pytest.mark.parametrize("xdt,ydt", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
+                                     (torch.bfloat16, torch.bfloat16)])
+@pytest.mark.parametrize("B,H,W,Cout,stride,act", [(2, 64, 96, 32, 2, 2), (1, 33, 47, 32, 2, 2), (1, 32, 48, 64, 1, 1),
+                                                   (1, 17, 19, 16, 1, 0)])
+def test_conv3x3_smallcin(xdt, ydt, B, H, W, Cout, stride, act):
+    x = _rand(B, 3, H, W, seed=1).to(xdt)
+    w = _rand(Cout, 3, 3, 3, seed=2, scale=0.3)
+    b = _rand(Cout, seed=3, scale=0.1)
+    ref = _act(F.conv2d(x.double(), w.double(), b.double(), stride, 1), act)
+    got = ops.conv3x3_smallcin(x, w.permute(2, 3, 1, 0).contiguous(), b, stride, act, ydt)
+    assert got.shape == (B, ref.shape[2], ref.shape[3], Cout)
+    assert _err(_nchw(got), ref) < TOL[ydt]
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,H,W,C,stride", [(2, 128, 256, 32, 1), (2, 128, 256, 96, 2), (1, 64, 128, 144, 1),
+                                            (2, 16, 32, 576, 2), (3, 8, 16, 960, 1), (1, 7, 9, 24, 1), (1, 9, 7, 8, 2),
+                                            (1, 1, 1, 16, 1), (1, 23, 40, 192, 2)])
+def test_dwconv3x3(dt, B, H, W, C, stride):
+    x = _rand(B, C, H, W, seed=4).to(dt)
+    w = _rand(C, 1, 3, 3, seed=5, scale=0.4)
+    b = _rand(C, seed=6, scale=0.1)
+    ref = torch.clamp(F.conv2d(x.double(), w.double(), b.double(), stride, 1, 1, C), 0, 6)
+    got = ops.dwconv3x3(_nhwc(x), w.reshape(C, 9).t().contiguous(), b, stride, 2)
+    assert _err(_nchw(got), ref) < TOL[dt]
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,H,W,Cin,Cout,taps,act,res", [
+    (2, 16, 32, 64, 64, 1, 2, False), (1, 8, 16, 320, 1280, 1, 2, False), (2, 16, 32, 384, 64, 1, 0, True),
+    (1, 13, 9, 24, 144, 1, 2, False), (1, 16, 32, 64, 64, 9, 1, False), (1, 5, 7, 152, 64, 9, 1, False),
+    (1, 8, 8, 16, 12, 1, 0, False)])
+def test_conv_simt(dt, B, H, W, Cin, Cout, taps, act, res):
+    k = 3 if taps == 9 else 1
+    x = _rand(B, Cin, H, W, seed=7).to(dt)
+    w = _rand(Cout, Cin, k, k, seed=8, scale=(2.0 / (Cin * taps)) ** 0.5)
+    b = _rand(Cout, seed=9, scale=0.1)
+    r = _rand(B, Cout, H, W, seed=10).to(dt) if res else None
+    ref = _act(F.conv2d(x.double(), w.double(), b.double(), 1, k // 2), act)
+    if res:
+        ref = ref + r.double()
+    got = ops.conv_simt(_nhwc(x), w.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous(), b, taps, act,
+                        _nhwc(r) if res else None)
+    assert _err(_nchw(got), ref) < TOL[dt]
+
+
+# (B,H,W,Cin,Cout,taps,act,res): the real MobileNetV2UNet layers at a small batch + ragged cases
+TC_CASES = [
+    (1, 8, 16, 64, 64, 1, 0, False),        # one M tile, one K chunk, N=64: the minimal tcgen05 case
+    (2, 16, 32, 64, 128, 1, 2, False),
+    (2, 128, 256, 32, 16, 1, 0, False),     # features.1 project
+    (1, 128, 256, 16, 96, 1, 2, False),     # features.2 expand (K=16: one UMMA k-step)
+    (1, 64, 128, 96, 24, 1, 0, False),      # N=24 -> UMMA N 32, store clipped
+    (2, 64, 128, 24, 144, 1, 2, False),     # K=24: ragged k chunk
+    (2, 64, 128, 144, 24, 1, 0, True),      # residual
+    (2, 16, 32, 384, 64, 1, 0, True),
+    (2, 16, 32, 64, 384, 1, 2, False),      # 2 N tiles of 192
+    (2, 8, 16, 160, 960, 1, 2, False),      # 5 N tiles of 192
+    (2, 8, 16, 960, 320, 1, 0, False),      # 15 K chunks, N tiles 192+128(clipped)
+    (2, 8, 16, 320, 1280, 1, 2, False),     # features.18
+    (1, 128, 256, 32, 16, 1, 1, False),     # outc.0
+    (1, 128, 256, 16, 16, 1, 0, False),     # outc.3 (padded to 16)
+    (1, 7, 9, 40, 72, 1, 2, True),          # ragged M (63 pixels), ragged K and N
+    (2, 16, 32, 64, 64, 9, 1, False),       # 3x3, tile = 4 rows x 32
+    (2, 16, 32, 1344, 256, 9, 1, False),    # up1.conv.0
+    (1, 32, 64, 288, 128, 9, 1, False),     # up2.conv.0 (ragged K chunk)
+    (1, 64, 128, 152, 64, 9, 1, False),     # up3.conv.0
+    (1, 128, 256, 80, 32, 9, 1, False),     # up4.conv.0 (tile = half a row)
+    (1, 128, 256, 32, 32, 9, 1, False),
+    (1, 23, 40, 64, 64, 9, 1, False),       # 736x1280 / 32: tile 3 x 40 = 120 rows
+    (2, 5, 7, 24, 40, 9, 0, True),          # tiny ragged everything
+    (1, 46, 80, 64, 32, 9, 1, False),
+]
+
+
+@pytest.mark.parametrize("flags", [0, 1], ids=["tma_store", "direct_store"])
+@pytest.mark.parametrize("B,H,W,Cin,Cout,taps,act,res", TC_CASES)
+def test_conv_tc(flags, B, H, W, Cin, Cout, taps, act, res):
+    k = 3 if taps == 9 else 1
+    x = _rand(B, Cin, H, W, seed=11).bfloat16()
+    w = _rand(Cout, Cin, k, k, seed=12, scale=(2.0 / (Cin * taps)) ** 0.5).bfloat16()
+    b = _rand(Cout, seed=13, scale=0.1)
+    r = _rand(B, Cout, H, W, seed=14).bfloat16() if res else None
+    ref = _act(F.conv2d(x.double(), w.double(), b.double(), 1, k // 2), act)
+    if res:
+        ref = ref + r.double()
+    got = ops.conv_tc(_nhwc(x), w.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous(), b, taps, act,
+                      _nhwc(r) if res else None, flags=flags)
+    torch.cuda.synchronize()
+    e = _err(_nchw(got), ref)
+    if e >= TOL[torch.bfloat16]:
+        d = (_nchw(got).double() - ref).abs()
+        bad = (d > TOL[torch.bfloat16] * ref.abs().max()).nonzero()
+        raise AssertionError(f"conv_tc err {e:.3e}; {bad.shape[0]} bad of {d.numel()}; first bad (b,c,h,w) {bad[:5].tolist()} "
+                             f"last {bad[-3:].tolist()}; got {_nchw(got)[tuple(bad[0])].item()} ref {ref[tuple(bad[0])].item()}")
+
+
+def test_conv_tc_rejects_bad_arguments():
+    x = torch.zeros(1, 4, 4, 12, device=DEV, dtype=torch.bfloat16)
+    w = torch.zeros(16, 12, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="multiple of 8"):
+        ops.conv_tc(x, w, None, 1, 0)
+    with pytest.raises(TypeError):
+        ops.conv_tc(x.float(), w, None, 1, 0)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,h,w,Cs,Cu", [(2, 8, 16, 64, 1280), (1, 16, 32, 32, 256), (1, 32, 64, 24, 128),
+                                         (2, 64, 128, 16, 64), (1, 3, 5, 8, 16), (1, 1, 1, 8, 8)])
+def test_upsample2x_concat(dt, B, h, w, Cs, Cu):
+    x = _rand(B, Cu, h, w, seed=15).to(dt)
+    skip = _rand(B, Cs, 2 * h, 2 * w, seed=16).to(dt)
+    ref = torch.cat([skip.double(), F.interpolate(x.double(), scale_factor=2, mode="bilinear", align_corners=False)], 1)
+    got = ops.upsample2x_concat(_nhwc(skip), _nhwc(x))
+    assert _err(_nchw(got), ref) < TOL[dt]
+    assert torch.equal(_nchw(got)[:, :Cs], skip)                 # the skip half is a bit-exact copy
+
+
+@pytest.mark.parametrize("dt,odt", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16),
+                                    (torch.bfloat16, torch.float32)])
+@pytest.mark.parametrize("B,h,w,C", [(2, 128, 256, 10), (1, 16, 24, 10), (1, 5, 7, 3), (1, 1, 2, 16)])
+def test_final_upsample_align_corners(dt, odt, B, h, w, C):
+    lg = torch.zeros(B, h, w, 16, device=DEV, dtype=dt)
+    lg[..., :C] = _nhwc(_rand(B, C, h, w, seed=17)).to(dt)
+    lg[..., C:] = 1e9 if C < 16 else 0      # padding channels must never leak into the output
+    ref = F.interpolate(_nchw(lg[..., :C].contiguous()).double(), scale_factor=2, mode="bilinear", align_corners=True)
+    got = ops.upsample2x_ac_nchw(lg, C, odt)
+    assert got.shape == (B, C, 2 * h, 2 * w) and got.dtype == odt
+    assert _err(got, ref) < TOL[odt]
+    if 2 * w % 4 == 0:
+        mask = ops.upsample2x_ac_argmax(lg, C)
+        ref32 = F.interpolate(_nchw(lg[..., :C].contiguous()).float(), scale_factor=2, mode="bilinear", align_corners=True)
+        agree = (mask.long() == ref32.argmax(1)).float().mean().item()
+        assert agree > 0.999, agree
+
+
+def test_maxpool_and_nhwc_to_nchw():
+    for dt in (torch.float32, torch.bfloat16):
+        x = _rand(2, 64, 12, 20, seed=18).to(dt)
+        got = ops.maxpool2x2(_nhwc(x))
+        assert torch.equal(_nchw(got), F.max_pool2d(x, 2))
+        y = ops.nhwc_to_nchw(_nhwc(x), 10, torch.float32)
+        assert torch.equal(y, x[:, :10].float())
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 10, 64, 128), (1, 10, 7, 9), (3, 19, 8, 8), (1, 1, 4, 4)])
+def test_softmax_ce_fused_forward_and_gradient(B, C, H, W):
+    lg = _rand(B, C, H, W, seed=19, scale=3.0).requires_grad_(True)
+    tg = torch.randint(0, C, (B, H, W), generator=torch.Generator().manual_seed(20)).to(DEV)
+    ref = F.cross_entropy(lg.double(), tg)
+    (gref,) = torch.autograd.grad(ref, lg)
+    loss, dl = ops.softmax_ce(lg.detach(), tg)
+    assert abs(loss.item() - ref.item()) < 2e-6 * max(1.0, abs(ref.item()))
+    assert _err(dl, gref) < 1e-5
+    # module form used at the train.py:37-38 call site
+    import b200seg
+    l2 = b200seg.CrossEntropyLoss()(lg, tg)
+    l2.backward()
+    assert _err(lg.grad, gref) < 1e-5
