@@ -84,7 +84,7 @@ def main():
 
     # ---------------- MobileNetV2UNet eval ----------------
     sd = O.synth_state_dict(O.mbv2unet_param_shapes(10), seed=0)
-    sd = O.calibrate_bn(sd, O.synth_input(4, 64, 96, seed=7))      # fixture F1; stats frozen below
+    sd = O.calibrate_bn(sd, O.synth_input(8, 256, 256, seed=7))    # fixture F1; stats frozen below
     bn_keys = O.bn_stat_keys(sd)
     np.savez_compressed(os.path.join(GOLD, "mbv2unet_bnstats.npz"),
                         **{k: sd[k].numpy() for k in bn_keys})
