@@ -74,6 +74,123 @@ conv3x3_smallcin_kernel(const TI* __restrict__ x, const float* __restrict__ w, c
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// conv3x3 Cin=3 on the tensor cores (bf16 output path).  K = 27 (padded to 32) is far too small for
+// a TMA/tcgen05 pipeline and the NCHW planar, stride-2 input cannot be described by one TMA box, so
+// the im2col fragment is gathered straight into registers and multiplied with warp-level
+// mma.sync.m16n8k16 (bf16 x bf16 -> f32): a warp owns 16 consecutive output pixels x all Cout.
+// Per pixel this needs ~1 load instruction + 0.5 MMA instead of 27 loads + 27 FMAs per 8 channels,
+// which is what moves the kernel from issue-bound to HBM-bound.  k = c*9 + kh*3 + kw.
+// The C fragments are transposed through a per-warp shared-memory patch so that every thread
+// stores whole 16-byte NHWC channel vectors (1 KB contiguous per warp).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <typename TI, int NT>   // NT = Cout / 8
+__global__ void __launch_bounds__(256)
+conv3x3_c3_mma_kernel(const TI* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                      __nv_bfloat16* __restrict__ y, int B, int H, int W, int Ho, int Wo, int stride, int act) {
+  constexpr int Cout = NT * 8;
+  __shared__ __align__(16) __nv_bfloat16 patch[8][16][Cout + 8];   // +8: conflict-free fragment writes
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+
+  // B fragments for both k-steps and all n-tiles: b0 = W[k=2t,2t+1][n=g], b1 = W[k=2t+8,2t+9][n=g]
+  uint32_t bf[2][NT][2];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int k = ks * 16 + h * 8 + 2 * t + e;          // k = c*9 + kh*3 + kw
+          const int c = k / 9, r9 = k - c * 9;
+          v[e] = (k < 27) ? __ldg(w + (r9 * 3 + c) * Cout + j * 8 + g) : 0.f;   // w is [kh][kw][c][Cout]
+        }
+        bf[ks][j][h] = pack_bf16x2(v[0], v[1]);
+      }
+  // this thread's 8 gather offsets (same for every pixel): k -> (c, kh, kw)
+  int kc[2][2][2], kh_[2][2][2], kw_[2][2][2];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int k = ks * 16 + h * 8 + 2 * t + e;
+        const int c = k / 9, r9 = k - c * 9;
+        kc[ks][h][e] = (k < 27) ? c : -1;
+        kh_[ks][h][e] = r9 / 3; kw_[ks][h][e] = r9 % 3;
+      }
+  float bias_v[NT][2];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    bias_v[j][0] = bias ? __ldg(bias + j * 8 + 2 * t) : 0.f;
+    bias_v[j][1] = bias ? __ldg(bias + j * 8 + 2 * t + 1) : 0.f;
+  }
+
+  const int groups_w = (Wo + 15) / 16;
+  const long long total = (long long)B * Ho * groups_w;
+  const long long HW = (long long)H * W;
+  for (long long grp = (long long)blockIdx.x * 8 + warp; grp < total; grp += (long long)gridDim.x * 8) {
+    const int gw = (int)(grp % groups_w);
+    long long p = grp / groups_w;
+    const int ho = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    const TI* xb = x + (long long)b * 3 * HW;
+    uint32_t afr[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int h = 0; h < 2; ++h)       // h: k half (cols 2t.. / 2t+8..)
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {  // rr: row g / row g+8
+          const int wo = gw * 16 + g + rr * 8;
+          float v[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int hi = ho * stride - 1 + kh_[ks][h][e], wi = wo * stride - 1 + kw_[ks][h][e];
+            const bool ok = kc[ks][h][e] >= 0 && wo < Wo && hi >= 0 && hi < H && wi >= 0 && wi < W;
+            v[e] = ok ? to_f32<TI>(xb[(long long)kc[ks][h][e] * HW + (long long)hi * W + wi]) : 0.f;
+          }
+          afr[ks][h * 2 + rr] = pack_bf16x2(v[0], v[1]);   // a0:(g,lo) a1:(g+8,lo) a2:(g,hi) a3:(g+8,hi)
+        }
+    float acc[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      acc[j][0] = bias_v[j][0]; acc[j][1] = bias_v[j][1]; acc[j][2] = bias_v[j][0]; acc[j][3] = bias_v[j][1];
+    }
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int j = 0; j < NT; ++j) mma_bf16_16816(acc[j], afr[ks], bf[ks][j][0], bf[ks][j][1]);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      *reinterpret_cast<uint32_t*>(&patch[warp][g][j * 8 + 2 * t]) =
+          pack_bf16x2(apply_act_rt(acc[j][0], act), apply_act_rt(acc[j][1], act));
+      *reinterpret_cast<uint32_t*>(&patch[warp][g + 8][j * 8 + 2 * t]) =
+          pack_bf16x2(apply_act_rt(acc[j][2], act), apply_act_rt(acc[j][3], act));
+    }
+    __syncwarp();
+    __nv_bfloat16* yrow = y + (((long long)b * Ho + ho) * Wo + gw * 16) * Cout;
+    for (int i = lane; i < 16 * NT; i += 32) {
+      const int px = i / NT, cv = i - px * NT;
+      if (gw * 16 + px < Wo)
+        *reinterpret_cast<uint4*>(yrow + px * Cout + cv * 8) = *reinterpret_cast<const uint4*>(&patch[warp][px][cv * 8]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // depthwise 3x3, NHWC.  One thread = TW consecutive output pixels along W x one 16-byte channel
 // vector; the 3 x (TW-1)*S+3 input window is walked row by row so each input vector is loaded
@@ -202,10 +319,35 @@ upsample2x_concat_kernel(const T* __restrict__ skip, const T* __restrict__ x, T*
 // One thread = PPT consecutive output pixels along W; stores are contiguous along W per plane.
 // src = dst * (in-1)/(out-1)  (PyTorch area_pixel_compute_scale with align_corners)
 // ------------------------------------------------------------------------------------------
+// 16 channels of one NHWC pixel as floats (ldc == 16: 32 B bf16 / 64 B f32, 16-byte vector loads)
+template <typename T>
+__device__ __forceinline__ void load_px16(const T* p, float (&v)[16]);
+template <>
+__device__ __forceinline__ void load_px16<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[16]) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(p)), b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+  v[0] = bf16lo(a.x); v[1] = bf16hi(a.x); v[2] = bf16lo(a.y); v[3] = bf16hi(a.y);
+  v[4] = bf16lo(a.z); v[5] = bf16hi(a.z); v[6] = bf16lo(a.w); v[7] = bf16hi(a.w);
+  v[8] = bf16lo(b.x); v[9] = bf16hi(b.x); v[10] = bf16lo(b.y); v[11] = bf16hi(b.y);
+  v[12] = bf16lo(b.z); v[13] = bf16hi(b.z); v[14] = bf16lo(b.w); v[15] = bf16hi(b.w);
+}
+template <>
+__device__ __forceinline__ void load_px16<float>(const float* p, float (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p) + i);
+    v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
+  }
+}
+
+// One thread = PPT consecutive output pixels along W of one output row.  The two source rows are
+// fixed per thread, so each source column is first blended vertically (hy*row0 + ly*row1) when it is
+// loaded; consecutive outputs advance the source column by < 0.5, so the thread walks its source
+// columns with a two-column register window and loads every logits pixel once, with 16-byte loads.
+// Stores are contiguous along W per class plane (8/16-byte vectors).
 template <typename T, typename TO, int PPT, int CMAX, bool ARGMAX>
 __global__ void __launch_bounds__(256)
-upsample2x_ac_kernel(const T* __restrict__ lg, int ldc, TO* __restrict__ out, uint8_t* __restrict__ mask, int B,
-                     int h, int w, int C) {
+upsample2x_ac_kernel(const T* __restrict__ lg, TO* __restrict__ out, uint8_t* __restrict__ mask, int B, int h, int w,
+                     int C) {
   const int Ho = 2 * h, Wo = 2 * w;
   const int wq = Wo / PPT;
   const long long total = (long long)B * Ho * wq;
@@ -221,28 +363,35 @@ upsample2x_ac_kernel(const T* __restrict__ lg, int ldc, TO* __restrict__ out, ui
   const int y0 = (int)sy;
   const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
   const float ly = sy - y0, hy = 1.f - ly;
-  const T* base = lg + (long long)b * h * w * ldc;
+  const T* r0 = lg + ((long long)b * h + y0) * w * 16;
+  const T* r1 = lg + ((long long)b * h + y1) * w * 16;
+
+  auto load_col = [&](int xcol, float (&dst)[CMAX]) {
+    float a[16], c[16];
+    load_px16<T>(r0 + (long long)xcol * 16, a);
+    load_px16<T>(r1 + (long long)xcol * 16, c);
+#pragma unroll
+    for (int i = 0; i < CMAX; ++i) dst[i] = hy * a[i] + ly * c[i];
+  };
+  int xc = (int)(scw * (q * PPT));
+  float lft[CMAX], rgt[CMAX];
+  load_col(xc, lft);
+  load_col(xc + (xc < w - 1 ? 1 : 0), rgt);
   float res[PPT][CMAX];
 #pragma unroll
   for (int t = 0; t < PPT; ++t) {
     const int wo = q * PPT + t;
     const float sx = scw * wo;
     const int x0 = (int)sx;
-    const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
-    const float lx = sx - x0, hx = 1.f - lx;
-    const T* p00 = base + ((long long)y0 * w + x0) * ldc;
-    const T* p01 = base + ((long long)y0 * w + x1) * ldc;
-    const T* p10 = base + ((long long)y1 * w + x0) * ldc;
-    const T* p11 = base + ((long long)y1 * w + x1) * ldc;
+    if (x0 != xc) {   // advance the window by one column
+      xc = x0;
 #pragma unroll
-    for (int c = 0; c < CMAX; ++c) {
-      if (c < C) {
-        res[t][c] = hy * (hx * to_f32<T>(p00[c]) + lx * to_f32<T>(p01[c])) +
-                    ly * (hx * to_f32<T>(p10[c]) + lx * to_f32<T>(p11[c]));
-      } else {
-        res[t][c] = -INFINITY;
-      }
+      for (int i = 0; i < CMAX; ++i) lft[i] = rgt[i];
+      load_col(xc + (xc < w - 1 ? 1 : 0), rgt);
     }
+    const float lx = sx - x0, hx = 1.f - lx;
+#pragma unroll
+    for (int i = 0; i < CMAX; ++i) res[t][i] = hx * lft[i] + lx * rgt[i];
   }
   if (ARGMAX) {
     uint32_t packed = 0;
@@ -252,7 +401,7 @@ upsample2x_ac_kernel(const T* __restrict__ lg, int ldc, TO* __restrict__ out, ui
       float bv = res[t][0];
 #pragma unroll
       for (int c = 1; c < CMAX; ++c)
-        if (res[t][c] > bv) { bv = res[t][c]; best = c; }   // first max wins, like torch.max
+        if (c < C && res[t][c] > bv) { bv = res[t][c]; best = c; }   // first max wins, like torch.max
       packed |= (uint32_t)best << (8 * t);
     }
     static_assert(!ARGMAX || PPT == 4, "argmax variant packs 4 pixels per 32-bit store");
@@ -262,8 +411,16 @@ upsample2x_ac_kernel(const T* __restrict__ lg, int ldc, TO* __restrict__ out, ui
     for (int c = 0; c < CMAX; ++c) {
       if (c < C) {
         TO* op = out + (((long long)b * C + c) * Ho + ho) * Wo + q * PPT;
+        if (sizeof(TO) == 2 && PPT == 4) {
+          uint2 v;
+          v.x = pack_bf16x2(res[0][c], res[1][c]); v.y = pack_bf16x2(res[2][c], res[3][c]);
+          *reinterpret_cast<uint2*>(op) = v;
+        } else if (sizeof(TO) == 4 && PPT == 4) {
+          *reinterpret_cast<float4*>(op) = make_float4(res[0][c], res[1][c], res[2][c], res[3][c]);
+        } else {
 #pragma unroll
-        for (int t = 0; t < PPT; ++t) op[t] = from_f32<TO>(res[t][c]);
+          for (int t = 0; t < PPT; ++t) op[t] = from_f32<TO>(res[t][c]);
+        }
       }
     }
   }
@@ -325,6 +482,19 @@ int b200seg_conv3x3_smallcin(const void* x, int x_dtype, const float* w, const f
   if (g > cap) g = cap;   // grid-stride: amortise the weight staging
   const size_t smem = (size_t)(9 * Cin * Cout + Cout) * sizeof(float);
   cudaStream_t st = (cudaStream_t)s;
+  if (y_dtype == B200SEG_BF16 && Cin == 3 && (Cout == 32 || Cout == 64 || Cout == 16)) {
+    // tensor-core path (bf16 storage): one warp = 16 output pixels x all Cout
+    const long long groups = (long long)B * Ho * ((Wo + 15) / 16);
+    long long gb = (groups + 7) / 8;
+    const long long capb = (long long)sm_count() * 16;
+    if (gb > capb) gb = capb;
+#define LAUNCH_MMA(TI, NT) conv3x3_c3_mma_kernel<TI, NT><<<(int)gb, 256, 0, st>>>((const TI*)x, w, b, (bf16*)y, B, H, W, Ho, Wo, stride, act)
+    if (x_dtype == B200SEG_F32) { if (Cout == 32) LAUNCH_MMA(float, 4); else if (Cout == 64) LAUNCH_MMA(float, 8); else LAUNCH_MMA(float, 2); }
+    else if (x_dtype == B200SEG_BF16) { if (Cout == 32) LAUNCH_MMA(bf16, 4); else if (Cout == 64) LAUNCH_MMA(bf16, 8); else LAUNCH_MMA(bf16, 2); }
+    else return set_error(-1, "conv3x3_smallcin: bad x dtype %d", x_dtype);
+#undef LAUNCH_MMA
+    return check_launch("conv3x3_c3_mma");
+  }
 #define LAUNCH(TI, TO)                                                                                      \
   conv3x3_smallcin_kernel<TI, TO><<<(int)g, threads, smem, st>>>((const TI*)x, w, b, (TO*)y, B, Cin, H, W, \
                                                                  Cout, Ho, Wo, stride, act)
@@ -379,16 +549,22 @@ int b200seg_upsample2x_concat(const void* skip, const void* x, void* y, int dtyp
 
 int b200seg_upsample2x_ac_nchw(const void* logits, int dtype, int ldc, void* out, int out_dtype, int B, int h,
                                int w, int C, b200seg_stream_t s) {
-  B200_REQUIRE(C >= 1 && C <= 16 && ldc >= C, "upsample2x_ac_nchw: C=%d (<=16) ldc=%d", C, ldc);
+  B200_REQUIRE(C >= 1 && C <= 16 && ldc == 16, "upsample2x_ac_nchw: C=%d (<=16), ldc=%d (must be 16)", C, ldc);
   B200_REQUIRE(B > 0 && h > 0 && w > 0, "upsample2x_ac_nchw: empty tensor");
   cudaStream_t st = (cudaStream_t)s;
-  const long long total = (long long)B * 2 * h * (2 * w / 2);
+  const bool v4 = (2 * w) % 4 == 0;
+  const long long total = (long long)B * 2 * h * (2 * w / (v4 ? 4 : 2));
   const int g = grid_for(total, 256);
-#define LAUNCH(T, TO) upsample2x_ac_kernel<T, TO, 2, 16, false><<<g, 256, 0, st>>>((const T*)logits, ldc, (TO*)out, nullptr, B, h, w, C)
-  if (dtype == B200SEG_BF16 && out_dtype == B200SEG_BF16) LAUNCH(bf16, bf16);
-  else if (dtype == B200SEG_BF16 && out_dtype == B200SEG_F32) LAUNCH(bf16, float);
-  else if (dtype == B200SEG_F32 && out_dtype == B200SEG_F32) LAUNCH(float, float);
-  else if (dtype == B200SEG_F32 && out_dtype == B200SEG_BF16) LAUNCH(float, bf16);
+#define LAUNCH(T, TO)                                                                                               \
+  {                                                                                                                 \
+    if (v4 && C <= 12) upsample2x_ac_kernel<T, TO, 4, 12, false><<<g, 256, 0, st>>>((const T*)logits, (TO*)out, nullptr, B, h, w, C); \
+    else if (v4) upsample2x_ac_kernel<T, TO, 4, 16, false><<<g, 256, 0, st>>>((const T*)logits, (TO*)out, nullptr, B, h, w, C);       \
+    else upsample2x_ac_kernel<T, TO, 2, 16, false><<<g, 256, 0, st>>>((const T*)logits, (TO*)out, nullptr, B, h, w, C);               \
+  }
+  if (dtype == B200SEG_BF16 && out_dtype == B200SEG_BF16) LAUNCH(bf16, bf16)
+  else if (dtype == B200SEG_BF16 && out_dtype == B200SEG_F32) LAUNCH(bf16, float)
+  else if (dtype == B200SEG_F32 && out_dtype == B200SEG_F32) LAUNCH(float, float)
+  else if (dtype == B200SEG_F32 && out_dtype == B200SEG_BF16) LAUNCH(float, bf16)
   else return set_error(-1, "upsample2x_ac_nchw: bad dtypes");
 #undef LAUNCH
   return check_launch("upsample2x_ac_nchw");
@@ -396,15 +572,17 @@ int b200seg_upsample2x_ac_nchw(const void* logits, int dtype, int ldc, void* out
 
 int b200seg_upsample2x_ac_argmax(const void* logits, int dtype, int ldc, uint8_t* mask, int B, int h, int w, int C,
                                  b200seg_stream_t s) {
-  B200_REQUIRE(C >= 1 && C <= 16 && ldc >= C, "upsample2x_ac_argmax: C=%d (<=16) ldc=%d", C, ldc);
+  B200_REQUIRE(C >= 1 && C <= 16 && ldc == 16, "upsample2x_ac_argmax: C=%d (<=16), ldc=%d (must be 16)", C, ldc);
   B200_REQUIRE(B > 0 && h > 0 && w > 0 && (2 * w) % 4 == 0, "upsample2x_ac_argmax: bad shape");
   cudaStream_t st = (cudaStream_t)s;
   const long long total = (long long)B * 2 * h * (2 * w / 4);
   const int g = grid_for(total, 256);
-  if (dtype == B200SEG_BF16)
-    upsample2x_ac_kernel<bf16, float, 4, 16, true><<<g, 256, 0, st>>>((const bf16*)logits, ldc, nullptr, mask, B, h, w, C);
+  if (dtype == B200SEG_BF16 && C <= 12)
+    upsample2x_ac_kernel<bf16, float, 4, 12, true><<<g, 256, 0, st>>>((const bf16*)logits, nullptr, mask, B, h, w, C);
+  else if (dtype == B200SEG_BF16)
+    upsample2x_ac_kernel<bf16, float, 4, 16, true><<<g, 256, 0, st>>>((const bf16*)logits, nullptr, mask, B, h, w, C);
   else if (dtype == B200SEG_F32)
-    upsample2x_ac_kernel<float, float, 4, 16, true><<<g, 256, 0, st>>>((const float*)logits, ldc, nullptr, mask, B, h, w, C);
+    upsample2x_ac_kernel<float, float, 4, 16, true><<<g, 256, 0, st>>>((const float*)logits, nullptr, mask, B, h, w, C);
   else return set_error(-1, "upsample2x_ac_argmax: bad dtype");
   return check_launch("upsample2x_ac_argmax");
 }

@@ -10,12 +10,13 @@ import torch.nn.functional as F
 from b200seg import ops
 
 DEV = "cuda"
-flags = 1 if (len(sys.argv) > 1 and sys.argv[1] == "direct") else 0
+flags = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 CASES = [  # B,H,W,Cin,Cout,taps,act,res
     (1, 8, 16, 64, 64, 1, 0, 0), (1, 8, 16, 64, 16, 1, 0, 0), (1, 8, 16, 16, 64, 1, 0, 0), (1, 8, 16, 128, 64, 1, 0, 0),
     (1, 8, 16, 512, 64, 1, 0, 0), (1, 8, 16, 64, 256, 1, 0, 0), (2, 16, 32, 64, 64, 1, 2, 1), (1, 8, 16, 64, 384, 1, 0, 0),
     (1, 7, 9, 40, 72, 1, 2, 1), (1, 8, 16, 64, 64, 9, 0, 0), (2, 16, 32, 64, 64, 9, 1, 0), (1, 23, 40, 64, 64, 9, 1, 0),
-    (2, 16, 32, 1344, 256, 9, 1, 0), (1, 128, 256, 80, 32, 9, 1, 0),
+    (2, 16, 32, 1344, 256, 9, 1, 0), (1, 128, 256, 80, 32, 9, 1, 0), (2, 64, 128, 152, 64, 9, 1, 0), (1, 33, 100, 32, 32, 9, 1, 0),
+    (3, 64, 128, 64, 64, 9, 1, 0), (2, 128, 256, 32, 32, 9, 1, 0), (4, 64, 128, 16, 96, 1, 2, 0), (4, 64, 128, 144, 24, 1, 0, 1),
 ]
 for (B, H, W, Cin, Cout, taps, act, res) in CASES:
     k = 3 if taps == 9 else 1
