@@ -65,6 +65,16 @@ int b200seg_dwconv3x3(const void* x, const float* w, const float* b, void* y, in
 int b200seg_conv_tc(const void* x, const void* w, const float* b, const void* res, void* y, int B, int H,
                     int W, int Cin, int Cout, int taps, int act, int flags, b200seg_stream_t s);
 
+/* Depthwise 3x3 on the tensor cores (bf16): the same TMA/tcgen05 pipeline as b200seg_conv_tc run over
+ * 64-channel chunks with BLOCK-DIAGONAL weights, so the 9-tap stencil costs no CUDA-core FMAs or
+ * bf16<->f32 conversions and the kernel is bounded by HBM instead of instruction issue
+ * (mobilenetv2.py:42-51; pad 1, stride 1|2 -- stride 2 uses TMA element strides).
+ *   x     : NHWC bf16 [B,H,W,C], C % 8 == 0
+ *   wdiag : bf16 [C][9][64], wdiag[c][t][k] = w[c][t] * bn_scale[c] if k == c % 64 else 0
+ *   b     : f32 [C] or NULL;   y : NHWC bf16 [B,Ho,Wo,C] */
+int b200seg_dwconv3x3_tc(const void* x, const void* wdiag, const float* b, void* y, int B, int H, int W,
+                         int C, int stride, int act, int flags, b200seg_stream_t s);
+
 /* Same contract on the FP32 SIMT pipes (no tensor cores) for the fp32 parity configuration
  * (BASELINE config 1: 1e-4 relative needs true fp32 products, SURVEY finding 10c).  dtype selects
  * the storage type of x/res/y; w is f32 [Cout][taps][Cin]. */

@@ -61,6 +61,31 @@ def dwconv3x3(x, w9c, b, stride: int, act: int, out=None):
     return out
 
 
+def pack_dw_diag(w9c: torch.Tensor) -> torch.Tensor:
+    """f32 [9, C] depthwise taps -> block-diagonal bf16 [C, 9, 64] for dwconv3x3_tc."""
+    C = w9c.shape[1]
+    out = torch.zeros(C, 9, 64, device=w9c.device, dtype=torch.bfloat16)
+    idx = torch.arange(C, device=w9c.device)
+    out[idx, :, idx % 64] = w9c.t().to(torch.bfloat16)
+    return out.contiguous()
+
+
+def dwconv3x3_tc(x, wdiag, b, stride: int, act: int, out=None, flags: int = 0):
+    """Depthwise 3x3 on the tensor cores. x NHWC bf16; wdiag from pack_dw_diag."""
+    _cuda(x, wdiag, b)
+    if x.dtype != torch.bfloat16 or wdiag.dtype != torch.bfloat16:
+        raise TypeError("dwconv3x3_tc is bf16-only")
+    B, H, W, Cc = x.shape
+    if tuple(wdiag.shape) != (Cc, 9, 64):
+        raise ValueError(f"dwconv3x3_tc: wdiag {tuple(wdiag.shape)} != ({Cc}, 9, 64)")
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    if out is None:
+        out = torch.empty((B, Ho, Wo, Cc), device=x.device, dtype=torch.bfloat16)
+    check(lib.b200seg_dwconv3x3_tc(ptr(x), ptr(wdiag), ptr(b), ptr(out), B, H, W, Cc, stride, act, flags, _stream()),
+          "dwconv3x3_tc")
+    return out
+
+
 def conv_tc(x, w, b, taps: int, act: int, res=None, out=None, flags: int = 0):
     """Tensor-core conv. x NHWC bf16 [B,H,W,Cin]; w bf16 [Cout, taps*Cin]; b f32 [Cout]."""
     _cuda(x, w, b, res)

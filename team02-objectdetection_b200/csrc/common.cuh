@@ -25,7 +25,8 @@ int sm_count();
 // TMA descriptor factory (cuTensorMapEncodeTiled resolved through the runtime, no -lcuda)
 // dims/strides innermost first; strides[i] is the byte stride of dim i+1.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                   const uint64_t* strides_bytes, const uint32_t* box, int swizzle128);
+                   const uint64_t* strides_bytes, const uint32_t* box, int swizzle128,
+                   const uint32_t* elem_strides = nullptr);   // box[i] is the TRAVERSED extent: loads ceil(box/es)
 
 // ------------------------------------------------------------------------------------------
 // device helpers
@@ -79,6 +80,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
       __trap();
     }
   }
+}
+
+// one lane of the (converged) warp; ptxas keeps the guarded code in the uniform datapath
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // ---- proxies / fences ----
@@ -138,6 +150,18 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// same, descriptors passed as 32-bit halves (the high word is a per-kernel constant)
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // mbarrier arrives once every previously issued tcgen05.mma of this thread has completed

@@ -5,8 +5,7 @@
 // Persistent, warp-specialised kernel: one CTA per SM slot loops over output tiles; three
 // pipelines run concurrently
 //     TMA producer --(smem ring: full/empty)--> MMA issuer --(TMEM x2: acc_full/acc_empty)--> epilogue
-//     epilogue --(staging smem x2)--> TMA store (bulk async group, drained one tile later)
-// so the loads of tile i+1, the MMAs of tile i and the stores of tile i-1 overlap.
+// so the loads of tile i+1, the MMAs of tile i and the epilogue/stores of tile i-1 overlap.
 //
 // A operand (activations, NHWC bf16) -- two addressing modes, both pure TMA:
 //   TAP   : a 4-D tiled tensor map (C, W, H, B), box {64, BW, BH, 1}; each 3x3 tap is the same box
@@ -20,8 +19,11 @@
 // B operand (weights bf16 [Cout][taps][Cin]): 3-D map, box {64,1,N}; when all taps/chunks of the N
 // tile fit in shared memory they are loaded once per CTA ("resident") instead of once per tile.
 //
-// Epilogue: TMEM -> registers (tcgen05.ld 32x32b.x16) -> +bias -> ReLU/ReLU6 -> +residual -> bf16 ->
-// 128B-swizzled staging tile -> TMA store (clips the image border and the Cout tail).
+// Epilogue: TMEM -> registers (tcgen05.ld 32x32b.x16, double-buffered) -> +bias -> ReLU/ReLU6 -> +residual
+// -> bf16 -> one 256-bit global store per 16 channels (thread = pixel, so each store is a full 32-byte
+// sector of that pixel's NHWC row).  An alternative epilogue (flag bit0) goes through a 128B-swizzled
+// staging tile and a TMA store; it is slower because the store queues behind the prefetched loads in the
+// same TMA unit and the staging buffer cannot be reused until the store has drained.
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
 // warps 2..5 = epilogue (TMEM lane quadrant = warp_id % 4).
@@ -32,7 +34,7 @@ namespace b200 {
 struct ConvTcArgs {
   const float* bias;
   const void* res;   // residual, read straight from global in the epilogue (or NULL)
-  void* y;           // only for the direct-store debug epilogue
+  void* y;
   int taps, Cin, Cout;
   int W, H, B;       // geometry the tile scheduler walks (1x1: W = #pixels, H = B = 1)
   int BW, BH;        // M tile = BH rows x BW columns of pixels, BW*BH <= 128
@@ -41,12 +43,14 @@ struct ConvTcArgs {
   int k_chunks;      // ceil(Cin / 64)
   int stages;
   int act;
-  int direct_store;
+  int tma_store;     // epilogue: 0 = 256-bit stores straight from registers, 1 = smem staging + TMA store
   int tmem_cols;
   int halo;          // A addressing mode (see above)
   int b_resident;    // weights loaded once per CTA
   int n_sbuf;        // staging buffers (1 or 2)
   int halo_bo;       // HALO: put the swizzle phase of the shifted start address into descriptor.base_offset
+  int dw;            // depthwise mode: B is block-diagonal, the only K chunk of N tile j is channel chunk j
+  int stride;        // 1, or 2 (TAP mode only; the A tensor map then carries elementStrides = 2)
   int a_stage_bytes, b_stage_bytes;
   long long total_tiles;
 };
@@ -86,7 +90,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (!a.direct_store) tma_prefetch_desc(&tmC);
+    if (a.tma_store) tma_prefetch_desc(&tmC);
     for (int i = 0; i < a.stages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
@@ -116,7 +120,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int c = 0; c < a.k_chunks; ++c)
           tma_load_3d(sB + (t * a.k_chunks + c) * b_tile_bytes, &tmB, b_full, c * 64, t, 0);
     }
-    long long kb_glob = 0;
+    int s = 0;
+    uint32_t ph = 0;
+    const int n_outer = a.halo ? a.k_chunks : a.taps;      // HALO: chunks x 3 rows;  TAP: taps x chunks
+    const int n_inner = a.halo ? 3 : a.k_chunks;
+    const uint32_t tx_bytes = a.halo ? 130u * 128u + (a.b_resident ? 0u : 3u * (uint32_t)b_tile_bytes)
+                                     : (uint32_t)(rows * 128 + (a.b_resident ? 0 : b_tile_bytes));
     for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
       const int n_tile = (int)(tile % a.n_tiles);
       long long mt = tile / a.n_tiles;
@@ -124,36 +133,50 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int th = (int)(mt % a.tiles_h);
       const int bb = (int)(mt / a.tiles_h);
       const int w0 = tw * a.BW, h0 = th * a.BH, n0 = n_tile * a.block_n;
-      for (int kb = 0; kb < kb_per_tile; ++kb, ++kb_glob) {
-        const int s = (int)(kb_glob % a.stages);
-        const uint32_t ph = (uint32_t)(kb_glob / a.stages) & 1u;
-        mbar_wait(&empty[s], ph ^ 1u, 1);
-        if (lane == 0) {
-          if (a.halo) {
-            const int chunk = kb / 3, dh = kb - chunk * 3;
-            const uint32_t bytes = 130u * 128u + (a.b_resident ? 0u : 3u * (uint32_t)b_tile_bytes);
-            mbar_arrive_expect_tx(&full[s], bytes);
-            tma_load_4d(sA + s * a.a_stage_bytes, &tmA, &full[s], chunk * 64, w0 - 1, h0 + dh - 1, bb);
-            if (!a.b_resident)
-              for (int dw = 0; dw < 3; ++dw)
-                tma_load_3d(sB + s * a.b_stage_bytes + dw * b_tile_bytes, &tmB, &full[s], chunk * 64, dh * 3 + dw, n0);
-          } else {
-            const int tap = kb / a.k_chunks, chunk = kb - tap * a.k_chunks;
-            int dw = 0, dh = 0;
-            if (a.taps == 9) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
-            mbar_arrive_expect_tx(&full[s], (uint32_t)(rows * 128 + (a.b_resident ? 0 : b_tile_bytes)));
-            tma_load_4d(sA + s * a.a_stage_bytes, &tmA, &full[s], chunk * 64, w0 + dw, h0 + dh, bb);
-            if (!a.b_resident) tma_load_3d(sB + s * a.b_stage_bytes, &tmB, &full[s], chunk * 64, tap, n0);
+      for (int o = 0; o < n_outer; ++o) {
+        for (int i = 0; i < n_inner; ++i) {
+          mbar_wait(&empty[s], ph ^ 1u, 1);
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&full[s], tx_bytes);
+            if (a.halo) {
+              const int chunk = o, dh = i;
+              const int ach = a.dw ? n_tile : chunk;           // channel chunk of the activations
+              tma_load_4d(sA + s * a.a_stage_bytes, &tmA, &full[s], ach * 64, w0 - 1, h0 + dh - 1, bb);
+              if (!a.b_resident)
+                for (int dw = 0; dw < 3; ++dw)
+                  tma_load_3d(sB + s * a.b_stage_bytes + dw * b_tile_bytes, &tmB, &full[s], a.dw ? 0 : chunk * 64,
+                              dh * 3 + dw, n0);
+            } else {
+              const int tap = o, chunk = i;
+              const int ach = a.dw ? n_tile : chunk;
+              int dw = 0, dh = 0;
+              if (a.taps == 9) { dh = tap / 3 - 1; dw = tap - (dh + 1) * 3 - 1; }
+              tma_load_4d(sA + s * a.a_stage_bytes, &tmA, &full[s], ach * 64, w0 * a.stride + dw, h0 * a.stride + dh, bb);
+              if (!a.b_resident)
+                tma_load_3d(sB + s * a.b_stage_bytes, &tmB, &full[s], a.dw ? 0 : chunk * 64, tap, n0);
+            }
           }
+          __syncwarp();
+          if (++s == a.stages) { s = 0; ph ^= 1u; }
         }
-        __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
+    // One thread issues every tcgen05.mma of the CTA, so its scalar instruction count per MMA bounds the
+    // tile rate of the short-K layers: descriptors are kept as {lo,hi} 32-bit halves (hi is constant), the
+    // k loop is fully unrolled, and ring indices are carried incrementally (no div/mod).
     const uint32_t idesc = umma_idesc_bf16(128, a.block_n);
+    const uint32_t desc_hi = (uint32_t)(umma_desc_k128(0) >> 32);
+    const uint32_t a_lo0 = (uint32_t)umma_desc_k128(smem_u32(sA));      // low word for stage 0
+    const uint32_t b_lo0 = (uint32_t)umma_desc_k128(smem_u32(sB));
+    const uint32_t a_stage16 = (uint32_t)a.a_stage_bytes >> 4, b_stage16 = (uint32_t)a.b_stage_bytes >> 4;
+    const uint32_t b_tile16 = (uint32_t)b_tile_bytes >> 4;
+    const int n_outer = a.halo ? a.k_chunks : a.taps;
+    const int n_inner = a.halo ? 3 : a.k_chunks;
     if (a.b_resident) mbar_wait(b_full, 0, 5);
-    long long kb_glob = 0;
+    int s = 0;
+    uint32_t ph = 0;
     int it = 0;
     for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
       const int ab = it & 1;
@@ -161,41 +184,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&acc_empty[ab], aph ^ 1u, 6);     // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)(ab * a.block_n);
-      for (int kb = 0; kb < kb_per_tile; ++kb, ++kb_glob) {
-        const int s = (int)(kb_glob % a.stages);
-        const uint32_t ph = (uint32_t)(kb_glob / a.stages) & 1u;
-        mbar_wait(&full[s], ph, 2);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_u32(sA + s * a.a_stage_bytes);
-          if (a.halo) {
-            const int chunk = kb / 3, dh = kb - chunk * 3;
-            const int ksteps = (min(64, a.Cin - chunk * 64) + 15) >> 4;
-            for (int dw = 0; dw < 3; ++dw) {
-              const int tap = dh * 3 + dw;
-              const uint64_t adesc = a.halo_bo ? umma_desc_k128_off(a_addr + (uint32_t)dw * 128u)
-                                                 : umma_desc_k128(a_addr + (uint32_t)dw * 128u);
-              const uint32_t b_addr = a.b_resident ? smem_u32(sB + (tap * a.k_chunks + chunk) * b_tile_bytes)
-                                                   : smem_u32(sB + s * a.b_stage_bytes + dw * b_tile_bytes);
-              const uint64_t bdesc = umma_desc_k128(b_addr);
-              for (int k = 0; k < ksteps; ++k)
-                umma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                          (kb > 0 || dw > 0 || k > 0) ? 1u : 0u);
+      const int n_tile = a.dw ? (int)(tile % a.n_tiles) : 0;
+      uint32_t first = 0;                           // 0 for the very first MMA of the tile (overwrite), then 1
+      for (int o = 0; o < n_outer; ++o) {
+        for (int i = 0; i < n_inner; ++i) {
+          const int chunk = a.halo ? o : i;
+          const int ksteps = (min(64, a.Cin - (a.dw ? n_tile : chunk) * 64) + 15) >> 4;
+          const uint32_t a_lo = a_lo0 + (uint32_t)s * a_stage16;
+          mbar_wait(&full[s], ph, 2);
+          tc_fence_after();
+          if (elect_one()) {
+            if (a.halo) {
+              const int dh = i;
+#pragma unroll
+              for (int dw = 0; dw < 3; ++dw) {
+                const int tap = dh * 3 + dw;
+                const uint32_t al = a_lo + (uint32_t)dw * 8u;                  // +128 B: one pixel to the right
+                const uint32_t bl = a.b_resident ? b_lo0 + (uint32_t)(tap * a.k_chunks + chunk) * b_tile16
+                                                 : b_lo0 + (uint32_t)s * b_stage16 + (uint32_t)dw * b_tile16;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  if (k < ksteps) { umma_bf16_lohi(tacc, al + 2u * k, bl + 2u * k, desc_hi, idesc, first); first = 1u; }
+              }
+            } else {
+              const int tap = o;
+              const uint32_t bl = a.b_resident ? b_lo0 + (uint32_t)(tap * a.k_chunks + chunk) * b_tile16
+                                               : b_lo0 + (uint32_t)s * b_stage16;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (k < ksteps) { umma_bf16_lohi(tacc, a_lo + 2u * k, bl + 2u * k, desc_hi, idesc, first); first = 1u; }
             }
-          } else {
-            const int tap = kb / a.k_chunks, chunk = kb - tap * a.k_chunks;
-            const int ksteps = (min(64, a.Cin - chunk * 64) + 15) >> 4;
-            const uint64_t adesc = umma_desc_k128(a_addr);
-            const uint32_t b_addr = a.b_resident ? smem_u32(sB + (tap * a.k_chunks + chunk) * b_tile_bytes)
-                                                 : smem_u32(sB + s * a.b_stage_bytes);
-            const uint64_t bdesc = umma_desc_k128(b_addr);
-            for (int k = 0; k < ksteps; ++k)
-              umma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty[s]);
+            if (o == n_outer - 1 && i == n_inner - 1) umma_commit(&acc_full[ab]);
           }
-          umma_commit(&empty[s]);
-          if (kb == kb_per_tile - 1) umma_commit(&acc_full[ab]);
+          __syncwarp();
+          if (++s == a.stages) { s = 0; ph ^= 1u; }
         }
-        __syncwarp();
       }
     }
   } else {
@@ -204,6 +228,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const int hl = r / a.BW, wl = r - hl * a.BW;
+    const float act_lo = (a.act != B200SEG_ACT_NONE) ? 0.f : -INFINITY;
+    const float act_hi = (a.act == B200SEG_ACT_RELU6) ? 6.f : INFINITY;
+    const bool vec32 = (a.Cout & 15) == 0;     // pixel pitch is a multiple of 32 B -> 256-bit accesses
     int it = 0;
     int cur_n_tile = -1;
     for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
@@ -215,7 +242,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int w0 = tw * a.BW, h0 = th * a.BH, n0 = n_tile * a.block_n;
       const int ab = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
-      uint8_t* stg = sOut + (a.n_sbuf == 2 ? (it & 1) : 0) * n_boxes * TILE_BYTES;
+      uint8_t* stg = sOut + (a.n_sbuf > 1 ? (it % a.n_sbuf) : 0) * n_boxes * TILE_BYTES;
 
       if (n_tile != cur_n_tile) {   // (re)stage the bias slice of this N tile
         named_bar_sync(2, 128);     // nobody is still reading the old slice
@@ -232,42 +259,76 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(a.res) + pix * a.Cout + n0;
       __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + pix * a.Cout + n0;
 
-      for (int c0 = 0; c0 < a.block_n; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(trow + (uint32_t)c0, v);
-        tmem_ld_wait();
+      // software pipeline over 16-column chunks: the TMEM load of chunk c+1 is in flight while chunk c
+      // is converted and stored
+      auto process = [&](const uint32_t (&vv)[16], const int c0) {
         float f[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = apply_act_rt(__uint_as_float(v[i]) + sBias[c0 + i], a.act);
+        for (int i = 0; i < 16; i += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(sBias + c0 + i);
+          f[i] = fminf(fmaxf(__uint_as_float(vv[i]) + b4.x, act_lo), act_hi);
+          f[i + 1] = fminf(fmaxf(__uint_as_float(vv[i + 1]) + b4.y, act_lo), act_hi);
+          f[i + 2] = fminf(fmaxf(__uint_as_float(vv[i + 2]) + b4.z, act_lo), act_hi);
+          f[i + 3] = fminf(fmaxf(__uint_as_float(vv[i + 3]) + b4.w, act_lo), act_hi);
+        }
+        const bool c_ok0 = n0 + c0 < a.Cout, c_ok1 = n0 + c0 + 8 < a.Cout;   // Cout % 8 == 0
+        if (a.res != nullptr && row_ok && c_ok0) {
+          uint32_t t[8];
+          if (vec32) {
+            asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7])
+                         : "l"(rp + c0));
+          } else {
+            const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(rp + c0));
+            uint4 u1 = make_uint4(0, 0, 0, 0);
+            if (c_ok1) u1 = __ldg(reinterpret_cast<const uint4*>(rp + c0 + 8));
+            t[0] = u0.x; t[1] = u0.y; t[2] = u0.z; t[3] = u0.w; t[4] = u1.x; t[5] = u1.y; t[6] = u1.z; t[7] = u1.w;
+          }
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          float* g = f + hh * 8;
-          const bool col_ok = n0 + c0 + hh * 8 < a.Cout;   // Cout % 8 == 0: 16-byte groups are all-in or all-out
-          if (a.res != nullptr && row_ok && col_ok) {
-            const uint4 t = __ldg(reinterpret_cast<const uint4*>(rp + c0 + hh * 8));
-            g[0] += bf16lo(t.x); g[1] += bf16hi(t.x); g[2] += bf16lo(t.y); g[3] += bf16hi(t.y);
-            g[4] += bf16lo(t.z); g[5] += bf16hi(t.z); g[6] += bf16lo(t.w); g[7] += bf16hi(t.w);
+          for (int i = 0; i < 8; ++i) { f[2 * i] += bf16lo(t[i]); f[2 * i + 1] += bf16hi(t[i]); }
+        }
+        uint32_t o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+        if (a.tma_store) {
+          const int bx = c0 >> 6, j = (c0 & 63) >> 3;
+          uint8_t* rowp = stg + bx * TILE_BYTES + r * 128;
+          *reinterpret_cast<uint4*>(rowp + ((j ^ (r & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(rowp + (((j + 1) ^ (r & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+        } else if (row_ok && c_ok0) {
+          if (vec32) {
+            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(yp + c0), "r"(o[0]), "r"(o[1]),
+                         "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
+                         : "memory");
+          } else {
+            *reinterpret_cast<uint4*>(yp + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+            if (c_ok1) *reinterpret_cast<uint4*>(yp + c0 + 8) = make_uint4(o[4], o[5], o[6], o[7]);
           }
-          uint4 o;
-          o.x = pack_bf16x2(g[0], g[1]); o.y = pack_bf16x2(g[2], g[3]);
-          o.z = pack_bf16x2(g[4], g[5]); o.w = pack_bf16x2(g[6], g[7]);
-          if (!a.direct_store) {
-            const int bx = c0 >> 6;
-            const int j = ((c0 & 63) >> 3) + hh;
-            *reinterpret_cast<uint4*>(stg + bx * TILE_BYTES + r * 128 + ((j ^ (r & 7)) << 4)) = o;
-          } else if (row_ok && col_ok) {
-            *reinterpret_cast<uint4*>(yp + c0 + hh * 8) = o;
-          }
+        }
+      };
+      uint32_t va[16], vb[16];
+      tmem_ld16(trow, va);
+      const int nch = a.block_n >> 4;
+      for (int ch = 0; ch < nch; ch += 2) {
+        tmem_ld_wait();
+        if (ch + 1 < nch) tmem_ld16(trow + (uint32_t)((ch + 1) << 4), vb);
+        process(va, ch << 4);
+        if (ch + 1 < nch) {
+          tmem_ld_wait();
+          if (ch + 2 < nch) tmem_ld16(trow + (uint32_t)((ch + 2) << 4), va);
+          process(vb, (ch + 1) << 4);
         }
       }
       // accumulator fully read -> hand it back to the MMA warp
       tc_fence_before();
       mbar_arrive(&acc_empty[ab]);
-      if (!a.direct_store) {
+      if (a.tma_store) {
         fence_proxy_async_smem();
-        // the staging buffer the NEXT tile will write must no longer be read by an in-flight store
+        // allow n_sbuf-2 stores in flight: the buffer the NEXT tile writes was last read by store(it+1-n_sbuf)
         if (et == 0) {
-          if (a.n_sbuf == 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (a.n_sbuf >= 4) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+          else if (a.n_sbuf == 3) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else if (a.n_sbuf == 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
         named_bar_sync(1, 128);
         if (et == 0) {
@@ -279,7 +340,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (a.n_sbuf == 1) named_bar_sync(1, 128);
       }
     }
-    if (!a.direct_store && et == 0) tma_store_wait_all();
+    if (a.tma_store && et == 0) tma_store_wait_all();
     tc_fence_before();
   }
   __syncthreads();
@@ -310,44 +371,51 @@ static void pick_tile(int W, int H, int* BW, int* BH) {
 
 using namespace b200;
 
-// flags: bit0 direct-store epilogue (debug); bit1 forbid HALO addressing; bit2 forbid resident weights;
-//        bit3 single staging buffer; bit4 HALO descriptors WITH base_offset (experiment: wrong on B200); bits 8..15: force grid size = value * 4 CTAs (0 = auto)
-extern "C" int b200seg_conv_tc(const void* x, const void* w, const float* bias, const void* res, void* y, int B,
-                               int H, int W, int Cin, int Cout, int taps, int act, int flags,
-                               b200seg_stream_t s) {
-  B200_REQUIRE(taps == 1 || taps == 9, "conv_tc: taps=%d (1 or 9)", taps);
-  B200_REQUIRE(Cin > 0 && Cin % 8 == 0, "conv_tc: Cin=%d must be a positive multiple of 8", Cin);
-  B200_REQUIRE(Cout > 0 && Cout % 8 == 0, "conv_tc: Cout=%d must be a positive multiple of 8", Cout);
-  B200_REQUIRE(B > 0 && H > 0 && W > 0, "conv_tc: empty tensor");
-  B200_REQUIRE(x && w && y, "conv_tc: null pointer");
-
+// flags: bit0 epilogue through smem staging + TMA store instead of direct 256-bit register stores;
+//        bit1 forbid HALO addressing; bit2 forbid resident weights; bit3 single staging buffer;
+//        bit4 HALO descriptors WITH base_offset (experiment: wrong on B200);
+//        bits 8..15: force grid size = value * 4 CTAs (0 = auto)
+// x: [B,H,W,Cin] input; output [B,Ho,Wo,Cout] with Ho = (H-1)/stride+1.  dwmode: w is the block-diagonal
+// packing bf16 [C][9][64] (see b200seg_dwconv3x3_tc).
+static int launch_conv_tc(const void* x, const void* w, const float* bias, const void* res, void* y, int B, int H,
+                          int W, int Cin, int Cout, int taps, int stride, int dwmode, int act, int flags,
+                          cudaStream_t stream) {
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   ConvTcArgs a;
   a.bias = bias; a.res = res; a.y = y;
   a.taps = taps; a.Cin = Cin; a.Cout = Cout;
-  a.halo = (taps == 9 && W >= 96 && !(flags & 2)) ? 1 : 0;
+  a.dw = dwmode; a.stride = stride;
+  a.halo = (taps == 9 && stride == 1 && W >= 96 && !(flags & 2)) ? 1 : 0;
   if (taps == 1) {   // pointwise: pixels are one flat axis
     const long long M = (long long)B * H * W;
     B200_REQUIRE(M < (1ll << 31), "conv_tc: too many pixels");
     a.W = (int)M; a.H = 1; a.B = 1;
   } else {
-    a.W = W; a.H = H; a.B = B;
+    a.W = Wo; a.H = Ho; a.B = B;
   }
-  if (a.halo) { a.BW = W < 128 ? W : 128; a.BH = 1; }
+  if (a.halo) { a.BW = Wo < 128 ? Wo : 128; a.BH = 1; }
   else pick_tile(a.W, a.H, &a.BW, &a.BH);
   a.tiles_w = (a.W + a.BW - 1) / a.BW;
   a.tiles_h = (a.H + a.BH - 1) / a.BH;
-  // N tiling: one tile if Cout <= 256 (rounded to the UMMA granule 16); otherwise tiles that are a
-  // multiple of 64 wide so that a 64-channel store box never spills into a neighbour tile.
-  if (Cout <= 256) {
-    a.block_n = (Cout + 15) & ~15; a.n_tiles = 1;
+  if (dwmode) {
+    // one N tile per 64-channel chunk; its single K chunk is the same 64 input channels
+    a.block_n = Cout >= 64 ? 64 : ((Cout + 15) & ~15);
+    a.n_tiles = (Cout + 63) / 64;
+    a.k_chunks = 1;
   } else {
-    int nt = (Cout + 255) / 256;
-    int bn = (((Cout + nt - 1) / nt) + 63) & ~63;
-    a.block_n = bn; a.n_tiles = (Cout + bn - 1) / bn;
+    // N tiling: one tile if Cout <= 256 (rounded to the UMMA granule 16); otherwise tiles that are a
+    // multiple of 64 wide so that a 64-channel store box never spills into a neighbour tile.
+    if (Cout <= 256) {
+      a.block_n = (Cout + 15) & ~15; a.n_tiles = 1;
+    } else {
+      int nt = (Cout + 255) / 256;
+      int bn = (((Cout + nt - 1) / nt) + 63) & ~63;
+      a.block_n = bn; a.n_tiles = (Cout + bn - 1) / bn;
+    }
+    a.k_chunks = (Cin + 63) / 64;
   }
-  a.k_chunks = (Cin + 63) / 64;
   a.act = act;
-  a.direct_store = flags & 1;
+  a.tma_store = flags & 1;
   a.halo_bo = (flags & 16) ? 1 : 0;   // measured on B200: the swizzle uses absolute smem address bits, base_offset must stay 0
   a.tmem_cols = 32;
   while (a.tmem_cols < 2 * a.block_n) a.tmem_cols <<= 1;   // two accumulators
@@ -358,8 +426,11 @@ extern "C" int b200seg_conv_tc(const void* x, const void* w, const float* bias, 
   a.a_stage_bytes = a.halo ? HALO_BYTES : TILE_BYTES;
   const int kb_per_tile = a.halo ? a.k_chunks * 3 : a.k_chunks * taps;
   const int b_all = taps * a.k_chunks * b_tile;
-  a.n_sbuf = (flags & 8) ? 1 : 2;
-  if (a.n_sbuf * n_boxes * TILE_BYTES > 96 * 1024) a.n_sbuf = 1;
+  a.n_sbuf = 0;
+  if (a.tma_store) {
+    a.n_sbuf = (flags & 8) ? 1 : 3;
+    while (a.n_sbuf > 1 && a.n_sbuf * n_boxes * TILE_BYTES > 64 * 1024) --a.n_sbuf;
+  }
   const int out_bytes = a.n_sbuf * n_boxes * TILE_BYTES;
   a.b_resident = (a.n_tiles == 1 && !(flags & 4) && b_all <= 80 * 1024 && b_all + out_bytes + 2 * a.a_stage_bytes <= smem_cap) ? 1 : 0;
   a.b_stage_bytes = a.b_resident ? 0 : (a.halo ? 3 * b_tile : b_tile);
@@ -378,24 +449,27 @@ extern "C" int b200seg_conv_tc(const void* x, const void* w, const float* bias, 
 
   CUtensorMap tmA, tmB, tmC;
   {
-    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
-    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)Cin * 2 * a.W, (uint64_t)Cin * 2 * a.W * a.H};
-    uint32_t box[4] = {64, (uint32_t)(a.halo ? 130 : a.BW), (uint32_t)a.BH, 1};
-    int rc = make_tmap_bf16(&tmA, x, 4, dims, str, box, 1);
+    // the activation map always describes the INPUT tensor; for 1x1 it is the flattened pixel axis
+    const uint64_t iw = taps == 1 ? (uint64_t)a.W : (uint64_t)W, ih = taps == 1 ? 1 : (uint64_t)H, ib = taps == 1 ? 1 : (uint64_t)B;
+    uint64_t dims[4] = {(uint64_t)Cin, iw, ih, ib};
+    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)Cin * 2 * iw, (uint64_t)Cin * 2 * iw * ih};
+    uint32_t box[4] = {64, (uint32_t)(a.halo ? 130 : a.BW * stride), (uint32_t)(a.BH * stride), 1};
+    uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+    int rc = make_tmap_bf16(&tmA, x, 4, dims, str, box, 1, es);
     if (rc) return rc;
   }
   {
-    uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)taps, (uint64_t)Cout};
-    uint64_t str[2] = {(uint64_t)Cin * 2, (uint64_t)Cin * 2 * taps};
+    uint64_t dims[3] = {(uint64_t)(dwmode ? 64 : Cin), (uint64_t)taps, (uint64_t)Cout};
+    uint64_t str[2] = {dims[0] * 2, dims[0] * 2 * taps};
     uint32_t box[3] = {64, 1, (uint32_t)a.block_n};
-    int rc = make_tmap_bf16(&tmB, w, 3, dims, str, box, 1);
+    int rc = make_tmap_bf16(&tmB, w, 3, dims, str, box, 1, nullptr);
     if (rc) return rc;
   }
   {
     uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
     uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)Cout * 2 * a.W, (uint64_t)Cout * 2 * a.W * a.H};
     uint32_t box[4] = {64, (uint32_t)a.BW, (uint32_t)a.BH, 1};
-    int rc = make_tmap_bf16(&tmC, y, 4, dims, str, box, 1);
+    int rc = make_tmap_bf16(&tmC, y, 4, dims, str, box, 1, nullptr);
     if (rc) return rc;
   }
   int dev = 0;
@@ -414,6 +488,26 @@ extern "C" int b200seg_conv_tc(const void* x, const void* w, const float* bias, 
   long long grid = (long long)sm_count() * per_sm;
   if ((flags >> 8) & 0xff) grid = (long long)((flags >> 8) & 0xff) * 4;
   if (grid > a.total_tiles) grid = a.total_tiles;
-  conv_tc_kernel<<<(unsigned)grid, TC_THREADS, smem, (cudaStream_t)s>>>(tmA, tmB, tmC, a);
+  conv_tc_kernel<<<(unsigned)grid, TC_THREADS, smem, stream>>>(tmA, tmB, tmC, a);
   return check_launch("conv_tc");
+}
+
+extern "C" int b200seg_conv_tc(const void* x, const void* w, const float* bias, const void* res, void* y, int B,
+                               int H, int W, int Cin, int Cout, int taps, int act, int flags,
+                               b200seg_stream_t s) {
+  B200_REQUIRE(taps == 1 || taps == 9, "conv_tc: taps=%d (1 or 9)", taps);
+  B200_REQUIRE(Cin > 0 && Cin % 8 == 0, "conv_tc: Cin=%d must be a positive multiple of 8", Cin);
+  B200_REQUIRE(Cout > 0 && Cout % 8 == 0, "conv_tc: Cout=%d must be a positive multiple of 8", Cout);
+  B200_REQUIRE(B > 0 && H > 0 && W > 0, "conv_tc: empty tensor");
+  B200_REQUIRE(x && w && y, "conv_tc: null pointer");
+  return launch_conv_tc(x, w, bias, res, y, B, H, W, Cin, Cout, taps, 1, 0, act, flags, (cudaStream_t)s);
+}
+
+extern "C" int b200seg_dwconv3x3_tc(const void* x, const void* wdiag, const float* bias, void* y, int B, int H,
+                                    int W, int C, int stride, int act, int flags, b200seg_stream_t s) {
+  B200_REQUIRE(C > 0 && C % 8 == 0, "dwconv3x3_tc: C=%d must be a positive multiple of 8", C);
+  B200_REQUIRE(stride == 1 || stride == 2, "dwconv3x3_tc: stride=%d", stride);
+  B200_REQUIRE(B > 0 && H > 0 && W > 0, "dwconv3x3_tc: empty tensor");
+  B200_REQUIRE(x && wdiag && y, "dwconv3x3_tc: null pointer");
+  return launch_conv_tc(x, wdiag, bias, nullptr, y, B, H, W, C, C, 9, stride, 1, act, flags, (cudaStream_t)s);
 }

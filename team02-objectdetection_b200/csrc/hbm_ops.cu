@@ -82,7 +82,9 @@ conv3x3_smallcin_kernel(const TI* __restrict__ x, const float* __restrict__ w, c
 // mma.sync.m16n8k16 (bf16 x bf16 -> f32): a warp owns 16 consecutive output pixels x all Cout.
 // Per pixel this needs ~1 load instruction + 0.5 MMA instead of 27 loads + 27 FMAs per 8 channels,
 // which is what moves the kernel from issue-bound to HBM-bound.  k = c*9 + kh*3 + kw.
-// The C fragments are transposed through a per-warp shared-memory patch so that every thread
+// Each CTA first stages the 3 channels x 3 input rows feeding 128 output pixels in shared memory with
+// coalesced loads (every input element is read once per CTA), and the warps gather their fragments from
+// there.  The C fragments are transposed through a per-warp shared-memory patch so that every thread
 // stores whole 16-byte NHWC channel vectors (1 KB contiguous per warp).
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -92,11 +94,14 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <typename TI, int NT>   // NT = Cout / 8
+template <typename TI, int NT, int S>   // NT = Cout / 8, S = stride
 __global__ void __launch_bounds__(256)
 conv3x3_c3_mma_kernel(const TI* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                      __nv_bfloat16* __restrict__ y, int B, int H, int W, int Ho, int Wo, int stride, int act) {
+                      __nv_bfloat16* __restrict__ y, int B, int H, int W, int Ho, int Wo, int act) {
   constexpr int Cout = NT * 8;
+  constexpr int NCOL = 127 * S + 3;            // input columns feeding 128 output pixels
+  constexpr int PITCH = NCOL + 3;              // odd-ish pitch: spreads the 9 row segments over banks
+  __shared__ float tile[9][PITCH];             // [c*3 + kh][column]
   __shared__ __align__(16) __nv_bfloat16 patch[8][16][Cout + 8];   // +8: conflict-free fragment writes
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -118,8 +123,8 @@ conv3x3_c3_mma_kernel(const TI* __restrict__ x, const float* __restrict__ w, con
         }
         bf[ks][j][h] = pack_bf16x2(v[0], v[1]);
       }
-  // this thread's 8 gather offsets (same for every pixel): k -> (c, kh, kw)
-  int kc[2][2][2], kh_[2][2][2], kw_[2][2][2];
+  // this thread's 8 gather offsets into the smem tile (same for every pixel group): k -> (c*3+kh, kw)
+  int koff[2][2][2];
 #pragma unroll
   for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
@@ -128,8 +133,7 @@ conv3x3_c3_mma_kernel(const TI* __restrict__ x, const float* __restrict__ w, con
       for (int e = 0; e < 2; ++e) {
         const int k = ks * 16 + h * 8 + 2 * t + e;
         const int c = k / 9, r9 = k - c * 9;
-        kc[ks][h][e] = (k < 27) ? c : -1;
-        kh_[ks][h][e] = r9 / 3; kw_[ks][h][e] = r9 % 3;
+        koff[ks][h][e] = (k < 27) ? (c * 3 + r9 / 3) * PITCH + r9 % 3 : -1;
       }
   float bias_v[NT][2];
 #pragma unroll
@@ -138,30 +142,40 @@ conv3x3_c3_mma_kernel(const TI* __restrict__ x, const float* __restrict__ w, con
     bias_v[j][1] = bias ? __ldg(bias + j * 8 + 2 * t + 1) : 0.f;
   }
 
-  const int groups_w = (Wo + 15) / 16;
-  const long long total = (long long)B * Ho * groups_w;
+  const int segs = (Wo + 127) / 128;
+  const long long total = (long long)B * Ho * segs;
   const long long HW = (long long)H * W;
-  for (long long grp = (long long)blockIdx.x * 8 + warp; grp < total; grp += (long long)gridDim.x * 8) {
-    const int gw = (int)(grp % groups_w);
-    long long p = grp / groups_w;
+  const float* tflat = &tile[0][0];
+  for (long long job = blockIdx.x; job < total; job += gridDim.x) {
+    const int sg = (int)(job % segs);
+    long long p = job / segs;
     const int ho = (int)(p % Ho);
     const int b = (int)(p / Ho);
+    const int wo0 = sg * 128;
     const TI* xb = x + (long long)b * 3 * HW;
+    const int wi0 = wo0 * S - 1, hi0 = ho * S - 1;
+    __syncthreads();                              // previous job's gathers are done
+    for (int i = threadIdx.x; i < 9 * NCOL; i += 256) {
+      const int rowi = i / NCOL, col = i - rowi * NCOL;
+      const int c = rowi / 3, kh = rowi - c * 3;
+      const int hi = hi0 + kh, wi = wi0 + col;
+      float v = 0.f;
+      if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = to_f32<TI>(xb[(long long)c * HW + (long long)hi * W + wi]);
+      tile[rowi][col] = v;
+    }
+    __syncthreads();
+    const int px0 = warp * 16;                    // this warp's 16 output pixels within the segment
     uint32_t afr[2][4];
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-      for (int h = 0; h < 2; ++h)       // h: k half (cols 2t.. / 2t+8..)
+      for (int h = 0; h < 2; ++h)                 // h: k half (cols 2t.. / 2t+8..)
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {  // rr: row g / row g+8
-          const int wo = gw * 16 + g + rr * 8;
+        for (int rr = 0; rr < 2; ++rr) {          // rr: row g / row g+8
+          const int col = (px0 + g + rr * 8) * S;
           float v[2];
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int hi = ho * stride - 1 + kh_[ks][h][e], wi = wo * stride - 1 + kw_[ks][h][e];
-            const bool ok = kc[ks][h][e] >= 0 && wo < Wo && hi >= 0 && hi < H && wi >= 0 && wi < W;
-            v[e] = ok ? to_f32<TI>(xb[(long long)kc[ks][h][e] * HW + (long long)hi * W + wi]) : 0.f;
-          }
+          for (int e = 0; e < 2; ++e) v[e] = koff[ks][h][e] >= 0 ? tflat[koff[ks][h][e] + col] : 0.f;
           afr[ks][h * 2 + rr] = pack_bf16x2(v[0], v[1]);   // a0:(g,lo) a1:(g+8,lo) a2:(g,hi) a3:(g+8,hi)
         }
     float acc[NT][4];
@@ -182,10 +196,10 @@ conv3x3_c3_mma_kernel(const TI* __restrict__ x, const float* __restrict__ w, con
           pack_bf16x2(apply_act_rt(acc[j][2], act), apply_act_rt(acc[j][3], act));
     }
     __syncwarp();
-    __nv_bfloat16* yrow = y + (((long long)b * Ho + ho) * Wo + gw * 16) * Cout;
+    __nv_bfloat16* yrow = y + (((long long)b * Ho + ho) * Wo + wo0 + px0) * Cout;
     for (int i = lane; i < 16 * NT; i += 32) {
       const int px = i / NT, cv = i - px * NT;
-      if (gw * 16 + px < Wo)
+      if (wo0 + px0 + px < Wo)
         *reinterpret_cast<uint4*>(yrow + px * Cout + cv * 8) = *reinterpret_cast<const uint4*>(&patch[warp][px][cv * 8]);
     }
   }
@@ -484,13 +498,17 @@ int b200seg_conv3x3_smallcin(const void* x, int x_dtype, const float* w, const f
   cudaStream_t st = (cudaStream_t)s;
   if (y_dtype == B200SEG_BF16 && Cin == 3 && (Cout == 32 || Cout == 64 || Cout == 16)) {
     // tensor-core path (bf16 storage): one warp = 16 output pixels x all Cout
-    const long long groups = (long long)B * Ho * ((Wo + 15) / 16);
-    long long gb = (groups + 7) / 8;
-    const long long capb = (long long)sm_count() * 16;
+    const long long jobs = (long long)B * Ho * ((Wo + 127) / 128);
+    long long gb = jobs;
+    const long long capb = (long long)sm_count() * 8;
     if (gb > capb) gb = capb;
-#define LAUNCH_MMA(TI, NT) conv3x3_c3_mma_kernel<TI, NT><<<(int)gb, 256, 0, st>>>((const TI*)x, w, b, (bf16*)y, B, H, W, Ho, Wo, stride, act)
-    if (x_dtype == B200SEG_F32) { if (Cout == 32) LAUNCH_MMA(float, 4); else if (Cout == 64) LAUNCH_MMA(float, 8); else LAUNCH_MMA(float, 2); }
-    else if (x_dtype == B200SEG_BF16) { if (Cout == 32) LAUNCH_MMA(bf16, 4); else if (Cout == 64) LAUNCH_MMA(bf16, 8); else LAUNCH_MMA(bf16, 2); }
+#define LAUNCH_MMA(TI, NT)                                                                                              \
+  {                                                                                                                     \
+    if (stride == 2) conv3x3_c3_mma_kernel<TI, NT, 2><<<(int)gb, 256, 0, st>>>((const TI*)x, w, b, (bf16*)y, B, H, W, Ho, Wo, act); \
+    else conv3x3_c3_mma_kernel<TI, NT, 1><<<(int)gb, 256, 0, st>>>((const TI*)x, w, b, (bf16*)y, B, H, W, Ho, Wo, act);             \
+  }
+    if (x_dtype == B200SEG_F32) { if (Cout == 32) LAUNCH_MMA(float, 4) else if (Cout == 64) LAUNCH_MMA(float, 8) else LAUNCH_MMA(float, 2) }
+    else if (x_dtype == B200SEG_BF16) { if (Cout == 32) LAUNCH_MMA(bf16, 4) else if (Cout == 64) LAUNCH_MMA(bf16, 8) else LAUNCH_MMA(bf16, 2) }
     else return set_error(-1, "conv3x3_smallcin: bad x dtype %d", x_dtype);
 #undef LAUNCH_MMA
     return check_launch("conv3x3_c3_mma");

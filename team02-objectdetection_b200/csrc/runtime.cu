@@ -56,7 +56,7 @@ static EncodeTiledFn resolve_encode() {
 }
 
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                   const uint64_t* strides_bytes, const uint32_t* box, int swizzle128) {
+                   const uint64_t* strides_bytes, const uint32_t* box, int swizzle128, const uint32_t* elem_strides) {
   EncodeTiledFn enc = resolve_encode();
   if (!enc) return set_error(-2, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
   cuuint64_t gdim[5];
@@ -65,7 +65,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = elem_strides ? elem_strides[i] : 1;
     if (i + 1 < rank) gstr[i] = strides_bytes[i];
   }
   if (((uintptr_t)base & 15) != 0) return set_error(-3, "TMA base %p not 16-byte aligned", base);

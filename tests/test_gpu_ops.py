@@ -67,6 +67,26 @@ def test_dwconv3x3(dt, B, H, W, C, stride):
     assert _err(_nchw(got), ref) < TOL[dt]
 
 
+@pytest.mark.parametrize("flags", [0, 2], ids=["auto", "tap_mode"])
+@pytest.mark.parametrize("B,H,W,C,stride", [(2, 128, 256, 32, 1), (1, 128, 256, 96, 2), (1, 64, 128, 144, 1),
+                                            (2, 16, 32, 576, 2), (3, 8, 16, 960, 1), (1, 7, 9, 24, 1), (1, 9, 7, 8, 2),
+                                            (1, 1, 1, 16, 1), (1, 23, 40, 192, 2), (1, 33, 100, 72, 1), (1, 64, 128, 64, 2)])
+def test_dwconv3x3_tensor_core(flags, B, H, W, C, stride):
+    """Depthwise 3x3 run as a block-diagonal implicit GEMM on tcgen05 (weights are bf16 on this path)."""
+    x = _rand(B, C, H, W, seed=4).bfloat16()
+    w = _rand(C, 1, 3, 3, seed=5, scale=0.4).bfloat16()
+    b = _rand(C, seed=6, scale=0.1)
+    ref = torch.clamp(F.conv2d(x.double(), w.double(), b.double(), stride, 1, 1, C), 0, 6)
+    wdiag = ops.pack_dw_diag(w.float().reshape(C, 9).t().contiguous())
+    got = ops.dwconv3x3_tc(_nhwc(x), wdiag, b, stride, 2, flags=flags)
+    torch.cuda.synchronize()
+    e = _err(_nchw(got), ref)
+    if e >= TOL[torch.bfloat16]:
+        d = (_nchw(got).double() - ref).abs()
+        bad = (d > TOL[torch.bfloat16] * ref.abs().max()).nonzero()
+        raise AssertionError(f"dw_tc err {e:.3e}; {bad.shape[0]} bad of {d.numel()}; first (b,c,h,w) {bad[:6].tolist()} last {bad[-3:].tolist()}")
+
+
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("B,H,W,Cin,Cout,taps,act,res", [
     (2, 16, 32, 64, 64, 1, 2, False), (1, 8, 16, 320, 1280, 1, 2, False), (2, 16, 32, 384, 64, 1, 0, True),
@@ -115,7 +135,7 @@ TC_CASES = [
 ]
 
 
-@pytest.mark.parametrize("flags", [0, 1], ids=["tma_store", "direct_store"])
+@pytest.mark.parametrize("flags", [0, 1], ids=["direct_store", "tma_store"])
 @pytest.mark.parametrize("B,H,W,Cin,Cout,taps,act,res", TC_CASES)
 def test_conv_tc(flags, B, H, W, Cin, Cout, taps, act, res):
     k = 3 if taps == 9 else 1

@@ -49,21 +49,20 @@ def conv_case(name, H, W, Cin, Cout, taps, res=False, flag_list=(0,)):
 
 
 def main():
-    FL3 = (0, 2, 4, 6, 8)            # default | no halo | no resident | neither | single staging
-    FL1 = (0, 4, 8, 1 << 8 | 0, 37 << 8, 74 << 8)   # default | no resident | single staging | grid 4 (!) | grid 148 | grid 296
+    FL3 = (0, 1, 2)                  # direct store | TMA store (3 staging buffers) | no halo
     conv_case("up4.0", 128, 256, 80, 32, 9, flag_list=FL3)
     conv_case("up4.3", 128, 256, 32, 32, 9, flag_list=FL3)
     conv_case("up3.0", 64, 128, 152, 64, 9, flag_list=FL3)
     conv_case("up3.3", 64, 128, 64, 64, 9, flag_list=FL3)
-    conv_case("up2.0", 32, 64, 288, 128, 9, flag_list=(0, 4))
-    conv_case("up2.3", 32, 64, 128, 128, 9, flag_list=(0, 4))
-    conv_case("up1.0", 16, 32, 1344, 256, 9, flag_list=(0, 8))
-    conv_case("up1.3", 16, 32, 256, 256, 9, flag_list=(0, 8))
-    conv_case("f2.expand", 128, 256, 16, 96, 1, flag_list=(0, 4, 8, 37 << 8))
-    conv_case("f1.project", 128, 256, 32, 16, 1, flag_list=(0, 4, 37 << 8))
-    conv_case("f2.project", 64, 128, 96, 24, 1, flag_list=(0, 4))
-    conv_case("f3.expand", 64, 128, 24, 144, 1, flag_list=(0, 4))
-    conv_case("f3.project", 64, 128, 144, 24, 1, res=True, flag_list=(0, 4))
+    conv_case("up2.0", 32, 64, 288, 128, 9, flag_list=(0, 1))
+    conv_case("up2.3", 32, 64, 128, 128, 9, flag_list=(0, 1))
+    conv_case("up1.0", 16, 32, 1344, 256, 9, flag_list=(0, 1))
+    conv_case("up1.3", 16, 32, 256, 256, 9, flag_list=(0, 1))
+    conv_case("f2.expand", 128, 256, 16, 96, 1, flag_list=(0, 1, 37 << 8))
+    conv_case("f1.project", 128, 256, 32, 16, 1, flag_list=(0, 1, 37 << 8))
+    conv_case("f2.project", 64, 128, 96, 24, 1, flag_list=(0, 1))
+    conv_case("f3.expand", 64, 128, 24, 144, 1, flag_list=(0, 1))
+    conv_case("f3.project", 64, 128, 144, 24, 1, res=True, flag_list=(0, 1))
     conv_case("f5.expand", 32, 64, 32, 192, 1)
     conv_case("f8.expand", 16, 32, 64, 384, 1)
     conv_case("f8.project", 16, 32, 384, 64, 1, res=True)
@@ -74,7 +73,7 @@ def main():
     conv_case("outc.3", 128, 256, 16, 16, 1)
     # HBM ops
     for (nm, H, W, C, s) in (("f1.dw", 128, 256, 32, 1), ("f2.dw", 128, 256, 96, 2), ("f3.dw", 64, 128, 144, 1),
-                             ("f5.dw", 32, 64, 192, 1), ("f8.dw", 16, 32, 384, 1), ("f15.dw", 8, 16, 960, 1)):
+                             ("f4.dw", 64, 128, 144, 2), ("f5.dw", 32, 64, 192, 1), ("f8.dw", 16, 32, 384, 1), ("f15.dw", 8, 16, 960, 1)):
         name = f"dwconv {nm} C={C} s{s} @{H}x{W}"
         if flt and flt not in name:
             continue
@@ -82,6 +81,10 @@ def main():
         out = torch.empty(B, (H - 1) // s + 1, (W - 1) // s + 1, C, device=DEV, dtype=torch.bfloat16)
         us = timeit(lambda: ops.dwconv3x3(x, w, b, s, 2, out=out))
         report(name, us, (x.numel() + out.numel()) * 2, 18 * out.numel())
+        wd = ops.pack_dw_diag(w)
+        for fl in (0, 2):
+            us = timeit(lambda: ops.dwconv3x3_tc(x, wd, b, s, 2, out=out, flags=fl))
+            report(name + f" TENSOR-CORE flags={fl}", us, (x.numel() + out.numel()) * 2, 18 * out.numel())
     for (nm, h, w_, Cs, Cu) in (("up1", 8, 16, 64, 1280), ("up2", 16, 32, 32, 256), ("up3", 32, 64, 24, 128), ("up4", 64, 128, 16, 64)):
         name = f"upcat {nm} {Cs}+{Cu} @{h}x{w_}"
         if flt and flt not in name:
