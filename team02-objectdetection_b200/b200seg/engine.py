@@ -115,7 +115,7 @@ class Engine:
         self.steps = build_steps_mbv2unet(model) if arch == "mbv2unet" else build_steps_unet(model)
         self.precision: Optional[str] = None       # None = derive from module dtype / autocast
         self.dense_impl: Optional[str] = None       # None = "tc" for bf16, "simt" for fp32 (tests may force)
-        self.dw_impl: Optional[str] = None          # None = "tc" (tensor-core depthwise) in bf16 mode, else "simt"
+        self.dw_impl: Optional[str] = None          # None = per-layer choice; "tc" / "simt" force one kernel
         self.tc_flags = 0
         self._packed: Dict[str, dict] = {}
         self._packed_key = None
@@ -201,7 +201,10 @@ class Engine:
             env[s.dst] = ops.conv3x3_smallcin(env[s.src], p["w"], p["b"], s.stride, s.act, sdt)
         elif s.op == "dw":
             p = pk[s.name]
-            if mode == "bf16" and (self.dw_impl or "tc") == "tc":
+            # tensor-core depthwise wins only where HALO addressing applies (stride 1, rows >= 96 px);
+            # elsewhere the register-blocked SIMT kernel is faster (tools/kbench.py)
+            use_tc = self.dw_impl == "tc" or (self.dw_impl is None and s.stride == 1 and env[s.src].shape[2] >= 96)
+            if mode == "bf16" and use_tc:
                 env[s.dst] = ops.dwconv3x3_tc(env[s.src], p["wdiag"], p["b"], s.stride, s.act, flags=self.tc_flags)
             else:
                 env[s.dst] = ops.dwconv3x3(env[s.src], p["w"], p["b"], s.stride, s.act)

@@ -374,7 +374,8 @@ using namespace b200;
 // flags: bit0 epilogue through smem staging + TMA store instead of direct 256-bit register stores;
 //        bit1 forbid HALO addressing; bit2 forbid resident weights; bit3 single staging buffer;
 //        bit4 HALO descriptors WITH base_offset (experiment: wrong on B200);
-//        bits 8..15: force grid size = value * 4 CTAs (0 = auto)
+//        bits 8..15: force grid size = value * 4 CTAs (0 = auto); bits 16..19: pipeline stages wanted (0 = auto);
+//        bits 20..21: CTAs per SM (0 = auto)
 // x: [B,H,W,Cin] input; output [B,Ho,Wo,Cout] with Ho = (H-1)/stride+1.  dwmode: w is the block-diagonal
 // packing bf16 [C][9][64] (see b200seg_dwconv3x3_tc).
 static int launch_conv_tc(const void* x, const void* w, const float* bias, const void* res, void* y, int B, int H,
@@ -436,11 +437,20 @@ static int launch_conv_tc(const void* x, const void* w, const float* bias, const
   a.b_stage_bytes = a.b_resident ? 0 : (a.halo ? 3 * b_tile : b_tile);
   const int per_stage = a.a_stage_bytes + a.b_stage_bytes;
   const int fixed = out_bytes + (a.b_resident ? b_all : 0);
-  // short pipelines leave room for a second CTA per SM (more tiles in flight for the HBM-bound layers)
+  // Measured on B200 (tools/kbench.py KB_SWEEP): two resident CTAs per SM (two MMA issuers, two epilogues)
+  // beat one CTA with a deeper ring whenever both fit, so: the deepest ring (<= want) that still leaves room
+  // for a second CTA (smem and 512 TMEM columns), else the deepest ring that fits at all.
   int want = kb_per_tile <= 3 ? 4 : 6;
+  if ((flags >> 16) & 0xf) want = (flags >> 16) & 0xf;
   int stages = (smem_cap - fixed) / per_stage;
   if (stages > want) stages = want;
   if (stages > 8) stages = 8;
+  if (!((flags >> 16) & 0xf) && 2 * a.tmem_cols <= 512) {
+    const int half_cap = (227 * 1024) / 2 - 1024 - (1024 + 1024 + 256);
+    int st2 = (half_cap - fixed) / per_stage;
+    if (st2 > want) st2 = want;
+    if (st2 >= 2) stages = st2;
+  }
   B200_REQUIRE(stages >= 1, "conv_tc: tile does not fit in shared memory (Cin=%d Cout=%d taps=%d)", Cin, Cout, taps);
   a.stages = stages;
   const int smem = fixed + stages * per_stage + 1024 + 1024 + 256;
@@ -484,6 +494,7 @@ static int launch_conv_tc(const void* x, const void* w, const float* bias, const
   int per_sm = (227 * 1024) / (smem + 1024);
   if (per_sm > 512 / a.tmem_cols) per_sm = 512 / a.tmem_cols;
   if (per_sm > 2) per_sm = 2;
+  if ((flags >> 20) & 0x3) per_sm = (flags >> 20) & 0x3;
   if (per_sm < 1) per_sm = 1;
   long long grid = (long long)sm_count() * per_sm;
   if ((flags >> 8) & 0xff) grid = (long long)((flags >> 8) & 0xff) * 4;

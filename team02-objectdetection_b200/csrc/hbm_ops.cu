@@ -6,6 +6,8 @@
 //   upsample2x_concat  bilinear x2 (align_corners=False) fused with cat([skip, up])
 //   upsample2x_ac_*    final bilinear x2 (align_corners=True) -> NCHW logits, or fused argmax mask
 //   nhwc_to_nchw, maxpool2x2
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -286,9 +288,248 @@ dwconv3x3_kernel(const T* __restrict__ x, const float* __restrict__ w, const flo
 }
 
 // ------------------------------------------------------------------------------------------
+// depthwise 3x3, bf16 NHWC, 2-D register blocking: one thread = TH x TW output pixels x 8 channels.
+// The (TH-1)*S+3 input rows are streamed one at a time: a row's (TW-1)*S+3 vectors are loaded with
+// 16-byte loads, converted to f32 ONCE, and scattered into every output row/tap that uses them, so
+// per output element the kernel issues ~4 loads/conversions instead of 9 and keeps only one input
+// row live (registers -> occupancy).  fp32 accumulation, folded-BN shift + activation, bf16 store.
+// ------------------------------------------------------------------------------------------
+template <int S, int TW, int TH>
+__global__ void __launch_bounds__(256, 2)
+dwconv3x3_bf16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                      __nv_bfloat16* __restrict__ y, int B, int H, int W, int C, int Ho, int Wo, int act) {
+  constexpr int NCOL = (TW - 1) * S + 3, NROW = (TH - 1) * S + 3;
+  const int cv = C >> 3;
+  const int sw_ = (Wo + TW - 1) / TW, sh_ = (Ho + TH - 1) / TH;
+  const long long total = (long long)B * sh_ * sw_ * cv;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c0 = (int)(idx % cv) << 3;
+  long long p = idx / cv;
+  const int tw = (int)(p % sw_); p /= sw_;
+  const int th = (int)(p % sh_);
+  const int b = (int)(p / sh_);
+  const int wo0 = tw * TW, ho0 = th * TH;
+  const int wi0 = wo0 * S - 1, hi0 = ho0 * S - 1;
+  const float lo = act != B200SEG_ACT_NONE ? 0.f : -INFINITY, hi_ = act == B200SEG_ACT_RELU6 ? 6.f : INFINITY;
+
+  float acc[TH][TW][8];
+  {
+    const float4 b0 = bias ? __ldg(reinterpret_cast<const float4*>(bias + c0)) : make_float4(0, 0, 0, 0);
+    const float4 b1 = bias ? __ldg(reinterpret_cast<const float4*>(bias + c0 + 4)) : make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int o = 0; o < TH; ++o)
+#pragma unroll
+      for (int t = 0; t < TW; ++t) {
+        acc[o][t][0] = b0.x; acc[o][t][1] = b0.y; acc[o][t][2] = b0.z; acc[o][t][3] = b0.w;
+        acc[o][t][4] = b1.x; acc[o][t][5] = b1.y; acc[o][t][6] = b1.z; acc[o][t][7] = b1.w;
+      }
+  }
+  const __nv_bfloat16* xb = x + (long long)b * H * W * C + c0;
+#pragma unroll
+  for (int r = 0; r < NROW; ++r) {
+    const int hi = hi0 + r;
+    if (hi < 0 || hi >= H) continue;            // zero padding row: contributes nothing
+    const __nv_bfloat16* row = xb + (long long)hi * W * C;
+    uint4 raw[NCOL];
+#pragma unroll
+    for (int i = 0; i < NCOL; ++i) {
+      const int wi = wi0 + i;
+      raw[i] = (wi >= 0 && wi < W) ? __ldg(reinterpret_cast<const uint4*>(row + (long long)wi * C)) : make_uint4(0, 0, 0, 0);
+    }
+    float in[NCOL][8];
+#pragma unroll
+    for (int i = 0; i < NCOL; ++i) {
+      in[i][0] = bf16lo(raw[i].x); in[i][1] = bf16hi(raw[i].x); in[i][2] = bf16lo(raw[i].y); in[i][3] = bf16hi(raw[i].y);
+      in[i][4] = bf16lo(raw[i].z); in[i][5] = bf16hi(raw[i].z); in[i][6] = bf16lo(raw[i].w); in[i][7] = bf16hi(raw[i].w);
+    }
+#pragma unroll
+    for (int o = 0; o < TH; ++o) {
+      const int kh = r - o * S;                 // compile-time after unrolling
+      if (kh < 0 || kh > 2) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const float* wp = w + (kh * 3 + kw) * C + c0;
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp)), w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int t = 0; t < TW; ++t)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[o][t][j] = fmaf(in[t * S + kw][j], wv[j], acc[o][t][j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < TH; ++o) {
+    const int ho = ho0 + o;
+    if (ho >= Ho) continue;
+    __nv_bfloat16* yrow = y + (((long long)b * Ho + ho) * Wo) * C + c0;
+#pragma unroll
+    for (int t = 0; t < TW; ++t) {
+      const int wo = wo0 + t;
+      if (wo >= Wo) continue;
+      float* a = acc[o][t];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = fminf(fmaxf(a[j], lo), hi_);
+      uint4 v;
+      v.x = pack_bf16x2(a[0], a[1]); v.y = pack_bf16x2(a[2], a[3]);
+      v.z = pack_bf16x2(a[4], a[5]); v.w = pack_bf16x2(a[6], a[7]);
+      *reinterpret_cast<uint4*>(yrow + (long long)wo * C) = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// depthwise 3x3, bf16 NHWC, ROW-STREAMING: one thread owns TW output columns x 8 channels and walks
+// RH output rows downwards.  Every input row is loaded (16-byte loads) and converted to f32 exactly
+// once per thread and scattered into the (at most 3) output rows it feeds, which are held as rotating
+// f32 accumulators; a finished output row is clamped, packed and stored.  Compared with a per-output
+// gather this cuts loads + conversions per output element from 9 (or 4.5 with a 1-D strip) to
+// (TW*S+2)/TW * (RH+2)/RH ~ 2, and the L2->SM traffic of the vertical halo from 3x to (RH+2)/RH.
+// ------------------------------------------------------------------------------------------
+template <int S, int TW>
+struct DwRows {
+  static constexpr int NCOL = (TW - 1) * S + 3;
+  const __nv_bfloat16* xb;   // image base + channel offset
+  const float* w;            // [9][C] + channel offset
+  __nv_bfloat16* yb;
+  int H, W, C, Wo, wi0, wo0;
+  float lo, hi;
+  float bias8[8];
+
+  __device__ __forceinline__ void load_row(int hrow, float (&in)[NCOL][8]) const {
+    if (hrow < 0 || hrow >= H) {
+#pragma unroll
+      for (int i = 0; i < NCOL; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) in[i][j] = 0.f;
+      return;
+    }
+    const __nv_bfloat16* row = xb + (long long)hrow * W * C;
+    uint4 raw[NCOL];
+#pragma unroll
+    for (int i = 0; i < NCOL; ++i) {
+      const int wi = wi0 + i;
+      raw[i] = (wi >= 0 && wi < W) ? __ldg(reinterpret_cast<const uint4*>(row + (long long)wi * C)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < NCOL; ++i) {
+      in[i][0] = bf16lo(raw[i].x); in[i][1] = bf16hi(raw[i].x); in[i][2] = bf16lo(raw[i].y); in[i][3] = bf16hi(raw[i].y);
+      in[i][4] = bf16lo(raw[i].z); in[i][5] = bf16hi(raw[i].z); in[i][6] = bf16lo(raw[i].w); in[i][7] = bf16hi(raw[i].w);
+    }
+  }
+  __device__ __forceinline__ void mac(float (&acc)[TW][8], const float (&in)[NCOL][8], int kh) const {
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      // asm volatile: the 72 tap weights are loop invariant, but keeping them in registers would spill;
+      // they are re-read from L1 at every use instead
+      const float* wp = w + (kh * 3 + kw) * C;
+      float wv[8];
+      asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(wv[0]), "=f"(wv[1]), "=f"(wv[2]), "=f"(wv[3]) : "l"(wp));
+      asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(wv[4]), "=f"(wv[5]), "=f"(wv[6]), "=f"(wv[7]) : "l"(wp + 4));
+#pragma unroll
+      for (int t = 0; t < TW; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(in[t * S + kw][j], wv[j], acc[t][j]);
+    }
+  }
+  __device__ __forceinline__ void arm(float (&acc)[TW][8]) const {
+#pragma unroll
+    for (int t = 0; t < TW; ++t)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[t][j] = bias8[j];
+  }
+  // clamp + pack + store output row `ho` if it is inside [ho_lo, ho_hi)
+  __device__ __forceinline__ void store_row(const float (&acc)[TW][8], int ho, int ho_lo, int ho_hi) const {
+    if (ho >= ho_lo && ho < ho_hi) {
+      __nv_bfloat16* yrow = yb + (long long)ho * Wo * C;
+#pragma unroll
+      for (int t = 0; t < TW; ++t) {
+        if (wo0 + t < Wo) {
+          uint4 v;
+          float a[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] = fminf(fmaxf(acc[t][j], lo), hi);
+          v.x = pack_bf16x2(a[0], a[1]); v.y = pack_bf16x2(a[2], a[3]);
+          v.z = pack_bf16x2(a[4], a[5]); v.w = pack_bf16x2(a[6], a[7]);
+          *reinterpret_cast<uint4*>(yrow + (long long)(wo0 + t) * C) = v;
+        }
+      }
+    }
+  }
+};
+
+template <int S, int TW>
+__global__ void __launch_bounds__(256, 2)
+dwconv3x3_rows_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                      __nv_bfloat16* __restrict__ y, int B, int H, int W, int C, int Ho, int Wo, int RH, int act) {
+  using D = DwRows<S, TW>;
+  const int cv = C >> 3;
+  const int sw_ = (Wo + TW - 1) / TW, sh_ = (Ho + RH - 1) / RH;
+  const long long total = (long long)B * sh_ * sw_ * cv;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c0 = (int)(idx % cv) << 3;
+  long long p = idx / cv;
+  const int tw = (int)(p % sw_); p /= sw_;
+  const int rc = (int)(p % sh_);
+  const int b = (int)(p / sh_);
+  D d;
+  d.xb = x + (long long)b * H * W * C + c0;
+  d.w = w + c0;
+  d.yb = y + (long long)b * Ho * Wo * C + c0;
+  d.H = H; d.W = W; d.C = C; d.Wo = Wo;
+  d.wo0 = tw * TW; d.wi0 = d.wo0 * S - 1;
+  d.lo = act != B200SEG_ACT_NONE ? 0.f : -INFINITY;
+  d.hi = act == B200SEG_ACT_RELU6 ? 6.f : INFINITY;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) d.bias8[j] = bias ? __ldg(bias + c0 + j) : 0.f;
+  const int ho_lo = rc * RH, ho_hi = min(ho_lo + RH, Ho);
+  const int n_out = ho_hi - ho_lo;
+  float in[D::NCOL][8];
+  if (S == 1) {
+    // input row r (absolute ho_lo - 1 + r) feeds output rows ho_lo+r (kh=0), +r-1 (kh=1), +r-2 (kh=2);
+    // A0/A1/A2 hold those three partial rows and rotate by one register move per step.
+    float A0[TW][8], A1[TW][8], A2[TW][8];
+    d.arm(A0); d.arm(A1); d.arm(A2);
+    const int hi0 = ho_lo - 1;
+#pragma unroll 1
+    for (int r = 0; r < n_out + 2; ++r) {
+      d.load_row(hi0 + r, in);
+      d.mac(A0, in, 0); d.mac(A1, in, 1); d.mac(A2, in, 2);
+      d.store_row(A2, ho_lo + r - 2, ho_lo, ho_hi);
+#pragma unroll
+      for (int t = 0; t < TW; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { A2[t][j] = A1[t][j]; A1[t][j] = A0[t][j]; A0[t][j] = d.bias8[j]; }
+    }
+  } else {
+    // stride 2: output row o consumes input rows 2o (kh=0), 2o+1 (kh=1), 2o+2 (kh=2); the even input row
+    // 2o also finishes output row o-1.
+    float A0[TW][8], A1[TW][8];
+    d.arm(A0); d.arm(A1);
+    const int hi0 = 2 * ho_lo - 1;
+#pragma unroll 1
+    for (int o = 0; o <= n_out; ++o) {
+      d.load_row(hi0 + 2 * o, in);
+      d.mac(A0, in, 0); d.mac(A1, in, 2);
+      d.store_row(A1, ho_lo + o - 1, ho_lo, ho_hi);
+      if (o < n_out) { d.load_row(hi0 + 2 * o + 1, in); d.mac(A0, in, 1); }
+#pragma unroll
+      for (int t = 0; t < TW; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { A1[t][j] = A0[t][j]; A0[t][j] = d.bias8[j]; }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // y[b,ho,wo,0:Cs] = skip ; y[b,ho,wo,Cs:] = bilinear x2 (align_corners=False) of x.
-// One thread = one 16-byte channel vector of one output pixel.
-// PyTorch source index: src = max(0, 0.5*(dst+0.5)-0.5); i0=floor(src); i1=min(i0+1,in-1).
+// One thread = one 16-byte channel vector of a 2x2 block of output pixels: the 3x3 source
+// neighbourhood is loaded and converted once (9 loads for 4 outputs instead of 16) and the
+// interpolation is done separably -- for scale 2 the weights are exactly {0.25, 0.75}; clamped
+// neighbour indices reproduce PyTorch's border rule (src = max(0, (dst+0.5)/2 - 0.5)) because
+// 0.25*a + 0.75*a == a exactly in one fma.
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -296,43 +537,58 @@ upsample2x_concat_kernel(const T* __restrict__ skip, const T* __restrict__ x, T*
                          int w, int Cs, int Cu) {
   using V = Vec16<T>;
   constexpr int VN = V::N;
-  const int C = Cs + Cu, cv = C / VN, Ho = 2 * h, Wo = 2 * w;
-  const long long total = (long long)B * Ho * Wo * cv;
+  const int C = Cs + Cu, cv = C / VN, Wo = 2 * w;
+  const long long total = (long long)B * h * w * cv;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int c = (int)(idx % cv) * VN;
   long long p = idx / cv;
-  const int wo = (int)(p % Wo); p /= Wo;
-  const int ho = (int)(p % Ho);
-  const int b = (int)(p / Ho);
-  T* yp = y + (((long long)b * Ho + ho) * Wo + wo) * C + c;
+  const int j = (int)(p % w); p /= w;
+  const int i = (int)(p % h);
+  const int b = (int)(p / h);
+  T* y00 = y + (((long long)b * 2 * h + 2 * i) * Wo + 2 * j) * C + c;     // output pixel (2i, 2j)
+  const long long yrow = (long long)Wo * C;
   if (c < Cs) {
-    const uint4 t = __ldg(reinterpret_cast<const uint4*>(skip + (((long long)b * Ho + ho) * Wo + wo) * Cs + c));
-    *reinterpret_cast<uint4*>(yp) = t;
+    const T* s00 = skip + (((long long)b * 2 * h + 2 * i) * Wo + 2 * j) * Cs + c;
+    const long long srow = (long long)Wo * Cs;
+    const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(s00)), a1 = __ldg(reinterpret_cast<const uint4*>(s00 + Cs));
+    const uint4 a2 = __ldg(reinterpret_cast<const uint4*>(s00 + srow)), a3 = __ldg(reinterpret_cast<const uint4*>(s00 + srow + Cs));
+    *reinterpret_cast<uint4*>(y00) = a0; *reinterpret_cast<uint4*>(y00 + C) = a1;
+    *reinterpret_cast<uint4*>(y00 + yrow) = a2; *reinterpret_cast<uint4*>(y00 + yrow + C) = a3;
     return;
   }
   const int cu = c - Cs;
-  const float sy = fmaxf(0.5f * (ho + 0.5f) - 0.5f, 0.f), sx = fmaxf(0.5f * (wo + 0.5f) - 0.5f, 0.f);
-  const int y0 = (int)sy, x0 = (int)sx;
-  const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
-  const float ly = sy - y0, lx = sx - x0;
-  const float hy = 1.f - ly, hx = 1.f - lx;
+  const int ri[3] = {max(i - 1, 0), i, min(i + 1, h - 1)};
+  const int qj[3] = {max(j - 1, 0), j, min(j + 1, w - 1)};
   const T* xb = x + (long long)b * h * w * Cu + cu;
-  V a, bq, cq, d, o;
-  a.load(xb + ((long long)y0 * w + x0) * Cu);
-  bq.load(xb + ((long long)y0 * w + x1) * Cu);
-  cq.load(xb + ((long long)y1 * w + x0) * Cu);
-  d.load(xb + ((long long)y1 * w + x1) * Cu);
+  float te[3][VN], to[3][VN];     // vertically blended columns for the even / odd output row
 #pragma unroll
-  for (int j = 0; j < VN; ++j) o.v[j] = hy * (hx * a.v[j] + lx * bq.v[j]) + ly * (hx * cq.v[j] + lx * d.v[j]);
-  o.store(yp);
+  for (int q = 0; q < 3; ++q) {
+    V a, m, d;
+    a.load(xb + ((long long)ri[0] * w + qj[q]) * Cu);
+    m.load(xb + ((long long)ri[1] * w + qj[q]) * Cu);
+    d.load(xb + ((long long)ri[2] * w + qj[q]) * Cu);
+#pragma unroll
+    for (int k = 0; k < VN; ++k) {
+      te[q][k] = fmaf(m.v[k], 0.75f, 0.25f * a.v[k]);
+      to[q][k] = fmaf(m.v[k], 0.75f, 0.25f * d.v[k]);
+    }
+  }
+  V o;
+#pragma unroll
+  for (int k = 0; k < VN; ++k) o.v[k] = fmaf(te[1][k], 0.75f, 0.25f * te[0][k]);
+  o.store(y00);
+#pragma unroll
+  for (int k = 0; k < VN; ++k) o.v[k] = fmaf(te[1][k], 0.75f, 0.25f * te[2][k]);
+  o.store(y00 + C);
+#pragma unroll
+  for (int k = 0; k < VN; ++k) o.v[k] = fmaf(to[1][k], 0.75f, 0.25f * to[0][k]);
+  o.store(y00 + yrow);
+#pragma unroll
+  for (int k = 0; k < VN; ++k) o.v[k] = fmaf(to[1][k], 0.75f, 0.25f * to[2][k]);
+  o.store(y00 + yrow + C);
 }
 
-// ------------------------------------------------------------------------------------------
-// final bilinear x2, align_corners=True, NHWC logits [B,h,w,ldc] -> NCHW [B,C,2h,2w] (or argmax).
-// One thread = PPT consecutive output pixels along W; stores are contiguous along W per plane.
-// src = dst * (in-1)/(out-1)  (PyTorch area_pixel_compute_scale with align_corners)
-// ------------------------------------------------------------------------------------------
 // 16 channels of one NHWC pixel as floats (ldc == 16: 32 B bf16 / 64 B f32, 16-byte vector loads)
 template <typename T>
 __device__ __forceinline__ void load_px16(const T* p, float (&v)[16]);
@@ -542,7 +798,34 @@ int b200seg_dwconv3x3(const void* x, const float* w, const float* b, void* y, in
                                                                              B, H, W, C, Ho, Wo, act); \
   }
   if (dtype == B200SEG_BF16) {
-    if (stride == 1) LAUNCH(bf16, 1, 4) else LAUNCH(bf16, 2, 2)
+    static int variant = -1;      // tuning knob (B200SEG_DW_VARIANT): 0 = default
+    if (variant < 0) { const char* e = getenv("B200SEG_DW_VARIANT"); variant = e ? atoi(e) : 0; }
+#define LAUNCH2(S, TW, TH)                                                                                        \
+  {                                                                                                               \
+    const long long total = (long long)B * ((Ho + TH - 1) / TH) * ((Wo + TW - 1) / TW) * (C / 8);                 \
+    dwconv3x3_bf16_kernel<S, TW, TH><<<grid_for(total, threads), threads, 0, st>>>((const bf16*)x, w, b, (bf16*)y, \
+                                                                                   B, H, W, C, Ho, Wo, act);      \
+  }
+#define LAUNCH3(S, TW, RH)                                                                                       \
+  {                                                                                                               \
+    const long long total = (long long)B * ((Ho + RH - 1) / RH) * ((Wo + TW - 1) / TW) * (C / 8);                 \
+    dwconv3x3_rows_kernel<S, TW><<<grid_for(total, threads), threads, 0, st>>>((const bf16*)x, w, b, (bf16*)y, B, H, \
+                                                                               W, C, Ho, Wo, RH, act);            \
+  }
+    if (variant >= 10 && variant < 100) {      // row streaming: variant = 10*TW + log2(RH)  (e.g. 23 = TW 2, RH 8)
+      const int twv = variant / 10, rh = 1 << (variant % 10);
+      if (stride == 1) { if (twv == 1) LAUNCH3(1, 1, rh) else if (twv == 2) LAUNCH3(1, 2, rh) else LAUNCH3(1, 4, rh) }
+      else { if (twv == 1) LAUNCH3(2, 1, rh) else if (twv == 2) LAUNCH3(2, 2, rh) else LAUNCH3(2, 4, rh) }
+    } else
+    if (stride == 1) {
+      if (variant == 1) LAUNCH2(1, 2, 1) else if (variant == 2) LAUNCH2(1, 4, 1) else if (variant == 3) LAUNCH2(1, 4, 2)
+      else if (variant == 9) LAUNCH(bf16, 1, 4) else if (variant == 4) LAUNCH2(1, 2, 2) else LAUNCH2(1, 4, 2)   // default: 4x2 block (measured best)
+    } else {
+      if (variant == 1) LAUNCH2(2, 2, 1) else if (variant == 2) LAUNCH2(2, 4, 1) else if (variant == 3) LAUNCH2(2, 1, 2)
+      else if (variant == 9) LAUNCH(bf16, 2, 2) else if (variant == 4) LAUNCH2(2, 2, 2) else LAUNCH2(2, 4, 1)   // default: 4x1 strip (measured best)
+    }
+#undef LAUNCH2
+#undef LAUNCH3
   } else {
     if (stride == 1) LAUNCH(float, 1, 4) else LAUNCH(float, 2, 2)
   }
@@ -556,7 +839,7 @@ int b200seg_upsample2x_concat(const void* skip, const void* x, void* y, int dtyp
   B200_REQUIRE(dtype == B200SEG_BF16 || dtype == B200SEG_F32, "upsample2x_concat: bad dtype %d", dtype);
   B200_REQUIRE(Cs % vn == 0 && Cu % vn == 0 && Cu > 0 && Cs >= 0, "upsample2x_concat: Cs=%d Cu=%d must be multiples of %d", Cs, Cu, vn);
   B200_REQUIRE(B > 0 && h > 0 && w > 0, "upsample2x_concat: empty tensor");
-  const long long total = (long long)B * 4 * h * w * ((Cs + Cu) / vn);
+  const long long total = (long long)B * h * w * ((Cs + Cu) / vn);     // one thread per 2x2 output block x vector
   cudaStream_t st = (cudaStream_t)s;
   if (dtype == B200SEG_BF16)
     upsample2x_concat_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)skip, (const bf16*)x, (bf16*)y, B, h, w, Cs, Cu);

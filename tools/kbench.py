@@ -41,7 +41,7 @@ def conv_case(name, H, W, Cin, Cout, taps, res=False, flag_list=(0,)):
     nbytes = (x.numel() + out.numel() + w.numel() + (r.numel() if res else 0)) * 2
     flops = 2 * B * H * W * Cout * taps * Cin
     for fl in flag_list:
-        nm = f"conv_tc {name} {Cin}->{Cout} k{taps} @{H}x{W} flags={fl}"
+        nm = f"conv_tc {name} {Cin}->{Cout} k{taps} @{H}x{W} flags={fl} (res={1 - ((fl >> 2) & 1)} st={(fl >> 16) & 15} ps={(fl >> 20) & 3})"
         if flt and flt not in nm:
             continue
         us = timeit(lambda: ops.conv_tc(x, w, b, taps, 1, r, out=out, flags=fl))
@@ -49,20 +49,45 @@ def conv_case(name, H, W, Cin, Cout, taps, res=False, flag_list=(0,)):
 
 
 def main():
+    def F(res=1, stages=0, per_sm=0, halo=1):
+        return (0 if res else 4) | (0 if halo else 2) | (stages << 16) | (per_sm << 20)
+    if os.environ.get("KB_SWEEP"):
+        sweep = [F(r, st, ps) for r in (1, 0) for st in (2, 3, 4, 6) for ps in (0,)]
+        conv_case("up4.0", 128, 256, 80, 32, 9, flag_list=sweep)
+        conv_case("up4.3", 128, 256, 32, 32, 9, flag_list=sweep)
+        conv_case("up3.0", 64, 128, 152, 64, 9, flag_list=sweep)
+        conv_case("up3.3", 64, 128, 64, 64, 9, flag_list=sweep)
+        conv_case("up2.0", 32, 64, 288, 128, 9, flag_list=[F(1, st) for st in (3, 4, 6, 8)])
+        conv_case("up1.0", 16, 32, 1344, 256, 9, flag_list=[F(1, st) for st in (2, 3, 4)])
+        sweep1 = [F(r, st, ps) for r in (1, 0) for st in (2, 4, 6) for ps in (0, 1)]
+        conv_case("f2.expand", 128, 256, 16, 96, 1, flag_list=sweep1)
+        conv_case("f1.project", 128, 256, 32, 16, 1, flag_list=sweep1)
+        conv_case("f3.expand", 64, 128, 24, 144, 1, flag_list=sweep1)
+        conv_case("f5.expand", 32, 64, 32, 192, 1, flag_list=sweep1)
+        conv_case("f8.expand", 16, 32, 64, 384, 1, flag_list=[F(0, st) for st in (2, 4, 6)])
+        conv_case("f18", 8, 16, 320, 1280, 1, flag_list=[F(0, st) for st in (2, 3, 4)])
+        for (nm, H, W, C, s_) in (("f1.dw", 128, 256, 32, 1), ("f2.dw", 128, 256, 96, 2), ("f3.dw", 64, 128, 144, 1), ("f5.dw", 32, 64, 192, 1), ("f8.dw", 16, 32, 384, 1)):
+            x = rnd(B, H, W, C); w = rnd(9, C, dt=torch.float32); b = rnd(C, dt=torch.float32)
+            out = torch.empty(B, (H - 1) // s_ + 1, (W - 1) // s_ + 1, C, device=DEV, dtype=torch.bfloat16)
+            wd = ops.pack_dw_diag(w)
+            for fl in [F(r, st, ps) for r in (1, 0) for st in (2, 4, 6) for ps in (0, 1)]:
+                us = timeit(lambda: ops.dwconv3x3_tc(x, wd, b, s_, 2, out=out, flags=fl))
+                report(f"dw_tc {nm} C={C} s{s_} flags={fl} (res={1 - ((fl >> 2) & 1)} st={(fl >> 16) & 15} ps={(fl >> 20) & 3})", us, (x.numel() + out.numel()) * 2)
+        return
     FL3 = (0, 1, 2)                  # direct store | TMA store (3 staging buffers) | no halo
     conv_case("up4.0", 128, 256, 80, 32, 9, flag_list=FL3)
     conv_case("up4.3", 128, 256, 32, 32, 9, flag_list=FL3)
     conv_case("up3.0", 64, 128, 152, 64, 9, flag_list=FL3)
     conv_case("up3.3", 64, 128, 64, 64, 9, flag_list=FL3)
-    conv_case("up2.0", 32, 64, 288, 128, 9, flag_list=(0, 1))
-    conv_case("up2.3", 32, 64, 128, 128, 9, flag_list=(0, 1))
-    conv_case("up1.0", 16, 32, 1344, 256, 9, flag_list=(0, 1))
-    conv_case("up1.3", 16, 32, 256, 256, 9, flag_list=(0, 1))
-    conv_case("f2.expand", 128, 256, 16, 96, 1, flag_list=(0, 1, 37 << 8))
-    conv_case("f1.project", 128, 256, 32, 16, 1, flag_list=(0, 1, 37 << 8))
-    conv_case("f2.project", 64, 128, 96, 24, 1, flag_list=(0, 1))
-    conv_case("f3.expand", 64, 128, 24, 144, 1, flag_list=(0, 1))
-    conv_case("f3.project", 64, 128, 144, 24, 1, res=True, flag_list=(0, 1))
+    conv_case("up2.0", 32, 64, 288, 128, 9)
+    conv_case("up2.3", 32, 64, 128, 128, 9)
+    conv_case("up1.0", 16, 32, 1344, 256, 9)
+    conv_case("up1.3", 16, 32, 256, 256, 9)
+    conv_case("f2.expand", 128, 256, 16, 96, 1)
+    conv_case("f1.project", 128, 256, 32, 16, 1)
+    conv_case("f2.project", 64, 128, 96, 24, 1)
+    conv_case("f3.expand", 64, 128, 24, 144, 1)
+    conv_case("f3.project", 64, 128, 144, 24, 1, res=True)
     conv_case("f5.expand", 32, 64, 32, 192, 1)
     conv_case("f8.expand", 16, 32, 64, 384, 1)
     conv_case("f8.project", 16, 32, 384, 64, 1, res=True)
