@@ -108,6 +108,57 @@ int b200seg_maxpool2x2(const void* x, void* y, int dtype, int B, int H, int W, i
 int b200seg_softmax_ce(const float* logits, const int64_t* target, float* loss_sum, float* dlogits,
                        float grad_scale, int B, int C, int H, int W, b200seg_stream_t s);
 
+/* ---------------------------------------------------------------------------------------------
+ * Training path (train.py:35-39: model.train() forward, loss.backward()).  Activations NHWC viewed as
+ * [P = B*H*W pixels, C]; per-channel statistics are accumulated across CTAs in f64 buffers the caller
+ * zeroes.  dgrad of the dense convs reuses b200seg_conv_simt / b200seg_conv_tc with transposed weights.
+ * --------------------------------------------------------------------------------------------- */
+/* native_batch_norm (training): sum[c] += sum_p z, sumsq[c] += sum_p z^2 */
+int b200seg_bn_stats(const void* z, int dtype, long long P, int C, double* sum, double* sumsq, b200seg_stream_t s);
+/* mean/biased var -> invstd; scale = gamma*invstd, shift = beta - mean*scale; running stats updated with
+ * momentum and the unbiased variance (nn.BatchNorm2d defaults); running_* may be NULL. */
+int b200seg_bn_finalize(const double* sum, const double* sumsq, long long n, const float* gamma, const float* beta,
+                        float eps, float momentum, float* running_mean, float* running_var, float* mean,
+                        float* invstd, float* scale, float* shift, int C, b200seg_stream_t s);
+/* a = act(z*scale + shift) (+ res)   -- BN apply + ReLU/ReLU6 (+ inverted-residual shortcut) */
+int b200seg_bn_apply(const void* z, const float* scale, const float* shift, const void* res, void* a, int dtype,
+                     long long P, int C, int act, b200seg_stream_t s);
+/* native_batch_norm_backward + hardtanh/threshold_backward, pass 1: sg[c] += sum g, sgx[c] += sum g*xhat,
+ * g = da * act'(z*scale+shift), xhat = (z-mean)*invstd.   (d beta = sg, d gamma = sgx) */
+int b200seg_bn_bwd_reduce(const void* da, const void* z, const float* scale, const float* shift, const float* mean,
+                          const float* invstd, int dtype, long long P, int C, int act, double* sg, double* sgx,
+                          b200seg_stream_t s);
+/* pass 2: dz = scale * (g - sg/P - xhat * sgx/P) */
+int b200seg_bn_bwd_apply(const void* da, const void* z, const float* scale, const float* shift, const float* mean,
+                         const float* invstd, const double* sg, const double* sgx, void* dz, int dtype, long long P,
+                         int C, int act, b200seg_stream_t s);
+/* dz = da * act'(a_out) for a layer without BatchNorm */
+int b200seg_act_bwd(const void* da, const void* a_out, void* dz, int dtype, long long N, int act, b200seg_stream_t s);
+/* out[c] += sum_p x[p][c]  (bias gradients) ; f64 -> f32 with a scale */
+int b200seg_colsum(const void* x, int dtype, long long P, int C, double* out, b200seg_stream_t s);
+int b200seg_f64_to_f32(const double* in, float* out, int n, float scale, b200seg_stream_t s);
+/* convolution_backward (weight): dw f32 [Cout][taps][Cin] += sum_p dz[p][co] * x[p shifted by tap][ci]; caller zeroes dw */
+int b200seg_conv_wgrad(const void* x, const void* dz, float* dw, int dtype, int B, int H, int W, int Cin, int Cout,
+                       int taps, b200seg_stream_t s);
+/* depthwise backward: dx (+= acc_in) from dz with taps w f32 [9][C]; dw f64 [9][C] += ... (caller zeroes) */
+int b200seg_dw_dgrad(const void* dz, const float* w, const void* acc_in, void* dx, int dtype, int B, int H, int W,
+                     int C, int stride, b200seg_stream_t s);
+int b200seg_dw_wgrad(const void* x, const void* dz, double* dw, int dtype, int B, int H, int W, int C, int stride,
+                     b200seg_stream_t s);
+/* stem / first-conv weight gradient: x NCHW, dz NHWC, dw f32 [3][3][Cin][Cout] += ... (caller zeroes) */
+int b200seg_smallcin_wgrad(const void* x, int x_dtype, const void* dz, int dtype, float* dw, int B, int Cin, int H,
+                           int W, int Cout, int stride, b200seg_stream_t s);
+/* adjoint of b200seg_upsample2x_concat: dskip = dcat[..., :Cs] (+ acc_skip), dx = bilinear^T(dcat[..., Cs:]) */
+int b200seg_upcat_bwd(const void* dcat, const void* acc_skip, void* dskip, void* dx, int dtype, int B, int h, int w,
+                      int Cs, int Cu, b200seg_stream_t s);
+/* adjoint of b200seg_upsample2x_ac_nchw: dout NCHW f32 [B,C,2h,2w] -> dlogits NHWC [B,h,w,16] */
+int b200seg_final_bwd(const float* dout, void* dlogits, int dtype, int B, int h, int w, int C, b200seg_stream_t s);
+/* adjoint of b200seg_nhwc_to_nchw, and of b200seg_maxpool2x2 (gradient to the first maximum, += acc_in) */
+int b200seg_nchw_to_nhwc_pad(const float* x, void* y, int dtype, int B, int C, int H, int W, int ldc,
+                             b200seg_stream_t s);
+int b200seg_maxpool_bwd(const void* x, const void* dy, const void* acc_in, void* dx, int dtype, int B, int H, int W,
+                        int C, b200seg_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

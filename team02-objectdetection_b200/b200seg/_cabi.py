@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libb200seg.so")
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
 
-_vp, _i, _f = C.c_void_p, C.c_int, C.c_float
+_vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 
 # name -> argtypes (restype is always int unless noted)
 _PROTOS = {
@@ -33,6 +33,23 @@ _PROTOS = {
     "b200seg_nhwc_to_nchw": [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp],
     "b200seg_maxpool2x2": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "b200seg_softmax_ce": [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _vp],
+    # training path
+    "b200seg_bn_stats": [_vp, _i, _ll, _i, _vp, _vp, _vp],
+    "b200seg_bn_finalize": [_vp, _vp, _ll, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+    "b200seg_bn_apply": [_vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _vp],
+    "b200seg_bn_bwd_reduce": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _vp, _vp, _vp],
+    "b200seg_bn_bwd_apply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _vp],
+    "b200seg_act_bwd": [_vp, _vp, _vp, _i, _ll, _i, _vp],
+    "b200seg_colsum": [_vp, _i, _ll, _i, _vp, _vp],
+    "b200seg_f64_to_f32": [_vp, _vp, _i, _f, _vp],
+    "b200seg_conv_wgrad": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "b200seg_dw_dgrad": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "b200seg_dw_wgrad": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "b200seg_smallcin_wgrad": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "b200seg_upcat_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "b200seg_final_bwd": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "b200seg_nchw_to_nhwc_pad": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "b200seg_maxpool_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
 }
 EXPORTS = sorted(list(_PROTOS) + ["b200seg_last_error"])
 

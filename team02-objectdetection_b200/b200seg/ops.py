@@ -185,3 +185,138 @@ def softmax_ce(logits, target, want_grad: bool = True, grad_scale: Optional[floa
     check(lib.b200seg_softmax_ce(ptr(logits), ptr(target), ptr(loss_sum), ptr(dl), gs, B, Cc, H, W, _stream()),
           "softmax_ce")
     return loss_sum[0] / n, dl
+
+
+# ------------------------------------------------------------------------------------------------
+# training-path wrappers (train.py:35-39).  Activations are NHWC [B,H,W,C]; P = B*H*W.
+# ------------------------------------------------------------------------------------------------
+def _P(t):
+    return t.shape[0] * t.shape[1] * t.shape[2]
+
+
+def bn_train_forward(z, gamma, beta, running_mean, running_var, eps: float, momentum: float, act: int, res=None):
+    """Train-mode BatchNorm over NHWC z (+act, +residual).  Updates the running stats in place.
+    Returns (a, saved) where saved = (mean, invstd, scale, shift) for the backward pass."""
+    _cuda(z, gamma, beta, running_mean, running_var, res)
+    C, P = z.shape[-1], _P(z)
+    st = torch.zeros(2, C, device=z.device, dtype=torch.float64)
+    check(lib.b200seg_bn_stats(ptr(z), _dt(z), P, C, ptr(st[0]), ptr(st[1]), _stream()), "bn_stats")
+    sv = torch.empty(4, C, device=z.device, dtype=torch.float32)
+    check(lib.b200seg_bn_finalize(ptr(st[0]), ptr(st[1]), P, ptr(gamma), ptr(beta), eps, momentum, ptr(running_mean),
+                                  ptr(running_var), ptr(sv[0]), ptr(sv[1]), ptr(sv[2]), ptr(sv[3]), C, _stream()),
+          "bn_finalize")
+    a = torch.empty_like(z)
+    check(lib.b200seg_bn_apply(ptr(z), ptr(sv[2]), ptr(sv[3]), ptr(res), ptr(a), _dt(z), P, C, act, _stream()), "bn_apply")
+    return a, sv
+
+
+def bn_train_backward(da, z, sv, act: int):
+    """Returns (dz, dgamma f32[C], dbeta f32[C])."""
+    _cuda(da, z, sv)
+    C, P = z.shape[-1], _P(z)
+    red = torch.zeros(2, C, device=z.device, dtype=torch.float64)
+    check(lib.b200seg_bn_bwd_reduce(ptr(da), ptr(z), ptr(sv[2]), ptr(sv[3]), ptr(sv[0]), ptr(sv[1]), _dt(z), P, C, act,
+                                    ptr(red[0]), ptr(red[1]), _stream()), "bn_bwd_reduce")
+    dz = torch.empty_like(z)
+    check(lib.b200seg_bn_bwd_apply(ptr(da), ptr(z), ptr(sv[2]), ptr(sv[3]), ptr(sv[0]), ptr(sv[1]), ptr(red[0]), ptr(red[1]),
+                                   ptr(dz), _dt(z), P, C, act, _stream()), "bn_bwd_apply")
+    g32 = torch.empty(2, C, device=z.device, dtype=torch.float32)
+    check(lib.b200seg_f64_to_f32(ptr(red), ptr(g32), 2 * C, 1.0, _stream()), "f64_to_f32")
+    return dz, g32[1], g32[0]
+
+
+def act_bwd(da, a_out, act: int):
+    _cuda(da, a_out)
+    dz = torch.empty_like(da)
+    check(lib.b200seg_act_bwd(ptr(da), ptr(a_out), ptr(dz), _dt(da), da.numel(), act, _stream()), "act_bwd")
+    return dz
+
+
+def colsum(x):
+    """f32 [C] = sum over pixels of NHWC x."""
+    _cuda(x)
+    C = x.shape[-1]
+    acc = torch.zeros(C, device=x.device, dtype=torch.float64)
+    check(lib.b200seg_colsum(ptr(x), _dt(x), _P(x), C, ptr(acc), _stream()), "colsum")
+    out = torch.empty(C, device=x.device, dtype=torch.float32)
+    check(lib.b200seg_f64_to_f32(ptr(acc), ptr(out), C, 1.0, _stream()), "f64_to_f32")
+    return out
+
+
+def conv_wgrad(x, dz, taps: int):
+    """f32 [Cout, taps*Cin] = sum_p dz[p] (outer) im2col(x)[p]."""
+    _cuda(x, dz)
+    B, H, W, Cin = x.shape
+    Cout = dz.shape[-1]
+    dw = torch.zeros(Cout, taps * Cin, device=x.device, dtype=torch.float32)
+    check(lib.b200seg_conv_wgrad(ptr(x), ptr(dz), ptr(dw), _dt(x), B, H, W, Cin, Cout, taps, _stream()), "conv_wgrad")
+    return dw
+
+
+def dw_dgrad(dz, w9c, in_shape, stride: int, acc=None):
+    _cuda(dz, w9c, acc)
+    B, H, W, Cc = in_shape
+    dx = torch.empty(in_shape, device=dz.device, dtype=dz.dtype)
+    check(lib.b200seg_dw_dgrad(ptr(dz), ptr(w9c), ptr(acc), ptr(dx), _dt(dz), B, H, W, Cc, stride, _stream()), "dw_dgrad")
+    return dx
+
+
+def dw_wgrad(x, dz, stride: int):
+    """f32 [9, C]."""
+    _cuda(x, dz)
+    B, H, W, Cc = x.shape
+    acc = torch.zeros(9, Cc, device=x.device, dtype=torch.float64)
+    check(lib.b200seg_dw_wgrad(ptr(x), ptr(dz), ptr(acc), _dt(x), B, H, W, Cc, stride, _stream()), "dw_wgrad")
+    out = torch.empty(9, Cc, device=x.device, dtype=torch.float32)
+    check(lib.b200seg_f64_to_f32(ptr(acc), ptr(out), 9 * Cc, 1.0, _stream()), "f64_to_f32")
+    return out
+
+
+def smallcin_wgrad(x_nchw, dz, stride: int):
+    """f32 [3,3,Cin,Cout]."""
+    _cuda(x_nchw, dz)
+    B, Cin, H, W = x_nchw.shape
+    Cout = dz.shape[-1]
+    dw = torch.zeros(3, 3, Cin, Cout, device=dz.device, dtype=torch.float32)
+    check(lib.b200seg_smallcin_wgrad(ptr(x_nchw), _dt(x_nchw), ptr(dz), _dt(dz), ptr(dw), B, Cin, H, W, Cout, stride,
+                                     _stream()), "smallcin_wgrad")
+    return dw
+
+
+def upcat_bwd(dcat, Cs: int, acc_skip=None):
+    """Returns (dskip [B,2h,2w,Cs] (+acc_skip), dx [B,h,w,Cu])."""
+    _cuda(dcat, acc_skip)
+    B, H2, W2, Cc = dcat.shape
+    h, w, Cu = H2 // 2, W2 // 2, Cc - Cs
+    dskip = torch.empty(B, H2, W2, Cs, device=dcat.device, dtype=dcat.dtype)
+    dx = torch.empty(B, h, w, Cu, device=dcat.device, dtype=dcat.dtype)
+    check(lib.b200seg_upcat_bwd(ptr(dcat), ptr(acc_skip), ptr(dskip), ptr(dx), _dt(dcat), B, h, w, Cs, Cu, _stream()),
+          "upcat_bwd")
+    return dskip, dx
+
+
+def final_bwd(dout_nchw, sdt):
+    """dout NCHW f32 [B,C,2h,2w] -> NHWC [B,h,w,16] of dtype sdt."""
+    _cuda(dout_nchw)
+    if dout_nchw.dtype != torch.float32:
+        raise TypeError("final_bwd expects f32 upstream gradients")
+    B, Cc, H2, W2 = dout_nchw.shape
+    dl = torch.empty(B, H2 // 2, W2 // 2, 16, device=dout_nchw.device, dtype=sdt)
+    check(lib.b200seg_final_bwd(ptr(dout_nchw), ptr(dl), _dt(dl), B, H2 // 2, W2 // 2, Cc, _stream()), "final_bwd")
+    return dl
+
+
+def nchw_to_nhwc_pad(x_nchw, ldc: int, sdt):
+    _cuda(x_nchw)
+    B, Cc, H, W = x_nchw.shape
+    y = torch.empty(B, H, W, ldc, device=x_nchw.device, dtype=sdt)
+    check(lib.b200seg_nchw_to_nhwc_pad(ptr(x_nchw), ptr(y), _dt(y), B, Cc, H, W, ldc, _stream()), "nchw_to_nhwc_pad")
+    return y
+
+
+def maxpool_bwd(x, dy, acc=None):
+    _cuda(x, dy, acc)
+    B, H, W, Cc = x.shape
+    dx = torch.empty_like(x)
+    check(lib.b200seg_maxpool_bwd(ptr(x), ptr(dy), ptr(acc), ptr(dx), _dt(x), B, H, W, Cc, _stream()), "maxpool_bwd")
+    return dx

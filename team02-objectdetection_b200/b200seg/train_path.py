@@ -1,0 +1,177 @@
+"""Training forward/backward of the drop-in models (model.train(): train.py:24,36,38).
+
+One ``torch.autograd.Function`` spans the whole network: ``forward`` runs the fused step schedule with
+train-mode BatchNorm (batch statistics, running-stat update, ``num_batches_tracked += 1``) and keeps, per
+layer, the pre-BN conv output ``z``, the BN statistics and the activation output; ``backward`` walks the
+schedule in reverse and returns one gradient per used parameter, so ``loss.backward()`` /
+``optimizer.step()`` at the reference call sites work unchanged.  ``backbone.classifier`` is not on the path:
+its ``.grad`` stays ``None`` exactly as in the reference (SURVEY finding 5).
+
+Kernels: forward convs and the dense data gradients (same conv with transposed/flipped weights) go through
+``conv_simt`` (f32) or ``conv_tc`` (bf16); everything else is in csrc/train_ops.cu.  Gradient accumulation for
+tensors with two consumers (skip connections, block inputs with a shortcut) rides on the conv kernels'
+``+residual`` epilogue or the ``acc`` argument of the adjoint kernels -- there is no separate add pass.
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import torch
+
+from . import ops
+from .ops import ACT_NONE
+
+
+def _train_params(engine) -> List[torch.nn.Parameter]:
+    ps = []
+    for s in engine.steps:
+        if s.conv is not None:
+            ps.append(s.conv.weight)
+            if s.conv.bias is not None:
+                ps.append(s.conv.bias)
+        if s.bn is not None:
+            ps += [s.bn.weight, s.bn.bias]
+    return ps
+
+
+def _mode(engine, x) -> str:
+    mode = engine._mode(x)
+    return mode
+
+
+class _TrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine, x, *params):
+        mode = _mode(engine, x)
+        sdt = torch.bfloat16 if mode == "bf16" else torch.float32
+        tc = mode == "bf16" and (engine.dense_impl or "tc") == "tc"
+        x = x.contiguous()
+        env: Dict[str, torch.Tensor] = {"x": x}
+        saved: Dict[str, dict] = {}
+        with torch.no_grad():
+            for s in engine.steps:
+                rec: dict = {}
+                if s.op in ("stem", "dw", "dense"):
+                    w = s.conv.weight.detach().float()
+                    cout = w.shape[0]
+                    bias = s.conv.bias.detach().float() if s.conv.bias is not None else None
+                    src = env[s.src]
+                    if s.op == "stem":
+                        rec["wp"] = w.permute(2, 3, 1, 0).contiguous()
+                        z = ops.conv3x3_smallcin(src, rec["wp"], bias, s.stride, ACT_NONE, sdt)
+                    elif s.op == "dw":
+                        rec["wp"] = w.reshape(cout, 9).t().contiguous()
+                        z = ops.dwconv3x3(src, rec["wp"], bias, s.stride, ACT_NONE)
+                    else:
+                        wk = w.permute(0, 2, 3, 1).reshape(cout, -1)
+                        if s.pad_cout and cout < s.pad_cout:
+                            wk = torch.cat([wk, wk.new_zeros(s.pad_cout - cout, wk.shape[1])], 0)
+                            if bias is not None:
+                                bias = torch.cat([bias, bias.new_zeros(s.pad_cout - cout)], 0)
+                        rec["wk"] = wk.contiguous()
+                        if tc:
+                            z = ops.conv_tc(src, rec["wk"].to(torch.bfloat16), bias, s.taps, ACT_NONE, None, flags=engine.tc_flags)
+                        else:
+                            z = ops.conv_simt(src, rec["wk"], bias, s.taps, ACT_NONE, None)
+                    rec["z"] = z
+                    if s.bn is not None:
+                        res = env[s.res] if (s.op == "dense" and s.res) else None
+                        a, sv = ops.bn_train_forward(z, s.bn.weight.detach().float(), s.bn.bias.detach().float(),
+                                                     s.bn.running_mean, s.bn.running_var, s.bn.eps,
+                                                     s.bn.momentum if s.bn.momentum is not None else 0.1, s.act, res)
+                        s.bn.num_batches_tracked += 1
+                        rec["sv"] = sv
+                        env[s.dst] = a
+                    else:
+                        env[s.dst] = z
+                elif s.op == "upcat":
+                    env[s.dst] = ops.upsample2x_concat(env[s.res], env[s.src])
+                elif s.op == "pool":
+                    env[s.dst] = ops.maxpool2x2(env[s.src])
+                elif s.op == "final":
+                    env[s.dst] = ops.upsample2x_ac_nchw(env[s.src], engine.out_ch, torch.float32)
+                elif s.op == "to_nchw":
+                    env[s.dst] = ops.nhwc_to_nchw(env[s.src], engine.out_ch, torch.float32)
+                else:  # pragma: no cover
+                    raise AssertionError(s.op)
+                saved[s.name] = rec
+        ctx.engine, ctx.env, ctx.saved, ctx.mode, ctx.sdt, ctx.tc = engine, env, saved, mode, sdt, tc
+        ctx.n_params = len(params)
+        out = env["out"]
+        return out.to(x.dtype) if x.dtype != torch.float32 else out
+
+    @staticmethod
+    def backward(ctx, dout):
+        engine, env, saved, sdt, tc = ctx.engine, ctx.env, ctx.saved, ctx.sdt, ctx.tc
+        g: Dict[str, torch.Tensor] = {"out": dout.float().contiguous()}
+        pgrad: Dict[int, torch.Tensor] = {}
+        with torch.no_grad():
+            for s in reversed(engine.steps):
+                rec = saved[s.name]
+                if s.op == "final":
+                    g[s.src] = ops.final_bwd(g.pop(s.dst), sdt)
+                elif s.op == "to_nchw":
+                    g[s.src] = ops.nchw_to_nhwc_pad(g.pop(s.dst), env[s.src].shape[-1], sdt)
+                elif s.op == "upcat":
+                    dcat = g.pop(s.dst)
+                    cs = env[s.res].shape[-1]
+                    dskip, dx = ops.upcat_bwd(dcat, cs, g.get(s.res))
+                    g[s.res] = dskip
+                    assert s.src not in g
+                    g[s.src] = dx
+                elif s.op == "pool":
+                    g[s.src] = ops.maxpool_bwd(env[s.src], g.pop(s.dst), g.get(s.src))
+                else:
+                    da = g.pop(s.dst)
+                    z = rec["z"]
+                    if s.bn is not None:
+                        if s.op == "dense" and s.res:           # shortcut: the same gradient flows to the block input
+                            assert s.res not in g
+                            g[s.res] = da
+                        dz, dgamma, dbeta = ops.bn_train_backward(da, z, rec["sv"], s.act)
+                        pgrad[id(s.bn.weight)] = dgamma
+                        pgrad[id(s.bn.bias)] = dbeta
+                    else:
+                        dz = da                                   # conv + bias only (the last 1x1 of outconv)
+                    w = s.conv.weight
+                    cout = w.shape[0]
+                    if s.conv.bias is not None:
+                        pgrad[id(s.conv.bias)] = ops.colsum(dz)[:cout].contiguous()
+                    src = env[s.src]
+                    if s.op == "stem":
+                        dwp = ops.smallcin_wgrad(src, dz, s.stride)            # [3,3,Cin,Cout]
+                        pgrad[id(w)] = dwp.permute(3, 2, 0, 1).contiguous()
+                    elif s.op == "dw":
+                        dw9 = ops.dw_wgrad(src, dz, s.stride)                  # [9,C]
+                        pgrad[id(w)] = dw9.t().reshape(cout, 1, 3, 3).contiguous()
+                        g[s.src] = ops.dw_dgrad(dz, rec["wp"], tuple(src.shape), s.stride, g.get(s.src))
+                    else:
+                        cin = src.shape[-1]
+                        k = 3 if s.taps == 9 else 1
+                        dwk = ops.conv_wgrad(src, dz, s.taps)                  # [Cout_pad, taps*Cin]
+                        pgrad[id(w)] = dwk[:cout].reshape(cout, k, k, cin).permute(0, 3, 1, 2).contiguous()
+                        # dgrad = the same conv with W transposed (and the 3x3 taps flipped)
+                        wk = rec["wk"]                                          # [Cout_pad, taps*Cin]
+                        cp = wk.shape[0]
+                        wt = wk.reshape(cp, k, k, cin).flip(1, 2).permute(3, 1, 2, 0).reshape(cin, -1).contiguous()
+                        if tc:
+                            g[s.src] = ops.conv_tc(dz, wt.to(torch.bfloat16), None, s.taps, ACT_NONE, g.get(s.src),
+                                                   flags=engine.tc_flags)
+                        else:
+                            g[s.src] = ops.conv_simt(dz, wt, None, s.taps, ACT_NONE, g.get(s.src))
+        params = _train_params(engine)
+        grads = []
+        for p in params:
+            gr = pgrad.get(id(p))
+            grads.append(gr.to(p.dtype) if gr is not None else None)
+        ctx.env = ctx.saved = None
+        return (None, None, *grads)
+
+
+def forward_train(engine, x: torch.Tensor) -> torch.Tensor:
+    params = _train_params(engine)
+    engine._check_input(x)
+    if not torch.is_grad_enabled():
+        # model.train() under no_grad (e.g. BN calibration): forward only, still updates running stats
+        return _TrainFn.apply(engine, x, *[p.detach() for p in params])
+    return _TrainFn.apply(engine, x, *params)

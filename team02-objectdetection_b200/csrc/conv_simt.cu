@@ -69,6 +69,13 @@ conv_simt_kernel(const T* __restrict__ x, const float* __restrict__ w, const flo
       Bs[lk + i][lrow] = bv[i];
     }
     __syncthreads();
+    // blocked summation: the 16 products of this K chunk are summed first and only then added to the running
+    // total, so the rounding error grows with sqrt(K/16) instead of sqrt(K) (K reaches 12096 in up1.conv.0)
+    float part[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) part[i][j] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < SM_BK; ++kk) {
       const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
@@ -77,8 +84,12 @@ conv_simt_kernel(const T* __restrict__ x, const float* __restrict__ w, const flo
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) part[i][j] = fmaf(a[i], b[j], part[i][j]);
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] += part[i][j];
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {

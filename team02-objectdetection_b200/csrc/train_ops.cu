@@ -1,0 +1,808 @@
+// train_ops.cu -- kernels that exist only on the training path (train.py:35-39): train-mode BatchNorm
+// (batch statistics, apply, backward), weight gradients, depthwise backward, the adjoints of the two
+// bilinear upsamplings / concat / maxpool.  NHWC activations in storage type T (f32 or bf16), all
+// arithmetic and all reductions in f32, cross-CTA accumulation of per-channel statistics in f64.
+//
+// Dense data gradients (dgrad) need no kernel of their own: dgrad of a stride-1 "same" convolution is
+// the same convolution with the weights transposed (and the 3x3 taps flipped), so the engine calls
+// b200seg_conv_simt / b200seg_conv_tc with a re-packed weight tensor; its "+residual" epilogue doubles
+// as the gradient accumulation for tensors with two consumers.
+#include "common.cuh"
+
+namespace b200 {
+
+static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------
+// per-channel reductions over all pixels of an NHWC tensor viewed as [P, C]
+//   block = 32 channel-vectors (x) x 8 pixel lanes (y); grid = (pixel chunks, channel-vector tiles)
+//   per-thread partials in f32 over <= PIX_PER_BLOCK/8 pixels, block tree in smem, one f64 atomic
+//   per channel per block.
+// ---------------------------------------------------------------------------------------------
+constexpr int RED_PIX = 1024;   // pixels per block
+
+template <typename T, int NOUT, typename F>
+__device__ __forceinline__ void channel_reduce(long long P, int C, double* const* out, F&& f) {
+  using V = Vec16<T>;
+  constexpr int VN = V::N;
+  const int cvec = blockIdx.y * 32 + threadIdx.x;
+  const int c0 = cvec * VN;
+  const bool active = c0 < C;
+  float acc[NOUT][VN];
+#pragma unroll
+  for (int o = 0; o < NOUT; ++o)
+#pragma unroll
+    for (int j = 0; j < VN; ++j) acc[o][j] = 0.f;
+  if (active) {
+    const long long p0 = (long long)blockIdx.x * RED_PIX, p1 = min(p0 + RED_PIX, P);
+    for (long long p = p0 + threadIdx.y; p < p1; p += 8) f(p, c0, acc);
+  }
+  __shared__ float red[8][32][VN + 1];
+#pragma unroll
+  for (int o = 0; o < NOUT; ++o) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < VN; ++j) red[threadIdx.y][threadIdx.x][j] = acc[o][j];
+    __syncthreads();
+    if (threadIdx.y == 0 && active) {
+#pragma unroll
+      for (int j = 0; j < VN; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) s += (double)red[y][threadIdx.x][j];
+        atomicAdd(out[o] + c0 + j, s);
+      }
+    }
+  }
+}
+
+// sum and sum of squares (BatchNorm batch statistics)
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const T* __restrict__ z, long long P, int C, double* sum, double* sumsq) {
+  using V = Vec16<T>;
+  double* const outs[2] = {sum, sumsq};
+  channel_reduce<T, 2>(P, C, outs, [&](long long p, int c0, float (&acc)[2][V::N]) {
+    V v;
+    v.load(z + p * C + c0);
+#pragma unroll
+    for (int j = 0; j < V::N; ++j) { acc[0][j] += v.v[j]; acc[1][j] = fmaf(v.v[j], v.v[j], acc[1][j]); }
+  });
+}
+
+// one thread per channel: mean, biased var -> invstd, fused scale/shift, running-stat update
+// (momentum 0.1, unbiased variance), exactly nn.BatchNorm2d in training mode.
+__global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sumsq, long long n,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* running_mean, float* running_var, float* mean_out,
+                                   float* invstd_out, float* scale_out, float* shift_out, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = sum[c] / (double)n;
+  double var = sumsq[c] / (double)n - m * m;
+  if (var < 0.0) var = 0.0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float sc = gamma[c] * invstd;
+  mean_out[c] = (float)m;
+  invstd_out[c] = invstd;
+  scale_out[c] = sc;
+  shift_out[c] = beta[c] - (float)m * sc;
+  if (running_mean) {
+    const double unbiased = n > 1 ? var * ((double)n / (double)(n - 1)) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// a = act(z * scale + shift) (+ residual)
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const T* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
+                const T* __restrict__ res, T* __restrict__ a, long long P, int C, int act) {
+  using V = Vec16<T>;
+  constexpr int VN = V::N;
+  const int cv = C / VN;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P * cv) return;
+  const int c0 = (int)(idx % cv) * VN;
+  const long long off = (idx / cv) * C + c0;
+  V v, r, o;
+  v.load(z + off);
+  if (res) r.load(res + off);
+#pragma unroll
+  for (int j = 0; j < VN; ++j) {
+    float u = apply_act_rt(fmaf(v.v[j], __ldg(scale + c0 + j), __ldg(shift + c0 + j)), act);
+    o.v[j] = res ? u + r.v[j] : u;
+  }
+  o.store(a + off);
+}
+
+// gradient of the activation evaluated at u = z*scale + shift
+__device__ __forceinline__ float act_grad(float u, int act) {
+  if (act == B200SEG_ACT_RELU) return u > 0.f ? 1.f : 0.f;
+  if (act == B200SEG_ACT_RELU6) return (u > 0.f && u < 6.f) ? 1.f : 0.f;
+  return 1.f;
+}
+
+// sum(g) and sum(g * xhat) with g = da * act'(u), xhat = (z - mean) * invstd
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ z, const float* __restrict__ scale,
+                     const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
+                     long long P, int C, int act, double* sg, double* sgx) {
+  using V = Vec16<T>;
+  double* const outs[2] = {sg, sgx};
+  channel_reduce<T, 2>(P, C, outs, [&](long long p, int c0, float (&acc)[2][V::N]) {
+    V d, v;
+    d.load(da + p * C + c0);
+    v.load(z + p * C + c0);
+#pragma unroll
+    for (int j = 0; j < V::N; ++j) {
+      const float u = fmaf(v.v[j], __ldg(scale + c0 + j), __ldg(shift + c0 + j));
+      const float g = d.v[j] * act_grad(u, act);
+      acc[0][j] += g;
+      acc[1][j] = fmaf(g, (v.v[j] - __ldg(mean + c0 + j)) * __ldg(invstd + c0 + j), acc[1][j]);
+    }
+  });
+}
+
+// dz = scale * (g - sum(g)/n - xhat * sum(g*xhat)/n)        (scale = gamma * invstd)
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const T* __restrict__ da, const T* __restrict__ z, const float* __restrict__ scale,
+                    const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
+                    const double* __restrict__ sg, const double* __restrict__ sgx, long long n, T* __restrict__ dz,
+                    long long P, int C, int act) {
+  using V = Vec16<T>;
+  constexpr int VN = V::N;
+  const int cv = C / VN;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P * cv) return;
+  const int c0 = (int)(idx % cv) * VN;
+  const long long off = (idx / cv) * C + c0;
+  V d, v, o;
+  d.load(da + off);
+  v.load(z + off);
+  const float inv_n = 1.f / (float)n;
+#pragma unroll
+  for (int j = 0; j < VN; ++j) {
+    const float sc = __ldg(scale + c0 + j);
+    const float u = fmaf(v.v[j], sc, __ldg(shift + c0 + j));
+    const float g = d.v[j] * act_grad(u, act);
+    const float xh = (v.v[j] - __ldg(mean + c0 + j)) * __ldg(invstd + c0 + j);
+    o.v[j] = sc * (g - (float)sg[c0 + j] * inv_n - xh * ((float)sgx[c0 + j] * inv_n));
+  }
+  o.store(dz + off);
+}
+
+// dz = da * act'(z + bias) for a conv+bias(+act) layer without BatchNorm; also used with act = NONE as a cast/copy
+template <typename T>
+__global__ void __launch_bounds__(256)
+act_bwd_kernel(const T* __restrict__ da, const T* __restrict__ a_out, T* __restrict__ dz, long long N, int act) {
+  using V = Vec16<T>;
+  const long long idx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * V::N;
+  if (idx >= N) return;
+  V d, o, v;
+  d.load(da + idx);
+  v.load(a_out + idx);
+#pragma unroll
+  for (int j = 0; j < V::N; ++j) o.v[j] = d.v[j] * act_grad(v.v[j], act);
+  o.store(dz + idx);
+}
+
+// per-channel column sum (bias gradients)
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ x, long long P, int C, double* out) {
+  using V = Vec16<T>;
+  double* const outs[1] = {out};
+  channel_reduce<T, 1>(P, C, outs, [&](long long p, int c0, float (&acc)[1][V::N]) {
+    V v;
+    v.load(x + p * C + c0);
+#pragma unroll
+    for (int j = 0; j < V::N; ++j) acc[0][j] += v.v[j];
+  });
+}
+
+__global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, int n, float scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i] * scale;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dense weight gradient: dW[co][tap][ci] += sum_p dz[p][co] * x[p shifted by tap][ci]
+// implicit GEMM with the PIXELS as the reduction axis, split over blockIdx.z, f32 atomics at the end.
+// tile 64 (co) x 64 (k = tap*Cin+ci), 16 pixels per smem step, 4x4 outputs per thread.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dz, float* __restrict__ dw, int B, int H, int W,
+                  int Cin, int Cout, int taps, long long pix_per_split) {
+  __shared__ float Ds[16][64 + 4];
+  __shared__ float Xs[16][64 + 4];
+  const int K = taps * Cin;
+  const long long P = (long long)B * H * W;
+  const int k0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  const long long p_begin = (long long)blockIdx.z * pix_per_split, p_end = min(p_begin + pix_per_split, P);
+  const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
+  const int lp = tid / 16, l4 = (tid % 16) * 4;     // loader: pixel lane, 4 consecutive columns
+  const int kk = k0 + l4;
+  int tap = 0, ci = 0, dh = 0, dwv = 0;
+  const bool k_ok = kk < K;
+  if (k_ok) {
+    tap = kk / Cin; ci = kk - tap * Cin;
+    if (taps == 9) { dh = tap / 3 - 1; dwv = tap % 3 - 1; }
+  }
+  const int co = n0 + l4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (long long pb = p_begin; pb < p_end; pb += 16) {
+    const long long p = pb + lp;
+    float dv[4] = {0.f, 0.f, 0.f, 0.f}, xv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p < p_end) {
+      if (co < Cout) {
+        const T* dp = dz + p * Cout + co;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (co + i < Cout) dv[i] = to_f32<T>(dp[i]);
+      }
+      if (k_ok) {
+        const int w_ = (int)(p % W);
+        const long long t = p / W;
+        const int h_ = (int)(t % H);
+        const int b_ = (int)(t / H);
+        const int hi = h_ + dh, wi = w_ + dwv;
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) {
+          const T* xp = x + (((long long)b_ * H + hi) * W + wi) * Cin + ci;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) xv[i] = to_f32<T>(xp[i]);   // Cin % 4 == 0: the 4 columns share the tap
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { Ds[lp][l4 + i] = dv[i]; Xs[lp][l4 + i] = xv[i]; }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&Ds[q][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Xs[q][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + ty * 4 + i;
+    if (n >= Cout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx * 4 + j;
+      if (k < K) atomicAdd(dw + (long long)n * K + k, acc[i][j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// depthwise 3x3 backward
+// ---------------------------------------------------------------------------------------------
+// dx[hi][wi][c] = sum over taps with (hi+1-kh) = S*ho, (wi+1-kw) = S*wo of dz[ho][wo][c] * w[kh*3+kw][c]
+template <typename T>
+__global__ void __launch_bounds__(256)
+dw_dgrad_kernel(const T* __restrict__ dz, const float* __restrict__ w, const T* __restrict__ acc_in, T* __restrict__ dx,
+                int B, int H, int W, int C, int Ho, int Wo, int S) {
+  using V = Vec16<T>;
+  constexpr int VN = V::N;
+  const int cv = C / VN;
+  const long long total = (long long)B * H * W * cv;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c0 = (int)(idx % cv) * VN;
+  long long p = idx / cv;
+  const int wi = (int)(p % W); p /= W;
+  const int hi = (int)(p % H);
+  const int b = (int)(p / H);
+  V o;
+  if (acc_in) o.load(acc_in + (((long long)b * H + hi) * W + wi) * C + c0);
+  else {
+#pragma unroll
+    for (int j = 0; j < VN; ++j) o.v[j] = 0.f;
+  }
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) {
+    const int th = hi + 1 - kh;
+    if (th < 0 || th % S) continue;
+    const int ho = th / S;
+    if (ho >= Ho) continue;
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int tw = wi + 1 - kw;
+      if (tw < 0 || tw % S) continue;
+      const int wo = tw / S;
+      if (wo >= Wo) continue;
+      V d;
+      d.load(dz + (((long long)b * Ho + ho) * Wo + wo) * C + c0);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) o.v[j] = fmaf(d.v[j], __ldg(w + (kh * 3 + kw) * C + c0 + j), o.v[j]);
+    }
+  }
+  o.store(dx + (((long long)b * H + hi) * W + wi) * C + c0);
+}
+
+// dw[tap][c] += sum_p dz[p][c] * x[p*S + tap - 1][c]
+template <typename T>
+__global__ void __launch_bounds__(256)
+dw_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dz, int B, int H, int W, int C, int Ho, int Wo, int S,
+                double* dw /* [9][C] */) {
+  using V = Vec16<T>;
+  constexpr int VN = V::N;
+  const long long P = (long long)B * Ho * Wo;
+  double* outs[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) outs[t] = dw + (long long)t * C;
+  channel_reduce<T, 9>(P, C, outs, [&](long long p, int c0, float (&acc)[9][VN]) {
+    const int wo = (int)(p % Wo);
+    const long long t = p / Wo;
+    const int ho = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    V d;
+    d.load(dz + p * C + c0);
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int hi = ho * S - 1 + kh;
+      if (hi < 0 || hi >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int wi = wo * S - 1 + kw;
+        if (wi < 0 || wi >= W) continue;
+        V xv;
+        xv.load(x + (((long long)b * H + hi) * W + wi) * C + c0);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) acc[kh * 3 + kw][j] = fmaf(d.v[j], xv.v[j], acc[kh * 3 + kw][j]);
+      }
+    }
+  });
+}
+
+// stem / first conv weight gradient: x NCHW [B,Cin<=4,H,W], dz NHWC [B,Ho,Wo,Cout]; dw f32 [3][3][Cin][Cout]
+template <typename TI, typename T>
+__global__ void __launch_bounds__(256)
+smallcin_wgrad_kernel(const TI* __restrict__ x, const T* __restrict__ dz, float* __restrict__ dw, int B, int Cin, int H,
+                      int W, int Cout, int Ho, int Wo, int S, int pix_per_block) {
+  extern __shared__ float sm[];            // [PIXB][Cout] dz, then [PIXB][9*Cin] patches
+  constexpr int PIXB = 32;
+  float* sd = sm;
+  float* sx = sm + PIXB * Cout;
+  const int KK = 9 * Cin;
+  const long long P = (long long)B * Ho * Wo;
+  const long long p_begin = (long long)blockIdx.x * pix_per_block, p_end = min(p_begin + pix_per_block, P);
+  const int npairs = KK * Cout;
+  float acc[8];                            // up to 8 (k, co) pairs per thread: KK*Cout <= 2048
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (long long pb = p_begin; pb < p_end; pb += PIXB) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < PIXB * Cout; i += blockDim.x) {
+      const long long p = pb + i / Cout;
+      sd[i] = p < p_end ? to_f32<T>(dz[p * Cout + i % Cout]) : 0.f;
+    }
+    for (int i = threadIdx.x; i < PIXB * KK; i += blockDim.x) {
+      const long long p = pb + i / KK;
+      const int k = i % KK;
+      float v = 0.f;
+      if (p < p_end) {
+        const int wo = (int)(p % Wo);
+        const long long t = p / Wo;
+        const int ho = (int)(t % Ho);
+        const int b = (int)(t / Ho);
+        const int tap = k / Cin, c = k % Cin;
+        const int hi = ho * S - 1 + tap / 3, wi = wo * S - 1 + tap % 3;
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = to_f32<TI>(x[(((long long)b * Cin + c) * H + hi) * W + wi]);
+      }
+      sx[i] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int pr = threadIdx.x + i * 256;
+      if (pr < npairs) {
+        const int k = pr / Cout, co = pr % Cout;
+        float s = 0.f;
+#pragma unroll 8
+        for (int q = 0; q < PIXB; ++q) s = fmaf(sx[q * KK + k], sd[q * Cout + co], s);
+        acc[i] += s;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int pr = threadIdx.x + i * 256;
+    if (pr < npairs) atomicAdd(dw + pr, acc[i]);     // layout [tap][c][co] == pr
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// adjoints of the bilinear upsamplings.  Gather form: every source pixel enumerates the few output
+// pixels that read it and re-evaluates PyTorch's forward index/weight formula for each, so clamped
+// borders are exact by construction.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bil_weight_ac_false(int r, int i, int n_in) {
+  // weight with which output index r reads input index i (scale 2, align_corners=False)
+  const float s = fmaxf(0.5f * (r + 0.5f) - 0.5f, 0.f);
+  const int i0 = (int)s;
+  const int i1 = min(i0 + 1, n_in - 1);
+  const float l = s - i0;
+  return (i0 == i ? 1.f - l : 0.f) + (i1 == i ? l : 0.f);
+}
+__device__ __forceinline__ float bil_weight_ac_true(int r, int i, int n_in, float scale) {
+  const float s = scale * r;
+  const int i0 = (int)s;
+  const int i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+  const float l = s - i0;
+  return (i0 == i ? 1.f - l : 0.f) + (i1 == i ? l : 0.f);
+}
+
+// dcat [B,2h,2w,Cs+Cu] -> dskip [B,2h,2w,Cs] (+= acc_skip) and dx [B,h,w,Cu]
+template <typename T>
+__global__ void __launch_bounds__(256)
+upcat_bwd_kernel(const T* __restrict__ dcat, const T* __restrict__ acc_skip, T* __restrict__ dskip, T* __restrict__ dx,
+                 int B, int h, int w, int Cs, int Cu) {
+  using V = Vec16<T>;
+  constexpr int VN = V::N;
+  const int C = Cs + Cu, cv = C / VN, Ho = 2 * h, Wo = 2 * w;
+  const long long total = (long long)B * h * w * cv;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % cv) * VN;
+  long long p = idx / cv;
+  const int j = (int)(p % w); p /= w;
+  const int i = (int)(p % h);
+  const int b = (int)(p / h);
+  if (c < Cs) {          // the skip half: plain slice (+ accumulation of the skip tensor's other gradient)
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const long long pix = ((long long)b * Ho + 2 * i + a) * Wo + 2 * j + q;
+        V v, u;
+        v.load(dcat + pix * C + c);
+        if (acc_skip) {
+          u.load(acc_skip + pix * Cs + c);
+#pragma unroll
+          for (int k = 0; k < VN; ++k) v.v[k] += u.v[k];
+        }
+        v.store(dskip + pix * Cs + c);
+      }
+    return;
+  }
+  const int cu = c - Cs;
+  float acc[VN];
+#pragma unroll
+  for (int k = 0; k < VN; ++k) acc[k] = 0.f;
+  for (int r = max(2 * i - 1, 0); r <= min(2 * i + 2, Ho - 1); ++r) {
+    const float wy = bil_weight_ac_false(r, i, h);
+    if (wy == 0.f) continue;
+    for (int q = max(2 * j - 1, 0); q <= min(2 * j + 2, Wo - 1); ++q) {
+      const float wx = bil_weight_ac_false(q, j, w);
+      if (wx == 0.f) continue;
+      V v;
+      v.load(dcat + (((long long)b * Ho + r) * Wo + q) * C + c);
+#pragma unroll
+      for (int k = 0; k < VN; ++k) acc[k] = fmaf(wy * wx, v.v[k], acc[k]);
+    }
+  }
+  V o;
+#pragma unroll
+  for (int k = 0; k < VN; ++k) o.v[k] = acc[k];
+  o.store(dx + (((long long)b * h + i) * w + j) * Cu + cu);
+}
+
+// dout NCHW f32 [B,C,2h,2w] -> dlogits NHWC T [B,h,w,16] (channels >= C zero), align_corners=True
+template <typename T>
+__global__ void __launch_bounds__(256)
+final_bwd_kernel(const float* __restrict__ dout, T* __restrict__ dl, int B, int h, int w, int C) {
+  const int Ho = 2 * h, Wo = 2 * w;
+  const long long total = (long long)B * h * w;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int j = (int)(idx % w);
+  long long p = idx / w;
+  const int i = (int)(p % h);
+  const int b = (int)(p / h);
+  const float sch = (Ho > 1) ? (float)(h - 1) / (float)(Ho - 1) : 0.f;
+  const float scw = (Wo > 1) ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
+  float acc[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+  const int r_lo = max(2 * i - 2, 0), r_hi = min(2 * i + 3, Ho - 1);
+  const int q_lo = max(2 * j - 2, 0), q_hi = min(2 * j + 3, Wo - 1);
+  for (int r = r_lo; r <= r_hi; ++r) {
+    const float wy = bil_weight_ac_true(r, i, h, sch);
+    if (wy == 0.f) continue;
+    for (int q = q_lo; q <= q_hi; ++q) {
+      const float wx = bil_weight_ac_true(q, j, w, scw);
+      if (wx == 0.f) continue;
+      const float ww = wy * wx;
+      const float* dp = dout + ((long long)b * C * Ho + r) * Wo + q;
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        if (c < C) acc[c] = fmaf(ww, __ldg(dp + (long long)c * Ho * Wo), acc[c]);
+    }
+  }
+  T* op = dl + idx * 16;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) op[c] = from_f32<T>(acc[c]);
+}
+
+// NCHW f32 [B,C,H,W] -> NHWC T [B,H,W,ldc] zero padded (plain UNet: gradient of nhwc_to_nchw)
+template <typename T>
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_pad_kernel(const float* __restrict__ x, T* __restrict__ y, int B, int C, long long HW, int ldc) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * HW) return;
+  const int b = (int)(idx / HW);
+  const long long pix = idx % HW;
+  for (int c = 0; c < ldc; ++c)
+    y[idx * ldc + c] = from_f32<T>(c < C ? x[((long long)b * C + c) * HW + pix] : 0.f);
+}
+
+// MaxPool2d(2) backward: the gradient goes to the first maximum of the window (PyTorch rule)
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __restrict__ acc_in, T* __restrict__ dx,
+                   int B, int H, int W, int C) {
+  using V = Vec16<T>;
+  constexpr int VN = V::N;
+  const int Ho = H / 2, Wo = W / 2, cv = C / VN;
+  const long long total = (long long)B * Ho * Wo * cv;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % cv) * VN;
+  long long p = idx / cv;
+  const int wo = (int)(p % Wo); p /= Wo;
+  const int ho = (int)(p % Ho);
+  const int b = (int)(p / Ho);
+  const long long o00 = (((long long)b * H + 2 * ho) * W + 2 * wo) * C + c;
+  const long long offs[4] = {o00, o00 + C, o00 + (long long)W * C, o00 + (long long)W * C + C};
+  V xv[4], g, out[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) xv[q].load(x + offs[q]);
+  g.load(dy + (((long long)b * Ho + ho) * Wo + wo) * C + c);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (acc_in) out[q].load(acc_in + offs[q]);
+    else {
+#pragma unroll
+      for (int k = 0; k < VN; ++k) out[q].v[k] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < VN; ++k) {
+    int best = 0;
+    float bv = xv[0].v[k];
+#pragma unroll
+    for (int q = 1; q < 4; ++q)
+      if (xv[q].v[k] > bv) { bv = xv[q].v[k]; best = q; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q == best) out[q].v[k] += g.v[k];
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) out[q].store(dx + offs[q]);
+}
+
+}  // namespace b200
+
+using namespace b200;
+typedef __nv_bfloat16 bf16;
+
+#define DISPATCH_T(dtype, CALL_F32, CALL_BF16, name)                    \
+  if ((dtype) == B200SEG_F32) { CALL_F32; }                            \
+  else if ((dtype) == B200SEG_BF16) { CALL_BF16; }                     \
+  else return set_error(-1, name ": bad dtype %d", (int)(dtype));
+
+extern "C" {
+
+int b200seg_bn_stats(const void* z, int dtype, long long P, int C, double* sum, double* sumsq, b200seg_stream_t s) {
+  const int vn = dtype == B200SEG_BF16 ? 8 : 4;
+  B200_REQUIRE(P > 0 && C > 0 && C % vn == 0, "bn_stats: P=%lld C=%d (C must be a multiple of %d)", P, C, vn);
+  dim3 grid(cdiv(P, RED_PIX), cdiv(C / vn, 32)), block(32, 8);
+  cudaStream_t st = (cudaStream_t)s;
+  DISPATCH_T(dtype, (bn_stats_kernel<float><<<grid, block, 0, st>>>((const float*)z, P, C, sum, sumsq)),
+             (bn_stats_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)z, P, C, sum, sumsq)), "bn_stats")
+  return check_launch("bn_stats");
+}
+
+int b200seg_bn_finalize(const double* sum, const double* sumsq, long long n, const float* gamma, const float* beta,
+                        float eps, float momentum, float* running_mean, float* running_var, float* mean,
+                        float* invstd, float* scale, float* shift, int C, b200seg_stream_t s) {
+  B200_REQUIRE(C > 0 && n > 0, "bn_finalize: C=%d n=%lld", C, n);
+  bn_finalize_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)s>>>(sum, sumsq, n, gamma, beta, eps, momentum, running_mean,
+                                                                 running_var, mean, invstd, scale, shift, C);
+  return check_launch("bn_finalize");
+}
+
+int b200seg_bn_apply(const void* z, const float* scale, const float* shift, const void* res, void* a, int dtype,
+                     long long P, int C, int act, b200seg_stream_t s) {
+  const int vn = dtype == B200SEG_BF16 ? 8 : 4;
+  B200_REQUIRE(P > 0 && C > 0 && C % vn == 0, "bn_apply: P=%lld C=%d", P, C);
+  const unsigned g = cdiv(P * (C / vn), 256);
+  cudaStream_t st = (cudaStream_t)s;
+  DISPATCH_T(dtype, (bn_apply_kernel<float><<<g, 256, 0, st>>>((const float*)z, scale, shift, (const float*)res, (float*)a, P, C, act)),
+             (bn_apply_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)z, scale, shift, (const bf16*)res, (bf16*)a, P, C, act)), "bn_apply")
+  return check_launch("bn_apply");
+}
+
+int b200seg_bn_bwd_reduce(const void* da, const void* z, const float* scale, const float* shift, const float* mean,
+                          const float* invstd, int dtype, long long P, int C, int act, double* sg, double* sgx,
+                          b200seg_stream_t s) {
+  const int vn = dtype == B200SEG_BF16 ? 8 : 4;
+  B200_REQUIRE(P > 0 && C > 0 && C % vn == 0, "bn_bwd_reduce: P=%lld C=%d", P, C);
+  dim3 grid(cdiv(P, RED_PIX), cdiv(C / vn, 32)), block(32, 8);
+  cudaStream_t st = (cudaStream_t)s;
+  DISPATCH_T(dtype, (bn_bwd_reduce_kernel<float><<<grid, block, 0, st>>>((const float*)da, (const float*)z, scale, shift, mean, invstd, P, C, act, sg, sgx)),
+             (bn_bwd_reduce_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)da, (const bf16*)z, scale, shift, mean, invstd, P, C, act, sg, sgx)), "bn_bwd_reduce")
+  return check_launch("bn_bwd_reduce");
+}
+
+int b200seg_bn_bwd_apply(const void* da, const void* z, const float* scale, const float* shift, const float* mean,
+                         const float* invstd, const double* sg, const double* sgx, void* dz, int dtype, long long P,
+                         int C, int act, b200seg_stream_t s) {
+  const int vn = dtype == B200SEG_BF16 ? 8 : 4;
+  B200_REQUIRE(P > 0 && C > 0 && C % vn == 0, "bn_bwd_apply: P=%lld C=%d", P, C);
+  const unsigned g = cdiv(P * (C / vn), 256);
+  cudaStream_t st = (cudaStream_t)s;
+  DISPATCH_T(dtype, (bn_bwd_apply_kernel<float><<<g, 256, 0, st>>>((const float*)da, (const float*)z, scale, shift, mean, invstd, sg, sgx, P, (float*)dz, P, C, act)),
+             (bn_bwd_apply_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)da, (const bf16*)z, scale, shift, mean, invstd, sg, sgx, P, (bf16*)dz, P, C, act)), "bn_bwd_apply")
+  return check_launch("bn_bwd_apply");
+}
+
+int b200seg_act_bwd(const void* da, const void* a_out, void* dz, int dtype, long long N, int act, b200seg_stream_t s) {
+  const int vn = dtype == B200SEG_BF16 ? 8 : 4;
+  B200_REQUIRE(N > 0 && N % vn == 0, "act_bwd: N=%lld", N);
+  const unsigned g = cdiv(N / vn, 256);
+  cudaStream_t st = (cudaStream_t)s;
+  DISPATCH_T(dtype, (act_bwd_kernel<float><<<g, 256, 0, st>>>((const float*)da, (const float*)a_out, (float*)dz, N, act)),
+             (act_bwd_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)da, (const bf16*)a_out, (bf16*)dz, N, act)), "act_bwd")
+  return check_launch("act_bwd");
+}
+
+int b200seg_colsum(const void* x, int dtype, long long P, int C, double* out, b200seg_stream_t s) {
+  const int vn = dtype == B200SEG_BF16 ? 8 : 4;
+  B200_REQUIRE(P > 0 && C > 0 && C % vn == 0, "colsum: P=%lld C=%d", P, C);
+  dim3 grid(cdiv(P, RED_PIX), cdiv(C / vn, 32)), block(32, 8);
+  cudaStream_t st = (cudaStream_t)s;
+  DISPATCH_T(dtype, (colsum_kernel<float><<<grid, block, 0, st>>>((const float*)x, P, C, out)),
+             (colsum_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)x, P, C, out)), "colsum")
+  return check_launch("colsum");
+}
+
+int b200seg_f64_to_f32(const double* in, float* out, int n, float scale, b200seg_stream_t s) {
+  B200_REQUIRE(n > 0, "f64_to_f32: n=%d", n);
+  f64_to_f32_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)s>>>(in, out, n, scale);
+  return check_launch("f64_to_f32");
+}
+
+int b200seg_conv_wgrad(const void* x, const void* dz, float* dw, int dtype, int B, int H, int W, int Cin, int Cout,
+                       int taps, b200seg_stream_t s) {
+  B200_REQUIRE(taps == 1 || taps == 9, "conv_wgrad: taps=%d", taps);
+  B200_REQUIRE(Cin > 0 && Cin % 4 == 0 && Cout > 0, "conv_wgrad: Cin=%d must be a multiple of 4", Cin);
+  B200_REQUIRE(B > 0 && H > 0 && W > 0, "conv_wgrad: empty tensor");
+  const long long P = (long long)B * H * W;
+  const int K = taps * Cin;
+  const unsigned gx = cdiv(K, 64), gy = cdiv(Cout, 64);
+  // enough pixel splits for ~4 waves of CTAs, at least 256 pixels each
+  long long splits = ((long long)sm_count() * 8 + (long long)gx * gy - 1) / ((long long)gx * gy);
+  if (splits > P / 256) splits = P / 256;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  long long pps = (P + splits - 1) / splits;
+  pps = (pps + 15) / 16 * 16;
+  splits = (P + pps - 1) / pps;
+  dim3 grid(gx, gy, (unsigned)splits);
+  cudaStream_t st = (cudaStream_t)s;
+  DISPATCH_T(dtype, (conv_wgrad_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (const float*)dz, dw, B, H, W, Cin, Cout, taps, pps)),
+             (conv_wgrad_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, (const bf16*)dz, dw, B, H, W, Cin, Cout, taps, pps)), "conv_wgrad")
+  return check_launch("conv_wgrad");
+}
+
+int b200seg_dw_dgrad(const void* dz, const float* w, const void* acc_in, void* dx, int dtype, int B, int H, int W,
+                     int C, int stride, b200seg_stream_t s) {
+  const int vn = dtype == B200SEG_BF16 ? 8 : 4;
+  B200_REQUIRE(C > 0 && C % vn == 0 && (stride == 1 || stride == 2), "dw_dgrad: C=%d stride=%d", C, stride);
+  B200_REQUIRE(B > 0 && H > 0 && W > 0, "dw_dgrad: empty tensor");
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const unsigned g = cdiv((long long)B * H * W * (C / vn), 256);
+  cudaStream_t st = (cudaStream_t)s;
+  DISPATCH_T(dtype, (dw_dgrad_kernel<float><<<g, 256, 0, st>>>((const float*)dz, w, (const float*)acc_in, (float*)dx, B, H, W, C, Ho, Wo, stride)),
+             (dw_dgrad_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)dz, w, (const bf16*)acc_in, (bf16*)dx, B, H, W, C, Ho, Wo, stride)), "dw_dgrad")
+  return check_launch("dw_dgrad");
+}
+
+int b200seg_dw_wgrad(const void* x, const void* dz, double* dw, int dtype, int B, int H, int W, int C, int stride,
+                     b200seg_stream_t s) {
+  const int vn = dtype == B200SEG_BF16 ? 8 : 4;
+  B200_REQUIRE(C > 0 && C % vn == 0 && (stride == 1 || stride == 2), "dw_wgrad: C=%d stride=%d", C, stride);
+  B200_REQUIRE(B > 0 && H > 0 && W > 0, "dw_wgrad: empty tensor");
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const long long P = (long long)B * Ho * Wo;
+  dim3 grid(cdiv(P, RED_PIX), cdiv(C / vn, 32)), block(32, 8);
+  cudaStream_t st = (cudaStream_t)s;
+  DISPATCH_T(dtype, (dw_wgrad_kernel<float><<<grid, block, 0, st>>>((const float*)x, (const float*)dz, B, H, W, C, Ho, Wo, stride, dw)),
+             (dw_wgrad_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)x, (const bf16*)dz, B, H, W, C, Ho, Wo, stride, dw)), "dw_wgrad")
+  return check_launch("dw_wgrad");
+}
+
+int b200seg_smallcin_wgrad(const void* x, int x_dtype, const void* dz, int dtype, float* dw, int B, int Cin, int H,
+                           int W, int Cout, int stride, b200seg_stream_t s) {
+  B200_REQUIRE(Cin >= 1 && Cin <= 4 && Cout > 0 && 9 * Cin * Cout <= 2048, "smallcin_wgrad: Cin=%d Cout=%d", Cin, Cout);
+  B200_REQUIRE(stride == 1 || stride == 2, "smallcin_wgrad: stride=%d", stride);
+  B200_REQUIRE(B > 0 && H > 0 && W > 0, "smallcin_wgrad: empty tensor");
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const long long P = (long long)B * Ho * Wo;
+  long long blocks = (long long)sm_count() * 4;
+  long long ppb = (P + blocks - 1) / blocks;
+  ppb = (ppb + 31) / 32 * 32;
+  blocks = (P + ppb - 1) / ppb;
+  const size_t smem = (size_t)32 * (Cout + 9 * Cin) * sizeof(float);
+  cudaStream_t st = (cudaStream_t)s;
+#define LAUNCH(TI, T) smallcin_wgrad_kernel<TI, T><<<(unsigned)blocks, 256, smem, st>>>((const TI*)x, (const T*)dz, dw, B, Cin, H, W, Cout, Ho, Wo, stride, (int)ppb)
+  if (x_dtype == B200SEG_F32 && dtype == B200SEG_F32) LAUNCH(float, float);
+  else if (x_dtype == B200SEG_F32 && dtype == B200SEG_BF16) LAUNCH(float, bf16);
+  else if (x_dtype == B200SEG_BF16 && dtype == B200SEG_BF16) LAUNCH(bf16, bf16);
+  else if (x_dtype == B200SEG_BF16 && dtype == B200SEG_F32) LAUNCH(bf16, float);
+  else return set_error(-1, "smallcin_wgrad: bad dtypes");
+#undef LAUNCH
+  return check_launch("smallcin_wgrad");
+}
+
+int b200seg_upcat_bwd(const void* dcat, const void* acc_skip, void* dskip, void* dx, int dtype, int B, int h, int w,
+                      int Cs, int Cu, b200seg_stream_t s) {
+  const int vn = dtype == B200SEG_BF16 ? 8 : 4;
+  B200_REQUIRE(Cs % vn == 0 && Cu % vn == 0 && Cu > 0 && Cs >= 0, "upcat_bwd: Cs=%d Cu=%d", Cs, Cu);
+  B200_REQUIRE(B > 0 && h > 0 && w > 0, "upcat_bwd: empty tensor");
+  const unsigned g = cdiv((long long)B * h * w * ((Cs + Cu) / vn), 256);
+  cudaStream_t st = (cudaStream_t)s;
+  DISPATCH_T(dtype, (upcat_bwd_kernel<float><<<g, 256, 0, st>>>((const float*)dcat, (const float*)acc_skip, (float*)dskip, (float*)dx, B, h, w, Cs, Cu)),
+             (upcat_bwd_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)dcat, (const bf16*)acc_skip, (bf16*)dskip, (bf16*)dx, B, h, w, Cs, Cu)), "upcat_bwd")
+  return check_launch("upcat_bwd");
+}
+
+int b200seg_final_bwd(const float* dout, void* dlogits, int dtype, int B, int h, int w, int C, b200seg_stream_t s) {
+  B200_REQUIRE(C >= 1 && C <= 16 && B > 0 && h > 0 && w > 0, "final_bwd: bad shape");
+  const unsigned g = cdiv((long long)B * h * w, 256);
+  cudaStream_t st = (cudaStream_t)s;
+  DISPATCH_T(dtype, (final_bwd_kernel<float><<<g, 256, 0, st>>>(dout, (float*)dlogits, B, h, w, C)),
+             (final_bwd_kernel<bf16><<<g, 256, 0, st>>>(dout, (bf16*)dlogits, B, h, w, C)), "final_bwd")
+  return check_launch("final_bwd");
+}
+
+int b200seg_nchw_to_nhwc_pad(const float* x, void* y, int dtype, int B, int C, int H, int W, int ldc,
+                             b200seg_stream_t s) {
+  B200_REQUIRE(C >= 1 && ldc >= C && B > 0 && H > 0 && W > 0, "nchw_to_nhwc_pad: bad shape");
+  const long long HW = (long long)H * W;
+  const unsigned g = cdiv((long long)B * HW, 256);
+  cudaStream_t st = (cudaStream_t)s;
+  DISPATCH_T(dtype, (nchw_to_nhwc_pad_kernel<float><<<g, 256, 0, st>>>(x, (float*)y, B, C, HW, ldc)),
+             (nchw_to_nhwc_pad_kernel<bf16><<<g, 256, 0, st>>>(x, (bf16*)y, B, C, HW, ldc)), "nchw_to_nhwc_pad")
+  return check_launch("nchw_to_nhwc_pad");
+}
+
+int b200seg_maxpool_bwd(const void* x, const void* dy, const void* acc_in, void* dx, int dtype, int B, int H, int W,
+                        int C, b200seg_stream_t s) {
+  const int vn = dtype == B200SEG_BF16 ? 8 : 4;
+  B200_REQUIRE(C % vn == 0 && H % 2 == 0 && W % 2 == 0 && B > 0 && H > 0 && W > 0, "maxpool_bwd: bad shape");
+  const unsigned g = cdiv((long long)B * (H / 2) * (W / 2) * (C / vn), 256);
+  cudaStream_t st = (cudaStream_t)s;
+  DISPATCH_T(dtype, (maxpool_bwd_kernel<float><<<g, 256, 0, st>>>((const float*)x, (const float*)dy, (const float*)acc_in, (float*)dx, B, H, W, C)),
+             (maxpool_bwd_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)x, (const bf16*)dy, (const bf16*)acc_in, (bf16*)dx, B, H, W, C)), "maxpool_bwd")
+  return check_launch("maxpool_bwd");
+}
+
+}  // extern "C"
