@@ -1,0 +1,135 @@
+"""Training-step benchmark (BASELINE config[2]): MobileNetV2UNet fwd + pixel CE + bwd + Adam, batch 32 per GPU at
+3x256x512, data parallel over the ranks.  Invoked as `python bench.py --workload train ...` (same launch contract
+as the inference bench; see bench.py).
+
+A step is exactly the reference's loop body (train.py:35-39): optimizer.zero_grad(); outputs = model(inputs);
+loss = criterion(outputs, targets); loss.backward(); optimizer.step() -- with torch.optim.Adam(lr=1.5e-4)
+(main.py:100) and, for N>1, the bucketed gradient all-reduce of b200seg.dp overlapped with backward.
+"""
+import json
+import os
+import sys
+
+import torch
+
+H, W, NCLS = 256, 512, 10
+
+
+def run_train(args, dev, dist, world, rank, pk):
+    import b200seg
+    from b200seg import dp, train_path
+    from bench import ClockSampler
+    B = args.batch or 32
+    precision = os.environ.get("B200SEG_TRAIN_PRECISION", "bf16")     # bf16 activations + tcgen05 convs, fp32 master weights
+    torch.manual_seed(0)
+    model = b200seg.MobileNetV2UNet(output_channels=NCLS).to(dev)
+    eng = model._get_engine()
+    eng.precision = precision
+    if dist is not None:
+        dp.broadcast_model(model)
+        dp.attach(model)
+    criterion = b200seg.CrossEntropyLoss()
+    optimizer = torch.optim.Adam(model.parameters(), lr=1.5e-4)       # main.py:100
+    model.train()
+    g = torch.Generator(device="cpu").manual_seed(rank)
+    nrot = 2
+    xs = [torch.randn(B, 3, H, W, generator=g).to(dev) for _ in range(nrot)]
+    ys = [torch.randint(0, NCLS, (B, H, W), generator=g).to(dev) for _ in range(nrot)]
+
+    def step(x, y):
+        optimizer.zero_grad()
+        out = model(x)
+        loss = criterion(out, y)
+        loss.backward()
+        optimizer.step()
+        return loss
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(xs[i % nrot], ys[i % nrot])
+    barrier()
+    clocks = ClockSampler(dev.index or 0)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = step(xs[i % nrot], ys[i % nrot])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    last_loss = float(loss)
+
+    # e2e: host (pinned) fp32 images + int64 labels in, loss.item() out, every step
+    xh = [torch.randn(B, 3, H, W, generator=g).pin_memory() for _ in range(2)]
+    yh = [torch.randint(0, NCLS, (B, H, W), generator=g).pin_memory() for _ in range(2)]
+
+    def e2e_steps(n):
+        for i in range(n):
+            x = xh[i & 1].to(dev, non_blocking=True)
+            y = yh[i & 1].to(dev, non_blocking=True)
+            step(x, y).item()                       # train.py:41-42 reads the loss every step
+
+    e2e_steps(2)
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    e2e_steps(args.steps)
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1)
+
+    # per-layer forward/backward times (CUDA events on the launch stream), one extra step
+    train_path.TRACE = []
+    step(xs[0], ys[0])
+    torch.cuda.synchronize()
+    tr, train_path.TRACE = train_path.TRACE, None
+    agg = {}
+    for phase, name, a, b in tr:
+        agg[(phase, name)] = agg.get((phase, name), 0.0) + a.elapsed_time(b)
+    rows = sorted(agg.items(), key=lambda kv: -kv[1])
+    tot = sum(v for _, v in rows)
+    if args.breakdown and rank == 0:
+        print(f"{'phase':4s} {'layer':34s} {'ms':>9s} {'share':>6s}", file=sys.stderr)
+        for (phase, name), v in rows[:30]:
+            print(f"{phase:4s} {name:34s} {v:9.3f} {v / tot:6.1%}", file=sys.stderr)
+        print(f"sum fwd {sum(v for (p, _), v in rows if p == 'fwd'):.2f} ms, bwd {sum(v for (p, _), v in rows if p == 'bwd'):.2f} ms; "
+              f"step {ms / args.steps:.2f} ms", file=sys.stderr)
+
+    if dist is not None:
+        t = torch.tensor([ms, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    (top_phase, top_name), top_ms = rows[0]
+    # algorithmic model of the whole step: 353 MB/img bf16 activations (706 MB fp32), 34.5 GFLOP/img
+    bytes_img = 353e6 if precision == "bf16" else 706e6
+    step_s = ms / args.steps * 1e-3
+    line = {"metric": "MobileNetV2UNet training images/s", "value": B * world * args.steps / (ms * 1e-3), "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": f"MobileNetV2UNet training step (fwd + pixel CE + bwd + Adam), batch {B}/GPU, 3x{H}x{W}, {NCLS} classes "
+                                   f"(BASELINE config[2]); activations {precision}, fp32 master weights, torch.optim.Adam(lr=1.5e-4); "
+                                   f"data parallel, per-replica BatchNorm, bucketed all-reduce overlapped with backward",
+                       "global_batch": B * world, "l2": "~20 GB of activations per step >> 126 MB L2", "last_loss": last_loss},
+            "e2e": {"value": B * world * args.steps / (ms_e2e * 1e-3), "unit": "images/s",
+                    "h2d_bytes_per_step": B * 3 * H * W * 4 + B * H * W * 8, "d2h_bytes_per_step": 4,
+                    "api": "train.py:32-42 loop body: pinned fp32 images + int64 labels -> .to(device), step, loss.item()"},
+            "roofline": {"kernel": f"{top_phase}:{top_name} (layer-level; dense weight gradients still run on the FP32 pipes)",
+                         "bound": "hbm", "achieved": bytes_img * B / step_s / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                         "frac": bytes_img * B / step_s / 1e9 / pk["hbm"], "traffic": None, "peak_source": pk["src"],
+                         "note": "whole-step algorithmic bytes / step time; per-layer shares in --breakdown",
+                         "share_of_step": top_ms / tot},
+            "gpu_launches": None, "clocks": clk}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()

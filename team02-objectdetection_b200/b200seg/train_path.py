@@ -34,6 +34,17 @@ def _train_params(engine) -> List[torch.nn.Parameter]:
     return ps
 
 
+TRACE = None      # set to a list to collect (phase, step name, start event, end event) per schedule step
+
+
+def _tick():
+    if TRACE is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
 def _mode(engine, x) -> str:
     mode = engine._mode(x)
     return mode
@@ -51,6 +62,7 @@ class _TrainFn(torch.autograd.Function):
         with torch.no_grad():
             for s in engine.steps:
                 rec: dict = {}
+                _e0 = _tick()
                 if s.op in ("stem", "dw", "dense"):
                     w = s.conv.weight.detach().float()
                     cout = w.shape[0]
@@ -95,6 +107,8 @@ class _TrainFn(torch.autograd.Function):
                 else:  # pragma: no cover
                     raise AssertionError(s.op)
                 saved[s.name] = rec
+                if _e0 is not None:
+                    TRACE.append(("fwd", s.name, _e0, _tick()))
         ctx.engine, ctx.env, ctx.saved, ctx.mode, ctx.sdt, ctx.tc = engine, env, saved, mode, sdt, tc
         ctx.n_params = len(params)
         out = env["out"]
@@ -105,9 +119,20 @@ class _TrainFn(torch.autograd.Function):
         engine, env, saved, sdt, tc = ctx.engine, ctx.env, ctx.saved, ctx.sdt, ctx.tc
         g: Dict[str, torch.Tensor] = {"out": dout.float().contiguous()}
         pgrad: Dict[int, torch.Tensor] = {}
+        red = getattr(engine, "reducer", None)      # data parallel: bucketed all-reduce overlapped with backward
+        if red is not None:
+            red.reset()
+
+        class _Emit(dict):                           # pgrad[id(p)] = grad  ->  also feeds the reducer
+            def set(self, p, grad):
+                self[id(p)] = grad
+                if red is not None:
+                    red.add(p, grad)
+        pgrad = _Emit()
         with torch.no_grad():
             for s in reversed(engine.steps):
                 rec = saved[s.name]
+                _e0 = _tick()
                 if s.op == "final":
                     g[s.src] = ops.final_bwd(g.pop(s.dst), sdt)
                 elif s.op == "to_nchw":
@@ -129,27 +154,27 @@ class _TrainFn(torch.autograd.Function):
                             assert s.res not in g
                             g[s.res] = da
                         dz, dgamma, dbeta = ops.bn_train_backward(da, z, rec["sv"], s.act)
-                        pgrad[id(s.bn.weight)] = dgamma
-                        pgrad[id(s.bn.bias)] = dbeta
+                        pgrad.set(s.bn.weight, dgamma)
+                        pgrad.set(s.bn.bias, dbeta)
                     else:
                         dz = da                                   # conv + bias only (the last 1x1 of outconv)
                     w = s.conv.weight
                     cout = w.shape[0]
                     if s.conv.bias is not None:
-                        pgrad[id(s.conv.bias)] = ops.colsum(dz)[:cout].contiguous()
+                        pgrad.set(s.conv.bias, ops.colsum(dz)[:cout].contiguous())
                     src = env[s.src]
                     if s.op == "stem":
                         dwp = ops.smallcin_wgrad(src, dz, s.stride)            # [3,3,Cin,Cout]
-                        pgrad[id(w)] = dwp.permute(3, 2, 0, 1).contiguous()
+                        pgrad.set(w, dwp.permute(3, 2, 0, 1).contiguous())
                     elif s.op == "dw":
                         dw9 = ops.dw_wgrad(src, dz, s.stride)                  # [9,C]
-                        pgrad[id(w)] = dw9.t().reshape(cout, 1, 3, 3).contiguous()
+                        pgrad.set(w, dw9.t().reshape(cout, 1, 3, 3).contiguous())
                         g[s.src] = ops.dw_dgrad(dz, rec["wp"], tuple(src.shape), s.stride, g.get(s.src))
                     else:
                         cin = src.shape[-1]
                         k = 3 if s.taps == 9 else 1
                         dwk = ops.conv_wgrad(src, dz, s.taps)                  # [Cout_pad, taps*Cin]
-                        pgrad[id(w)] = dwk[:cout].reshape(cout, k, k, cin).permute(0, 3, 1, 2).contiguous()
+                        pgrad.set(w, dwk[:cout].reshape(cout, k, k, cin).permute(0, 3, 1, 2).contiguous())
                         # dgrad = the same conv with W transposed (and the 3x3 taps flipped)
                         wk = rec["wk"]                                          # [Cout_pad, taps*Cin]
                         cp = wk.shape[0]
@@ -159,8 +184,12 @@ class _TrainFn(torch.autograd.Function):
                                                    flags=engine.tc_flags)
                         else:
                             g[s.src] = ops.conv_simt(dz, wt, None, s.taps, ACT_NONE, g.get(s.src))
+                if _e0 is not None:
+                    TRACE.append(("bwd", s.name, _e0, _tick()))
         params = _train_params(engine)
         grads = []
+        if red is not None:
+            pgrad = red.finish()                     # rank-averaged views into the flat buckets
         for p in params:
             gr = pgrad.get(id(p))
             grads.append(gr.to(p.dtype) if gr is not None else None)
