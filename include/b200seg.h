@@ -140,6 +140,10 @@ int b200seg_f64_to_f32(const double* in, float* out, int n, float scale, b200seg
 /* convolution_backward (weight): dw f32 [Cout][taps][Cin] += sum_p dz[p][co] * x[p shifted by tap][ci]; caller zeroes dw */
 int b200seg_conv_wgrad(const void* x, const void* dz, float* dw, int dtype, int B, int H, int W, int Cin, int Cout,
                        int taps, b200seg_stream_t s);
+/* same on the tensor cores (bf16 x / dz, Cin % 8 == 0, Cout % 8 == 0): the pixel axis is the MMA reduction axis,
+ * the NHWC tiles are read as MN-major UMMA operands, partial tiles are added with red.global.add.v4.f32 */
+int b200seg_conv_wgrad_tc(const void* x, const void* dz, float* dw, int B, int H, int W, int Cin, int Cout, int taps,
+                          b200seg_stream_t s);
 /* depthwise backward: dx (+= acc_in) from dz with taps w f32 [9][C]; dw f64 [9][C] += ... (caller zeroes) */
 int b200seg_dw_dgrad(const void* dz, const float* w, const void* acc_in, void* dx, int dtype, int B, int H, int W,
                      int C, int stride, b200seg_stream_t s);

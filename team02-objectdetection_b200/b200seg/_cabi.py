@@ -43,6 +43,7 @@ _PROTOS = {
     "b200seg_colsum": [_vp, _i, _ll, _i, _vp, _vp],
     "b200seg_f64_to_f32": [_vp, _vp, _i, _f, _vp],
     "b200seg_conv_wgrad": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "b200seg_conv_wgrad_tc": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "b200seg_dw_dgrad": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "b200seg_dw_wgrad": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "b200seg_smallcin_wgrad": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp],

@@ -253,6 +253,18 @@ def conv_wgrad(x, dz, taps: int):
     return dw
 
 
+def conv_wgrad_tc(x, dz, taps: int):
+    """Tensor-core weight gradient: bf16 NHWC x / dz -> f32 [Cout, taps*Cin]."""
+    _cuda(x, dz)
+    if x.dtype != torch.bfloat16 or dz.dtype != torch.bfloat16:
+        raise TypeError("conv_wgrad_tc is bf16-only")
+    B, H, W, Cin = x.shape
+    Cout = dz.shape[-1]
+    dw = torch.zeros(Cout, taps * Cin, device=x.device, dtype=torch.float32)
+    check(lib.b200seg_conv_wgrad_tc(ptr(x), ptr(dz), ptr(dw), B, H, W, Cin, Cout, taps, _stream()), "conv_wgrad_tc")
+    return dw
+
+
 def dw_dgrad(dz, w9c, in_shape, stride: int, acc=None):
     _cuda(dz, w9c, acc)
     B, H, W, Cc = in_shape

@@ -173,7 +173,7 @@ class _TrainFn(torch.autograd.Function):
                     else:
                         cin = src.shape[-1]
                         k = 3 if s.taps == 9 else 1
-                        dwk = ops.conv_wgrad(src, dz, s.taps)                  # [Cout_pad, taps*Cin]
+                        dwk = ops.conv_wgrad_tc(src, dz, s.taps) if tc else ops.conv_wgrad(src, dz, s.taps)   # [Cout_pad, taps*Cin]
                         pgrad.set(w, dwk[:cout].reshape(cout, k, k, cin).permute(0, 3, 1, 2).contiguous())
                         # dgrad = the same conv with W transposed (and the 3x3 taps flipped)
                         wk = rec["wk"]                                          # [Cout_pad, taps*Cin]

@@ -96,6 +96,27 @@ def test_conv_wgrad_and_dgrad(dt, B, H, W, Cin, Cout, taps):
         assert _err(_nchw(got_tc), ref_tc) < TOL[dt]
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,taps", [
+    (2, 16, 32, 64, 64, 1), (2, 16, 32, 64, 128, 1), (4, 32, 64, 16, 96, 1), (2, 16, 16, 144, 24, 1), (2, 8, 16, 320, 1280, 1),
+    (1, 7, 9, 40, 72, 1), (2, 16, 32, 64, 64, 9), (2, 16, 32, 1344, 256, 9), (1, 32, 64, 288, 128, 9), (2, 64, 128, 80, 32, 9),
+    (1, 23, 40, 64, 64, 9), (2, 5, 7, 24, 40, 9), (4, 128, 256, 32, 16, 1)])
+def test_conv_wgrad_tensor_core(B, H, W, Cin, Cout, taps):
+    """tcgen05 weight gradient (MN-major operands, pixels as the reduction axis) vs float64 autograd."""
+    k = 3 if taps == 9 else 1
+    x = _rand(B, Cin, H, W, seed=8).bfloat16()
+    dz = _rand(B, Cout, H, W, seed=10).bfloat16()
+    ww = torch.zeros(Cout, Cin, k, k, device=DEV, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x.double(), ww, None, 1, k // 2).backward(dz.double())
+    got = ops.conv_wgrad_tc(_nhwc(x), _nhwc(dz), taps).reshape(Cout, k, k, Cin).permute(0, 3, 1, 2)
+    torch.cuda.synchronize()
+    e = _err(got, ww.grad)
+    if e >= 1e-3:
+        d = (got.double() - ww.grad).abs()
+        bad = (d > 1e-3 * ww.grad.abs().max()).nonzero()
+        raise AssertionError(f"wgrad_tc err {e:.3e}; {bad.shape[0]} bad of {d.numel()}; first (co,ci,kh,kw) {bad[:6].tolist()} last {bad[-3:].tolist()}; "
+                             f"got {got[tuple(bad[0])].item():.4f} ref {ww.grad[tuple(bad[0])].item():.4f}")
+
+
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("B,H,W,C,stride", [(2, 16, 32, 32, 1), (2, 16, 32, 96, 2), (1, 9, 7, 24, 2), (1, 7, 9, 144, 1),
                                             (2, 8, 16, 960, 1)])
