@@ -56,9 +56,12 @@ def run_train(args, dev, dist, world, rank, pk):
     if rank == 0:
         clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import time
     e0.record()
+    th0 = time.perf_counter()
     for i in range(args.steps):
         loss = step(xs[i % nrot], ys[i % nrot])
+    host_issue_ms = (time.perf_counter() - th0) * 1e3 / args.steps      # host time to ISSUE a step (no sync inside)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -120,7 +123,8 @@ def run_train(args, dev, dist, world, rank, pk):
             "config": {"workload": f"MobileNetV2UNet training step (fwd + pixel CE + bwd + Adam), batch {B}/GPU, 3x{H}x{W}, {NCLS} classes "
                                    f"(BASELINE config[2]); activations {precision}, fp32 master weights, torch.optim.Adam(lr=1.5e-4); "
                                    f"data parallel, per-replica BatchNorm, bucketed all-reduce overlapped with backward",
-                       "global_batch": B * world, "l2": "~20 GB of activations per step >> 126 MB L2", "last_loss": last_loss},
+                       "global_batch": B * world, "l2": "~20 GB of activations per step >> 126 MB L2", "last_loss": last_loss,
+                       "host_issue_ms_per_step": host_issue_ms},
             "e2e": {"value": B * world * args.steps / (ms_e2e * 1e-3), "unit": "images/s",
                     "h2d_bytes_per_step": B * 3 * H * W * 4 + B * H * W * 8, "d2h_bytes_per_step": 4,
                     "api": "train.py:32-42 loop body: pinned fp32 images + int64 labels -> .to(device), step, loss.item()"},

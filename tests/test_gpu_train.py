@@ -362,3 +362,37 @@ def test_bf16_training_path_tracks_fp32():
     assert vals[len(vals) // 2] > fvals[len(fvals) // 2] - 0.1, (vals[len(vals) // 2], fvals[len(fvals) // 2])
     for name in ("outc.conv.3.weight", "outc.conv.0.weight", "up4.conv.conv.3.weight"):
         assert cosines[name] > min(0.9, floor[name] - 0.05), (name, cosines[name], floor[name])
+
+
+def test_train_step_cuda_graph_replay_matches_eager():
+    """From the third step on the fwd/bwd passes are replayed from CUDA graphs: same losses, same parameters as the
+    eager launches, running statistics and num_batches_tracked included."""
+    sd = fixture_sd()
+
+    def run(use_graphs):
+        m = b200seg.MobileNetV2UNet(output_channels=10)
+        m.load_state_dict(expand_aliases(sd), strict=True)
+        m = m.to(DEV).train()
+        m._get_engine().use_graphs = use_graphs
+        opt = torch.optim.Adam(m.parameters(), lr=1.5e-4)
+        crit = b200seg.CrossEntropyLoss()
+        losses = []
+        for i in range(6):
+            x, t = O.synth_input(2, 64, 64, seed=30 + i).to(DEV), O.synth_target(2, 64, 64, seed=30 + i).to(DEV)
+            opt.zero_grad()
+            loss = crit(m(x), t)
+            loss.backward()
+            opt.step()
+            losses.append(loss.item())
+        captured = any(getattr(e.get("graph"), "bwd", None) is not None for e in m._get_engine()._graphs.values())
+        return losses, {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}, captured
+
+    l_e, sd_e, cap_e = run(False)
+    l_g, sd_g, cap_g = run(True)
+    assert cap_g and not cap_e
+    # weight gradients use float atomics (summation order varies run to run), so agreement is tight but not bitwise
+    assert abs(l_e[0] - l_g[0]) < 1e-6 and max(abs(a - b) for a, b in zip(l_e, l_g)) < 5e-3, (l_e, l_g)
+    assert int(sd_g["outc.conv.1.num_batches_tracked"]) == 6
+    for k in ("outc.conv.3.weight", "up1.conv.conv.0.weight", "backbone.features.0.0.weight", "backbone.features.18.1.running_var"):
+        assert torch.allclose(sd_e[k], sd_g[k], rtol=0, atol=4 * 6 * 1.5e-4 if "running" not in k else 1e-3), k
+        assert float((sd_e[k] - sd_g[k]).abs().mean()) < 2e-5 + (1e-4 if "running" in k else 0), k
