@@ -99,11 +99,15 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 template <typename TI, int NT, int S>   // NT = Cout / 8, S = stride
 __global__ void __launch_bounds__(256)
 conv3x3_c3_mma_kernel(const TI* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                      __nv_bfloat16* __restrict__ y, int B, int H, int W, int Ho, int Wo, int act) {
+                      __nv_bfloat16* __restrict__ y, int B, int H, int W, int Ho, int Wo, int act, int vec_ok) {
   constexpr int Cout = NT * 8;
   constexpr int NCOL = 127 * S + 3;            // input columns feeding 128 output pixels
-  constexpr int PITCH = NCOL + 3;              // odd-ish pitch: spreads the 9 row segments over banks
-  __shared__ float tile[9][PITCH];             // [c*3 + kh][column]
+  constexpr int LEAD = 8;                      // the tile starts 8 columns left of the first output's centre so that
+                                               // every 16-byte input vector is either fully inside or fully outside
+  constexpr int JN = ((LEAD - 1 + NCOL) + 7) / 8 * 8;
+  constexpr int PITCH = JN + 4;
+  constexpr int VL = 16 / (int)sizeof(TI);     // elements per 16-byte global load
+  __shared__ __align__(16) float tile[9][PITCH];   // [c*3 + kh][column]; column j <-> input column wo0*S - LEAD + j
   __shared__ __align__(16) __nv_bfloat16 patch[8][16][Cout + 8];   // +8: conflict-free fragment writes
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -135,7 +139,7 @@ conv3x3_c3_mma_kernel(const TI* __restrict__ x, const float* __restrict__ w, con
       for (int e = 0; e < 2; ++e) {
         const int k = ks * 16 + h * 8 + 2 * t + e;
         const int c = k / 9, r9 = k - c * 9;
-        koff[ks][h][e] = (k < 27) ? (c * 3 + r9 / 3) * PITCH + r9 % 3 : -1;
+        koff[ks][h][e] = (k < 27) ? (c * 3 + r9 / 3) * PITCH + r9 % 3 + (LEAD - 1) : -1;
       }
   float bias_v[NT][2];
 #pragma unroll
@@ -155,15 +159,37 @@ conv3x3_c3_mma_kernel(const TI* __restrict__ x, const float* __restrict__ w, con
     const int b = (int)(p / Ho);
     const int wo0 = sg * 128;
     const TI* xb = x + (long long)b * 3 * HW;
-    const int wi0 = wo0 * S - 1, hi0 = ho * S - 1;
+    const int wi0 = wo0 * S - LEAD, hi0 = ho * S - 1;
     __syncthreads();                              // previous job's gathers are done
-    for (int i = threadIdx.x; i < 9 * NCOL; i += 256) {
-      const int rowi = i / NCOL, col = i - rowi * NCOL;
-      const int c = rowi / 3, kh = rowi - c * 3;
-      const int hi = hi0 + kh, wi = wi0 + col;
-      float v = 0.f;
-      if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = to_f32<TI>(xb[(long long)c * HW + (long long)hi * W + wi]);
-      tile[rowi][col] = v;
+    if (vec_ok) {
+      // 16-byte coalesced loads; W % VL == 0 and wi0 % VL == 0, so a vector never straddles the image border
+      for (int i = threadIdx.x; i < 9 * (JN / VL); i += 256) {
+        const int rowi = i / (JN / VL), v = i - rowi * (JN / VL);
+        const int c = rowi / 3, kh = rowi - c * 3;
+        const int hi = hi0 + kh, wi = wi0 + v * VL;
+        float f[VL];
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) {
+          Vec16<TI> t;
+          t.load(xb + (long long)c * HW + (long long)hi * W + wi);
+#pragma unroll
+          for (int e = 0; e < VL; ++e) f[e] = t.v[e];
+        } else {
+#pragma unroll
+          for (int e = 0; e < VL; ++e) f[e] = 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < VL; e += 4)
+          *reinterpret_cast<float4*>(&tile[rowi][v * VL + e]) = make_float4(f[e], f[e + 1], f[e + 2], f[e + 3]);
+      }
+    } else {
+      for (int i = threadIdx.x; i < 9 * JN; i += 256) {
+        const int rowi = i / JN, col = i - rowi * JN;
+        const int c = rowi / 3, kh = rowi - c * 3;
+        const int hi = hi0 + kh, wi = wi0 + col;
+        float v = 0.f;
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = to_f32<TI>(xb[(long long)c * HW + (long long)hi * W + wi]);
+        tile[rowi][col] = v;
+      }
     }
     __syncthreads();
     const int px0 = warp * 16;                    // this warp's 16 output pixels within the segment
@@ -760,8 +786,10 @@ int b200seg_conv3x3_smallcin(const void* x, int x_dtype, const float* w, const f
     if (gb > capb) gb = capb;
 #define LAUNCH_MMA(TI, NT)                                                                                              \
   {                                                                                                                     \
-    if (stride == 2) conv3x3_c3_mma_kernel<TI, NT, 2><<<(int)gb, 256, 0, st>>>((const TI*)x, w, b, (bf16*)y, B, H, W, Ho, Wo, act); \
-    else conv3x3_c3_mma_kernel<TI, NT, 1><<<(int)gb, 256, 0, st>>>((const TI*)x, w, b, (bf16*)y, B, H, W, Ho, Wo, act);             \
+    const int vl = 16 / (int)sizeof(TI);                                                                                \
+    const int vok = (W % vl == 0) && (((uintptr_t)x & 15) == 0);                                                        \
+    if (stride == 2) conv3x3_c3_mma_kernel<TI, NT, 2><<<(int)gb, 256, 0, st>>>((const TI*)x, w, b, (bf16*)y, B, H, W, Ho, Wo, act, vok); \
+    else conv3x3_c3_mma_kernel<TI, NT, 1><<<(int)gb, 256, 0, st>>>((const TI*)x, w, b, (bf16*)y, B, H, W, Ho, Wo, act, vok);             \
   }
     if (x_dtype == B200SEG_F32) { if (Cout == 32) LAUNCH_MMA(float, 4) else if (Cout == 64) LAUNCH_MMA(float, 8) else LAUNCH_MMA(float, 2) }
     else if (x_dtype == B200SEG_BF16) { if (Cout == 32) LAUNCH_MMA(bf16, 4) else if (Cout == 64) LAUNCH_MMA(bf16, 8) else LAUNCH_MMA(bf16, 2) }
