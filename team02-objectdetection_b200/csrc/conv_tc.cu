@@ -52,6 +52,9 @@ struct ConvTcArgs {
   int dw;            // depthwise mode: B is block-diagonal, the only K chunk of N tile j is channel chunk j
   int stride;        // 1, or 2 (TAP mode only; the A tensor map then carries elementStrides = 2)
   int a_stage_bytes, b_stage_bytes;
+  int mpair;         // M tiles (128 pixels each) per work item that share every B stage (1 or 2)
+  int acc_bufs;      // TMEM accumulator sets: 2 = epilogue overlaps the next item's MMAs, 1 = no room
+  long long m_tiles; // real pixel tiles; work items = ceil(m_tiles / mpair) * n_tiles
   long long total_tiles;
 };
 
@@ -64,6 +67,7 @@ __device__ __forceinline__ uint64_t umma_desc_k128_off(uint32_t smem_addr) {
   return umma_desc_k128(smem_addr) | ((uint64_t)((smem_addr >> 7) & 7u) << 49);
 }
 
+template <int MPAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const ConvTcArgs a) {
@@ -77,7 +81,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int b_tile_bytes = a.block_n * 128;
 
   uint8_t* sA = smem;
-  uint8_t* sB = sA + a.stages * a.a_stage_bytes;
+  const int a_stride = MPAIR * a.a_stage_bytes;      // one ring slot holds the A tiles of all paired M tiles
+  uint8_t* sB = sA + a.stages * a_stride;
   uint8_t* sOut = sB + (a.b_resident ? b_tiles_resident * b_tile_bytes : a.stages * a.b_stage_bytes);
   float* sBias = reinterpret_cast<float*>(sOut + a.n_sbuf * n_boxes * TILE_BYTES);
   uint64_t* full = reinterpret_cast<uint64_t*>(sBias + 256);
@@ -124,15 +129,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t ph = 0;
     const int n_outer = a.halo ? a.k_chunks : a.taps;      // HALO: chunks x 3 rows;  TAP: taps x chunks
     const int n_inner = a.halo ? 3 : a.k_chunks;
-    const uint32_t tx_bytes = a.halo ? 130u * 128u + (a.b_resident ? 0u : 3u * (uint32_t)b_tile_bytes)
-                                     : (uint32_t)(rows * 128 + (a.b_resident ? 0 : b_tile_bytes));
+    const uint32_t tx_bytes = a.halo ? (uint32_t)MPAIR * 130u * 128u + (a.b_resident ? 0u : 3u * (uint32_t)b_tile_bytes)
+                                     : (uint32_t)(MPAIR * rows * 128 + (a.b_resident ? 0 : b_tile_bytes));
     for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
       const int n_tile = (int)(tile % a.n_tiles);
-      long long mt = tile / a.n_tiles;
-      const int tw = (int)(mt % a.tiles_w); mt /= a.tiles_w;
-      const int th = (int)(mt % a.tiles_h);
-      const int bb = (int)(mt / a.tiles_h);
-      const int w0 = tw * a.BW, h0 = th * a.BH, n0 = n_tile * a.block_n;
+      const int n0 = n_tile * a.block_n;
+      int w0v[MPAIR], h0v[MPAIR], bbv[MPAIR];
+#pragma unroll
+      for (int j = 0; j < MPAIR; ++j) {       // a pair index past the last real tile decodes to bb >= B: all OOB
+        long long mt = (tile / a.n_tiles) * MPAIR + j;
+        w0v[j] = (int)(mt % a.tiles_w) * a.BW; mt /= a.tiles_w;
+        h0v[j] = (int)(mt % a.tiles_h) * a.BH;
+        bbv[j] = (int)(mt / a.tiles_h);
+      }
       for (int o = 0; o < n_outer; ++o) {
         for (int i = 0; i < n_inner; ++i) {
           mbar_wait(&empty[s], ph ^ 1u, 1);
@@ -141,7 +150,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (a.halo) {
               const int chunk = o, dh = i;
               const int ach = a.dw ? n_tile : chunk;           // channel chunk of the activations
-              tma_load_4d(sA + s * a.a_stage_bytes, &tmA, &full[s], ach * 64, w0 - 1, h0 + dh - 1, bb);
+#pragma unroll
+              for (int j = 0; j < MPAIR; ++j)
+                tma_load_4d(sA + s * a_stride + j * a.a_stage_bytes, &tmA, &full[s], ach * 64, w0v[j] - 1,
+                            h0v[j] + dh - 1, bbv[j]);
               if (!a.b_resident)
                 for (int dw = 0; dw < 3; ++dw)
                   tma_load_3d(sB + s * a.b_stage_bytes + dw * b_tile_bytes, &tmB, &full[s], a.dw ? 0 : chunk * 64,
@@ -151,7 +163,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int ach = a.dw ? n_tile : chunk;
               int dw = 0, dh = 0;
               if (a.taps == 9) { dh = tap / 3 - 1; dw = tap - (dh + 1) * 3 - 1; }
-              tma_load_4d(sA + s * a.a_stage_bytes, &tmA, &full[s], ach * 64, w0 * a.stride + dw, h0 * a.stride + dh, bb);
+#pragma unroll
+              for (int j = 0; j < MPAIR; ++j)
+                tma_load_4d(sA + s * a_stride + j * a.a_stage_bytes, &tmA, &full[s], ach * 64, w0v[j] * a.stride + dw,
+                            h0v[j] * a.stride + dh, bbv[j]);
               if (!a.b_resident)
                 tma_load_3d(sB + s * a.b_stage_bytes, &tmB, &full[s], a.dw ? 0 : chunk * 64, tap, n0);
             }
@@ -170,7 +185,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t desc_hi = (uint32_t)(umma_desc_k128(0) >> 32);
     const uint32_t a_lo0 = (uint32_t)umma_desc_k128(smem_u32(sA));      // low word for stage 0
     const uint32_t b_lo0 = (uint32_t)umma_desc_k128(smem_u32(sB));
-    const uint32_t a_stage16 = (uint32_t)a.a_stage_bytes >> 4, b_stage16 = (uint32_t)a.b_stage_bytes >> 4;
+    const uint32_t a_stage16 = (uint32_t)a_stride >> 4, a_tile16 = (uint32_t)a.a_stage_bytes >> 4;
+    const uint32_t b_stage16 = (uint32_t)a.b_stage_bytes >> 4;
     const uint32_t b_tile16 = (uint32_t)b_tile_bytes >> 4;
     const int n_outer = a.halo ? a.k_chunks : a.taps;
     const int n_inner = a.halo ? 3 : a.k_chunks;
@@ -179,13 +195,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t ph = 0;
     int it = 0;
     for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
-      const int ab = it & 1;
-      const uint32_t aph = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(&acc_empty[ab], aph ^ 1u, 6);     // epilogue has drained this accumulator
+      const int ab = a.acc_bufs == 2 ? (it & 1) : 0;
+      const uint32_t aph = (uint32_t)(a.acc_bufs == 2 ? (it >> 1) : it) & 1u;
+      mbar_wait(&acc_empty[ab], aph ^ 1u, 6);     // epilogue has drained this accumulator set
       tc_fence_after();
-      const uint32_t tacc = tmem_base + (uint32_t)(ab * a.block_n);
+      const uint32_t tacc0 = tmem_base + (uint32_t)(ab * MPAIR * a.block_n);
       const int n_tile = a.dw ? (int)(tile % a.n_tiles) : 0;
-      uint32_t first = 0;                           // 0 for the very first MMA of the tile (overwrite), then 1
+      uint32_t first = 0;                           // 0 for the very first k-block of the item (overwrite), then 1
       for (int o = 0; o < n_outer; ++o) {
         for (int i = 0; i < n_inner; ++i) {
           const int chunk = a.halo ? o : i;
@@ -197,23 +213,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (a.halo) {
               const int dh = i;
 #pragma unroll
-              for (int dw = 0; dw < 3; ++dw) {
-                const int tap = dh * 3 + dw;
-                const uint32_t al = a_lo + (uint32_t)dw * 8u;                  // +128 B: one pixel to the right
-                const uint32_t bl = a.b_resident ? b_lo0 + (uint32_t)(tap * a.k_chunks + chunk) * b_tile16
-                                                 : b_lo0 + (uint32_t)s * b_stage16 + (uint32_t)dw * b_tile16;
+              for (int j = 0; j < MPAIR; ++j) {
+                const uint32_t tacc = tacc0 + (uint32_t)(j * a.block_n);
+                uint32_t fj = first;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  if (k < ksteps) { umma_bf16_lohi(tacc, al + 2u * k, bl + 2u * k, desc_hi, idesc, first); first = 1u; }
+                for (int dw = 0; dw < 3; ++dw) {
+                  const int tap = dh * 3 + dw;
+                  const uint32_t al = a_lo + (uint32_t)j * a_tile16 + (uint32_t)dw * 8u;   // +128 B: one pixel to the right
+                  const uint32_t bl = a.b_resident ? b_lo0 + (uint32_t)(tap * a.k_chunks + chunk) * b_tile16
+                                                   : b_lo0 + (uint32_t)s * b_stage16 + (uint32_t)dw * b_tile16;
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    if (k < ksteps) { umma_bf16_lohi(tacc, al + 2u * k, bl + 2u * k, desc_hi, idesc, fj); fj = 1u; }
+                }
               }
             } else {
               const int tap = o;
               const uint32_t bl = a.b_resident ? b_lo0 + (uint32_t)(tap * a.k_chunks + chunk) * b_tile16
                                                : b_lo0 + (uint32_t)s * b_stage16;
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (k < ksteps) { umma_bf16_lohi(tacc, a_lo + 2u * k, bl + 2u * k, desc_hi, idesc, first); first = 1u; }
+              for (int j = 0; j < MPAIR; ++j) {
+                const uint32_t tacc = tacc0 + (uint32_t)(j * a.block_n);
+                const uint32_t al = a_lo + (uint32_t)j * a_tile16;
+                uint32_t fj = first;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  if (k < ksteps) { umma_bf16_lohi(tacc, al + 2u * k, bl + 2u * k, desc_hi, idesc, fj); fj = 1u; }
+              }
             }
+            first = 1u;
             umma_commit(&empty[s]);
             if (o == n_outer - 1 && i == n_inner - 1) umma_commit(&acc_full[ab]);
           }
@@ -235,13 +263,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int cur_n_tile = -1;
     for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
       const int n_tile = (int)(tile % a.n_tiles);
-      long long mt = tile / a.n_tiles;
-      const int tw = (int)(mt % a.tiles_w); mt /= a.tiles_w;
-      const int th = (int)(mt % a.tiles_h);
-      const int bb = (int)(mt / a.tiles_h);
-      const int w0 = tw * a.BW, h0 = th * a.BH, n0 = n_tile * a.block_n;
-      const int ab = it & 1;
-      const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+      const int n0 = n_tile * a.block_n;
+      const int ab = a.acc_bufs == 2 ? (it & 1) : 0;
+      const uint32_t aph = (uint32_t)(a.acc_bufs == 2 ? (it >> 1) : it) & 1u;
+      int w0 = 0, h0 = 0, bb = 0;
       uint8_t* stg = sOut + (a.n_sbuf > 1 ? (it % a.n_sbuf) : 0) * n_boxes * TILE_BYTES;
 
       if (n_tile != cur_n_tile) {   // (re)stage the bias slice of this N tile
@@ -253,9 +278,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&acc_full[ab], aph, 3);
       tc_fence_after();
 
-      const bool row_ok = r < rows && (h0 + hl) < a.H && (w0 + wl) < a.W;
+      for (int j = 0; j < MPAIR; ++j) {
+      {
+        long long mt = (tile / a.n_tiles) * MPAIR + j;
+        w0 = (int)(mt % a.tiles_w) * a.BW; mt /= a.tiles_w;
+        h0 = (int)(mt % a.tiles_h) * a.BH;
+        bb = (int)(mt / a.tiles_h);
+      }
+      const bool row_ok = r < rows && (h0 + hl) < a.H && (w0 + wl) < a.W && bb < a.B;
       const long long pix = ((long long)bb * a.H + (h0 + hl)) * a.W + (w0 + wl);
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * a.block_n);
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((ab * MPAIR + j) * a.block_n);
       const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(a.res) + pix * a.Cout + n0;
       __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + pix * a.Cout + n0;
 
@@ -319,7 +351,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           process(vb, (ch + 1) << 4);
         }
       }
-      // accumulator fully read -> hand it back to the MMA warp
+      }   // paired M tiles
+      // accumulators fully read -> hand them back to the MMA warp
       tc_fence_before();
       mbar_arrive(&acc_empty[ab]);
       if (a.tma_store) {
@@ -375,7 +408,7 @@ using namespace b200;
 //        bit1 forbid HALO addressing; bit2 forbid resident weights; bit3 single staging buffer;
 //        bit4 HALO descriptors WITH base_offset (experiment: wrong on B200);
 //        bits 8..15: force grid size = value * 4 CTAs (0 = auto); bits 16..19: pipeline stages wanted (0 = auto);
-//        bits 20..21: CTAs per SM (0 = auto)
+//        bits 20..21: CTAs per SM (0 = auto); bit5: never pair M tiles over a shared B stage
 // x: [B,H,W,Cin] input; output [B,Ho,Wo,Cout] with Ho = (H-1)/stride+1.  dwmode: w is the block-diagonal
 // packing bf16 [C][9][64] (see b200seg_dwconv3x3_tc).
 static int launch_conv_tc(const void* x, const void* w, const float* bias, const void* res, void* y, int B, int H,
@@ -435,7 +468,14 @@ static int launch_conv_tc(const void* x, const void* w, const float* bias, const
   const int out_bytes = a.n_sbuf * n_boxes * TILE_BYTES;
   a.b_resident = (a.n_tiles == 1 && !(flags & 4) && b_all <= 80 * 1024 && b_all + out_bytes + 2 * a.a_stage_bytes <= smem_cap) ? 1 : 0;
   a.b_stage_bytes = a.b_resident ? 0 : (a.halo ? 3 * b_tile : b_tile);
-  const int per_stage = a.a_stage_bytes + a.b_stage_bytes;
+  // streamed weights are the L2->SM bottleneck of the 3x3 layers with large Cin: let two M tiles share every B
+  // stage (A traffic unchanged, B traffic halved).  flags bit5 disables.
+  a.m_tiles = (long long)a.tiles_w * a.tiles_h * a.B;
+  a.mpair = (!a.b_resident && taps * a.k_chunks >= 27 && !a.tma_store && !(flags & 32) && a.m_tiles >= 2) ? 2 : 1;   // measured: pays from ~27 k-blocks
+  a.acc_bufs = (a.mpair == 1 || a.block_n <= 64) ? 2 : 1;   // 2 x mpair x block_n columns must fit 512 (and leave room for a 2nd CTA when small)
+  a.tmem_cols = 32;
+  while (a.tmem_cols < a.acc_bufs * a.mpair * a.block_n) a.tmem_cols <<= 1;
+  const int per_stage = a.mpair * a.a_stage_bytes + a.b_stage_bytes;
   const int fixed = out_bytes + (a.b_resident ? b_all : 0);
   // Measured on B200 (tools/kbench.py KB_SWEEP): two resident CTAs per SM (two MMA issuers, two epilogues)
   // beat one CTA with a deeper ring whenever both fit, so: the deepest ring (<= want) that still leaves room
@@ -455,7 +495,7 @@ static int launch_conv_tc(const void* x, const void* w, const float* bias, const
   a.stages = stages;
   const int smem = fixed + stages * per_stage + 1024 + 1024 + 256;
   B200_REQUIRE(smem <= 227 * 1024, "conv_tc: smem %d too large", smem);
-  a.total_tiles = (long long)a.tiles_w * a.tiles_h * a.B * a.n_tiles;
+  a.total_tiles = ((a.m_tiles + a.mpair - 1) / a.mpair) * a.n_tiles;
 
   CUtensorMap tmA, tmB, tmC;
   {
@@ -486,7 +526,8 @@ static int launch_conv_tc(const void* x, const void* w, const float* bias, const
   cudaGetDevice(&dev);
   static bool attr_set[64] = {false};
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return set_error((int)e, "conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set[dev] = true;
   }
@@ -499,7 +540,8 @@ static int launch_conv_tc(const void* x, const void* w, const float* bias, const
   long long grid = (long long)sm_count() * per_sm;
   if ((flags >> 8) & 0xff) grid = (long long)((flags >> 8) & 0xff) * 4;
   if (grid > a.total_tiles) grid = a.total_tiles;
-  conv_tc_kernel<<<(unsigned)grid, TC_THREADS, smem, stream>>>(tmA, tmB, tmC, a);
+  if (a.mpair == 2) conv_tc_kernel<2><<<(unsigned)grid, TC_THREADS, smem, stream>>>(tmA, tmB, tmC, a);
+  else conv_tc_kernel<1><<<(unsigned)grid, TC_THREADS, smem, stream>>>(tmA, tmB, tmC, a);
   return check_launch("conv_tc");
 }
 

@@ -74,15 +74,15 @@ def main():
                 us = timeit(lambda: ops.dwconv3x3_tc(x, wd, b, s_, 2, out=out, flags=fl))
                 report(f"dw_tc {nm} C={C} s{s_} flags={fl} (res={1 - ((fl >> 2) & 1)} st={(fl >> 16) & 15} ps={(fl >> 20) & 3})", us, (x.numel() + out.numel()) * 2)
         return
-    FL3 = (0, 1, 2)                  # direct store | TMA store (3 staging buffers) | no halo
+    FL3 = (0, 32, 2)                 # default | no M-tile pairing | no halo
     conv_case("up4.0", 128, 256, 80, 32, 9, flag_list=FL3)
     conv_case("up4.3", 128, 256, 32, 32, 9, flag_list=FL3)
     conv_case("up3.0", 64, 128, 152, 64, 9, flag_list=FL3)
     conv_case("up3.3", 64, 128, 64, 64, 9, flag_list=FL3)
-    conv_case("up2.0", 32, 64, 288, 128, 9)
-    conv_case("up2.3", 32, 64, 128, 128, 9)
-    conv_case("up1.0", 16, 32, 1344, 256, 9)
-    conv_case("up1.3", 16, 32, 256, 256, 9)
+    conv_case("up2.0", 32, 64, 288, 128, 9, flag_list=(0, 32))
+    conv_case("up2.3", 32, 64, 128, 128, 9, flag_list=(0, 32))
+    conv_case("up1.0", 16, 32, 1344, 256, 9, flag_list=(0, 32))
+    conv_case("up1.3", 16, 32, 256, 256, 9, flag_list=(0, 32))
     conv_case("f2.expand", 128, 256, 16, 96, 1)
     conv_case("f1.project", 128, 256, 32, 16, 1)
     conv_case("f2.project", 64, 128, 96, 24, 1)
