@@ -113,13 +113,14 @@ int b200seg_softmax_ce(const float* logits, const int64_t* target, float* loss_s
  * [P = B*H*W pixels, C]; per-channel statistics are accumulated across CTAs in f64 buffers the caller
  * zeroes.  dgrad of the dense convs reuses b200seg_conv_simt / b200seg_conv_tc with transposed weights.
  * --------------------------------------------------------------------------------------------- */
-/* native_batch_norm (training): sum[c] += sum_p z, sumsq[c] += sum_p z^2 */
+/* native_batch_norm (training): sum[c] += sum_p (z-k), sumsq[c] += sum_p (z-k)^2 with the per-channel shift k = z at
+ * pixel 0 (shifted sums: no catastrophic cancellation for nearly constant channels); bn_finalize adds k back. */
 int b200seg_bn_stats(const void* z, int dtype, long long P, int C, double* sum, double* sumsq, b200seg_stream_t s);
 /* mean/biased var -> invstd; scale = gamma*invstd, shift = beta - mean*scale; running stats updated with
  * momentum and the unbiased variance (nn.BatchNorm2d defaults); running_* may be NULL. */
-int b200seg_bn_finalize(const double* sum, const double* sumsq, long long n, const float* gamma, const float* beta,
-                        float eps, float momentum, float* running_mean, float* running_var, float* mean,
-                        float* invstd, float* scale, float* shift, int C, b200seg_stream_t s);
+int b200seg_bn_finalize(const void* z, int dtype, const double* sum, const double* sumsq, long long n, const float* gamma,
+                        const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                        float* mean, float* invstd, float* scale, float* shift, int C, b200seg_stream_t s);
 /* a = act(z*scale + shift) (+ res)   -- BN apply + ReLU/ReLU6 (+ inverted-residual shortcut) */
 int b200seg_bn_apply(const void* z, const float* scale, const float* shift, const void* res, void* a, int dtype,
                      long long P, int C, int act, b200seg_stream_t s);

@@ -35,7 +35,7 @@ _PROTOS = {
     "b200seg_softmax_ce": [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _vp],
     # training path
     "b200seg_bn_stats": [_vp, _i, _ll, _i, _vp, _vp, _vp],
-    "b200seg_bn_finalize": [_vp, _vp, _ll, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+    "b200seg_bn_finalize": [_vp, _i, _vp, _vp, _ll, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "b200seg_bn_apply": [_vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _vp],
     "b200seg_bn_bwd_reduce": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _vp, _vp, _vp],
     "b200seg_bn_bwd_apply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _vp],

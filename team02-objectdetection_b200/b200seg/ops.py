@@ -202,7 +202,7 @@ def bn_train_forward(z, gamma, beta, running_mean, running_var, eps: float, mome
     st = torch.zeros(2, C, device=z.device, dtype=torch.float64)
     check(lib.b200seg_bn_stats(ptr(z), _dt(z), P, C, ptr(st[0]), ptr(st[1]), _stream()), "bn_stats")
     sv = torch.empty(4, C, device=z.device, dtype=torch.float32)
-    check(lib.b200seg_bn_finalize(ptr(st[0]), ptr(st[1]), P, ptr(gamma), ptr(beta), eps, momentum, ptr(running_mean),
+    check(lib.b200seg_bn_finalize(ptr(z), _dt(z), ptr(st[0]), ptr(st[1]), P, ptr(gamma), ptr(beta), eps, momentum, ptr(running_mean),
                                   ptr(running_var), ptr(sv[0]), ptr(sv[1]), ptr(sv[2]), ptr(sv[3]), C, _stream()),
           "bn_finalize")
     a = torch.empty_like(z)

@@ -15,17 +15,25 @@ static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b
 
 // ---------------------------------------------------------------------------------------------
 // per-channel reductions over all pixels of an NHWC tensor viewed as [P, C]
-//   block = 32 channel-vectors (x) x 8 pixel lanes (y); grid = (pixel chunks, channel-vector tiles)
-//   per-thread partials in f32 over <= PIX_PER_BLOCK/8 pixels, block tree in smem, one f64 atomic
-//   per channel per block.
+//   block = TX channel-vectors (x) x 256/TX pixel lanes (y), TX = the power of two covering min(C/VN, 32):
+//   narrow tensors (C = 16..32, which have the MOST pixels) still keep all 256 threads busy and every warp
+//   reads a contiguous run of pixels.  grid = (pixel chunks, channel-vector tiles).  Per-thread partials in
+//   f32 over RED_PIX/TY pixels, tree over y in shared memory, one f64 atomic per channel per block.
 // ---------------------------------------------------------------------------------------------
-constexpr int RED_PIX = 1024;   // pixels per block
+constexpr int RED_PIX = 2048;   // pixels per block
+
+static inline dim3 red_block(int cvecs) {
+  int tx = 1;
+  while (tx < cvecs && tx < 32) tx <<= 1;
+  return dim3(tx, 256 / tx);
+}
 
 template <typename T, int NOUT, typename F>
 __device__ __forceinline__ void channel_reduce(long long P, int C, double* const* out, F&& f) {
   using V = Vec16<T>;
   constexpr int VN = V::N;
-  const int cvec = blockIdx.y * 32 + threadIdx.x;
+  const int TX = blockDim.x, TY = blockDim.y;
+  const int cvec = blockIdx.y * TX + threadIdx.x;
   const int c0 = cvec * VN;
   const bool active = c0 < C;
   float acc[NOUT][VN];
@@ -35,23 +43,26 @@ __device__ __forceinline__ void channel_reduce(long long P, int C, double* const
     for (int j = 0; j < VN; ++j) acc[o][j] = 0.f;
   if (active) {
     const long long p0 = (long long)blockIdx.x * RED_PIX, p1 = min(p0 + RED_PIX, P);
-    for (long long p = p0 + threadIdx.y; p < p1; p += 8) f(p, c0, acc);
+    for (long long p = p0 + threadIdx.y; p < p1; p += TY) f(p, c0, acc);
   }
-  __shared__ float red[8][32][VN + 1];
+  __shared__ float red[256][VN + 1];
+  const int tid = threadIdx.y * TX + threadIdx.x;
 #pragma unroll
   for (int o = 0; o < NOUT; ++o) {
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < VN; ++j) red[threadIdx.y][threadIdx.x][j] = acc[o][j];
+    for (int j = 0; j < VN; ++j) red[tid][j] = acc[o][j];
     __syncthreads();
+    for (int stride = TY >> 1; stride >= 1; stride >>= 1) {      // tree over the pixel lanes
+      if (threadIdx.y < stride) {
+#pragma unroll
+        for (int j = 0; j < VN; ++j) red[tid][j] += red[tid + stride * TX][j];
+      }
+      __syncthreads();
+    }
     if (threadIdx.y == 0 && active) {
 #pragma unroll
-      for (int j = 0; j < VN; ++j) {
-        double s = 0.0;
-#pragma unroll
-        for (int y = 0; y < 8; ++y) s += (double)red[y][threadIdx.x][j];
-        atomicAdd(out[o] + c0 + j, s);
-      }
+      for (int j = 0; j < VN; ++j) atomicAdd(out[o] + c0 + j, (double)red[threadIdx.x][j]);
     }
   }
 }
@@ -62,25 +73,31 @@ __global__ void __launch_bounds__(256)
 bn_stats_kernel(const T* __restrict__ z, long long P, int C, double* sum, double* sumsq) {
   using V = Vec16<T>;
   double* const outs[2] = {sum, sumsq};
+  // shifted sums: every channel is offset by its own value at pixel 0, so that sum((z-k)^2) - sum(z-k)^2/n does not
+  // cancel catastrophically for channels whose spread is tiny compared with their mean (a nearly constant channel
+  // otherwise gets a variance -- hence a d(gamma) -- that is pure rounding noise).
   channel_reduce<T, 2>(P, C, outs, [&](long long p, int c0, float (&acc)[2][V::N]) {
-    V v;
+    V v, k;
     v.load(z + p * C + c0);
+    k.load(z + c0);
 #pragma unroll
-    for (int j = 0; j < V::N; ++j) { acc[0][j] += v.v[j]; acc[1][j] = fmaf(v.v[j], v.v[j], acc[1][j]); }
+    for (int j = 0; j < V::N; ++j) { const float d = v.v[j] - k.v[j]; acc[0][j] += d; acc[1][j] = fmaf(d, d, acc[1][j]); }
   });
 }
 
 // one thread per channel: mean, biased var -> invstd, fused scale/shift, running-stat update
 // (momentum 0.1, unbiased variance), exactly nn.BatchNorm2d in training mode.
-__global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sumsq, long long n,
+template <typename T>
+__global__ void bn_finalize_kernel(const T* __restrict__ z0, const double* __restrict__ sum, const double* __restrict__ sumsq, long long n,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, float* running_mean, float* running_var, float* mean_out,
                                    float* invstd_out, float* scale_out, float* shift_out, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double m = sum[c] / (double)n;
-  double var = sumsq[c] / (double)n - m * m;
+  const double ms = sum[c] / (double)n;                 // mean of (z - k), k = z at pixel 0
+  double var = sumsq[c] / (double)n - ms * ms;
   if (var < 0.0) var = 0.0;
+  const double m = ms + (double)to_f32<T>(z0[c]);
   const float invstd = (float)(1.0 / sqrt(var + (double)eps));
   const float sc = gamma[c] * invstd;
   mean_out[c] = (float)m;
@@ -132,16 +149,27 @@ bn_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ z, const fl
                      long long P, int C, int act, double* sg, double* sgx) {
   using V = Vec16<T>;
   double* const outs[2] = {sg, sgx};
+  // per-channel constants live in registers for the whole pixel loop (the channel vector of a thread is fixed)
+  float ksc[V::N], ksh[V::N], kmu[V::N], kis[V::N];
+  {
+    const int c0 = (blockIdx.y * blockDim.x + threadIdx.x) * V::N;
+#pragma unroll
+    for (int j = 0; j < V::N; ++j) {
+      const bool ok = c0 + j < C;
+      ksc[j] = ok ? __ldg(scale + c0 + j) : 0.f; ksh[j] = ok ? __ldg(shift + c0 + j) : 0.f;
+      kmu[j] = ok ? __ldg(mean + c0 + j) : 0.f;  kis[j] = ok ? __ldg(invstd + c0 + j) : 0.f;
+    }
+  }
   channel_reduce<T, 2>(P, C, outs, [&](long long p, int c0, float (&acc)[2][V::N]) {
     V d, v;
     d.load(da + p * C + c0);
     v.load(z + p * C + c0);
 #pragma unroll
     for (int j = 0; j < V::N; ++j) {
-      const float u = fmaf(v.v[j], __ldg(scale + c0 + j), __ldg(shift + c0 + j));
+      const float u = fmaf(v.v[j], ksc[j], ksh[j]);
       const float g = d.v[j] * act_grad(u, act);
       acc[0][j] += g;
-      acc[1][j] = fmaf(g, (v.v[j] - __ldg(mean + c0 + j)) * __ldg(invstd + c0 + j), acc[1][j]);
+      acc[1][j] = fmaf(g, (v.v[j] - kmu[j]) * kis[j], acc[1][j]);
     }
   });
 }
@@ -612,19 +640,21 @@ extern "C" {
 int b200seg_bn_stats(const void* z, int dtype, long long P, int C, double* sum, double* sumsq, b200seg_stream_t s) {
   const int vn = dtype == B200SEG_BF16 ? 8 : 4;
   B200_REQUIRE(P > 0 && C > 0 && C % vn == 0, "bn_stats: P=%lld C=%d (C must be a multiple of %d)", P, C, vn);
-  dim3 grid(cdiv(P, RED_PIX), cdiv(C / vn, 32)), block(32, 8);
+  const dim3 block = red_block(C / vn);
+  dim3 grid(cdiv(P, RED_PIX), cdiv(C / vn, block.x));
   cudaStream_t st = (cudaStream_t)s;
   DISPATCH_T(dtype, (bn_stats_kernel<float><<<grid, block, 0, st>>>((const float*)z, P, C, sum, sumsq)),
              (bn_stats_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)z, P, C, sum, sumsq)), "bn_stats")
   return check_launch("bn_stats");
 }
 
-int b200seg_bn_finalize(const double* sum, const double* sumsq, long long n, const float* gamma, const float* beta,
-                        float eps, float momentum, float* running_mean, float* running_var, float* mean,
-                        float* invstd, float* scale, float* shift, int C, b200seg_stream_t s) {
-  B200_REQUIRE(C > 0 && n > 0, "bn_finalize: C=%d n=%lld", C, n);
-  bn_finalize_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)s>>>(sum, sumsq, n, gamma, beta, eps, momentum, running_mean,
-                                                                 running_var, mean, invstd, scale, shift, C);
+int b200seg_bn_finalize(const void* z, int dtype, const double* sum, const double* sumsq, long long n, const float* gamma,
+                        const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                        float* mean, float* invstd, float* scale, float* shift, int C, b200seg_stream_t s) {
+  B200_REQUIRE(C > 0 && n > 0 && z, "bn_finalize: C=%d n=%lld", C, n);
+  cudaStream_t st = (cudaStream_t)s;
+  DISPATCH_T(dtype, (bn_finalize_kernel<float><<<cdiv(C, 128), 128, 0, st>>>((const float*)z, sum, sumsq, n, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, scale, shift, C)),
+             (bn_finalize_kernel<bf16><<<cdiv(C, 128), 128, 0, st>>>((const bf16*)z, sum, sumsq, n, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, scale, shift, C)), "bn_finalize")
   return check_launch("bn_finalize");
 }
 
@@ -644,7 +674,8 @@ int b200seg_bn_bwd_reduce(const void* da, const void* z, const float* scale, con
                           b200seg_stream_t s) {
   const int vn = dtype == B200SEG_BF16 ? 8 : 4;
   B200_REQUIRE(P > 0 && C > 0 && C % vn == 0, "bn_bwd_reduce: P=%lld C=%d", P, C);
-  dim3 grid(cdiv(P, RED_PIX), cdiv(C / vn, 32)), block(32, 8);
+  const dim3 block = red_block(C / vn);
+  dim3 grid(cdiv(P, RED_PIX), cdiv(C / vn, block.x));
   cudaStream_t st = (cudaStream_t)s;
   DISPATCH_T(dtype, (bn_bwd_reduce_kernel<float><<<grid, block, 0, st>>>((const float*)da, (const float*)z, scale, shift, mean, invstd, P, C, act, sg, sgx)),
              (bn_bwd_reduce_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)da, (const bf16*)z, scale, shift, mean, invstd, P, C, act, sg, sgx)), "bn_bwd_reduce")
@@ -676,7 +707,8 @@ int b200seg_act_bwd(const void* da, const void* a_out, void* dz, int dtype, long
 int b200seg_colsum(const void* x, int dtype, long long P, int C, double* out, b200seg_stream_t s) {
   const int vn = dtype == B200SEG_BF16 ? 8 : 4;
   B200_REQUIRE(P > 0 && C > 0 && C % vn == 0, "colsum: P=%lld C=%d", P, C);
-  dim3 grid(cdiv(P, RED_PIX), cdiv(C / vn, 32)), block(32, 8);
+  const dim3 block = red_block(C / vn);
+  dim3 grid(cdiv(P, RED_PIX), cdiv(C / vn, block.x));
   cudaStream_t st = (cudaStream_t)s;
   DISPATCH_T(dtype, (colsum_kernel<float><<<grid, block, 0, st>>>((const float*)x, P, C, out)),
              (colsum_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)x, P, C, out)), "colsum")
@@ -732,7 +764,8 @@ int b200seg_dw_wgrad(const void* x, const void* dz, double* dw, int dtype, int B
   B200_REQUIRE(B > 0 && H > 0 && W > 0, "dw_wgrad: empty tensor");
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   const long long P = (long long)B * Ho * Wo;
-  dim3 grid(cdiv(P, RED_PIX), cdiv(C / vn, 32)), block(32, 8);
+  const dim3 block = red_block(C / vn);
+  dim3 grid(cdiv(P, RED_PIX), cdiv(C / vn, block.x));
   cudaStream_t st = (cudaStream_t)s;
   DISPATCH_T(dtype, (dw_wgrad_kernel<float><<<grid, block, 0, st>>>((const float*)x, (const float*)dz, B, H, W, C, Ho, Wo, stride, dw)),
              (dw_wgrad_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)x, (const bf16*)dz, B, H, W, C, Ho, Wo, stride, dw)), "dw_wgrad")
