@@ -129,9 +129,10 @@ int b200seg_bn_apply(const void* z, const float* scale, const float* shift, cons
 int b200seg_bn_bwd_reduce(const void* da, const void* z, const float* scale, const float* shift, const float* mean,
                           const float* invstd, int dtype, long long P, int C, int act, double* sg, double* sgx,
                           b200seg_stream_t s);
-/* pass 2: dz = scale * (g - sg/P - xhat * sgx/P) */
+/* pass 2: dz = scale * (g - sg/P - xhat * sgx/P); sg/sgx are the pass-1 sums converted to f32 (f64 arithmetic in
+ * the per-element loop would run at 1/64 rate) */
 int b200seg_bn_bwd_apply(const void* da, const void* z, const float* scale, const float* shift, const float* mean,
-                         const float* invstd, const double* sg, const double* sgx, void* dz, int dtype, long long P,
+                         const float* invstd, const float* sg, const float* sgx, void* dz, int dtype, long long P,
                          int C, int act, b200seg_stream_t s);
 /* dz = da * act'(a_out) for a layer without BatchNorm */
 int b200seg_act_bwd(const void* da, const void* a_out, void* dz, int dtype, long long N, int act, b200seg_stream_t s);

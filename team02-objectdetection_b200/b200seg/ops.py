@@ -217,11 +217,11 @@ def bn_train_backward(da, z, sv, act: int):
     red = torch.zeros(2, C, device=z.device, dtype=torch.float64)
     check(lib.b200seg_bn_bwd_reduce(ptr(da), ptr(z), ptr(sv[2]), ptr(sv[3]), ptr(sv[0]), ptr(sv[1]), _dt(z), P, C, act,
                                     ptr(red[0]), ptr(red[1]), _stream()), "bn_bwd_reduce")
-    dz = torch.empty_like(z)
-    check(lib.b200seg_bn_bwd_apply(ptr(da), ptr(z), ptr(sv[2]), ptr(sv[3]), ptr(sv[0]), ptr(sv[1]), ptr(red[0]), ptr(red[1]),
-                                   ptr(dz), _dt(z), P, C, act, _stream()), "bn_bwd_apply")
     g32 = torch.empty(2, C, device=z.device, dtype=torch.float32)
     check(lib.b200seg_f64_to_f32(ptr(red), ptr(g32), 2 * C, 1.0, _stream()), "f64_to_f32")
+    dz = torch.empty_like(z)
+    check(lib.b200seg_bn_bwd_apply(ptr(da), ptr(z), ptr(sv[2]), ptr(sv[3]), ptr(sv[0]), ptr(sv[1]), ptr(g32[0]), ptr(g32[1]),
+                                   ptr(dz), _dt(z), P, C, act, _stream()), "bn_bwd_apply")
     return dz, g32[1], g32[0]
 
 

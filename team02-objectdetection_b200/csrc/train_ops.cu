@@ -20,16 +20,24 @@ static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b
 //   reads a contiguous run of pixels.  grid = (pixel chunks, channel-vector tiles).  Per-thread partials in
 //   f32 over RED_PIX/TY pixels, tree over y in shared memory, one f64 atomic per channel per block.
 // ---------------------------------------------------------------------------------------------
-constexpr int RED_PIX = 2048;   // pixels per block
-
 static inline dim3 red_block(int cvecs) {
   int tx = 1;
   while (tx < cvecs && tx < 32) tx <<= 1;
   return dim3(tx, 256 / tx);
 }
+// pixels per block: enough blocks (~8 per SM) to cover the memory latency even for the small deep layers, at least
+// 4 pixels per thread so the f64 atomics stay a minor cost
+static inline int red_ppb(long long P, const dim3& block, int cvecs) {
+  const long long gy = (cvecs + block.x - 1) / block.x;
+  long long ppb = (P * gy + (long long)sm_count() * 8 - 1) / ((long long)sm_count() * 8);
+  const long long lo = 4LL * block.y;
+  if (ppb < lo) ppb = lo;
+  if (ppb > 8192) ppb = 8192;
+  return (int)ppb;
+}
 
 template <typename T, int NOUT, typename F>
-__device__ __forceinline__ void channel_reduce(long long P, int C, double* const* out, F&& f) {
+__device__ __forceinline__ void channel_reduce(long long P, int C, int ppb, double* const* out, F&& f) {
   using V = Vec16<T>;
   constexpr int VN = V::N;
   const int TX = blockDim.x, TY = blockDim.y;
@@ -42,7 +50,8 @@ __device__ __forceinline__ void channel_reduce(long long P, int C, double* const
 #pragma unroll
     for (int j = 0; j < VN; ++j) acc[o][j] = 0.f;
   if (active) {
-    const long long p0 = (long long)blockIdx.x * RED_PIX, p1 = min(p0 + RED_PIX, P);
+    const long long p0 = (long long)blockIdx.x * ppb, p1 = min(p0 + ppb, P);
+#pragma unroll 4
     for (long long p = p0 + threadIdx.y; p < p1; p += TY) f(p, c0, acc);
   }
   __shared__ float red[256][VN + 1];
@@ -70,13 +79,13 @@ __device__ __forceinline__ void channel_reduce(long long P, int C, double* const
 // sum and sum of squares (BatchNorm batch statistics)
 template <typename T>
 __global__ void __launch_bounds__(256)
-bn_stats_kernel(const T* __restrict__ z, long long P, int C, double* sum, double* sumsq) {
+bn_stats_kernel(const T* __restrict__ z, long long P, int C, int ppb, double* sum, double* sumsq) {
   using V = Vec16<T>;
   double* const outs[2] = {sum, sumsq};
   // shifted sums: every channel is offset by its own value at pixel 0, so that sum((z-k)^2) - sum(z-k)^2/n does not
   // cancel catastrophically for channels whose spread is tiny compared with their mean (a nearly constant channel
   // otherwise gets a variance -- hence a d(gamma) -- that is pure rounding noise).
-  channel_reduce<T, 2>(P, C, outs, [&](long long p, int c0, float (&acc)[2][V::N]) {
+  channel_reduce<T, 2>(P, C, ppb, outs, [&](long long p, int c0, float (&acc)[2][V::N]) {
     V v, k;
     v.load(z + p * C + c0);
     k.load(z + c0);
@@ -111,27 +120,35 @@ __global__ void bn_finalize_kernel(const T* __restrict__ z0, const double* __res
   }
 }
 
-// a = act(z * scale + shift) (+ residual)
+// a = act(z * scale + shift) (+ residual).  Thread = one channel vector x several pixels (same (tx, ty) layout as the
+// reductions): the per-channel constants are loaded once per thread instead of once per element.
 template <typename T>
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const T* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
-                const T* __restrict__ res, T* __restrict__ a, long long P, int C, int act) {
+                const T* __restrict__ res, T* __restrict__ a, long long P, int C, int ppb, int act) {
   using V = Vec16<T>;
   constexpr int VN = V::N;
-  const int cv = C / VN;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= P * cv) return;
-  const int c0 = (int)(idx % cv) * VN;
-  const long long off = (idx / cv) * C + c0;
-  V v, r, o;
-  v.load(z + off);
-  if (res) r.load(res + off);
+  const int TY = blockDim.y;
+  const int c0 = (blockIdx.y * blockDim.x + threadIdx.x) * VN;
+  if (c0 >= C) return;
+  float ksc[VN], ksh[VN];
 #pragma unroll
-  for (int j = 0; j < VN; ++j) {
-    float u = apply_act_rt(fmaf(v.v[j], __ldg(scale + c0 + j), __ldg(shift + c0 + j)), act);
-    o.v[j] = res ? u + r.v[j] : u;
+  for (int j = 0; j < VN; ++j) { ksc[j] = __ldg(scale + c0 + j); ksh[j] = __ldg(shift + c0 + j); }
+  const float lo = act != B200SEG_ACT_NONE ? 0.f : -INFINITY, hi = act == B200SEG_ACT_RELU6 ? 6.f : INFINITY;
+  const long long p0 = (long long)blockIdx.x * ppb, p1 = min(p0 + ppb, P);
+#pragma unroll 4
+  for (long long p = p0 + threadIdx.y; p < p1; p += TY) {
+    const long long off = p * C + c0;
+    V v, r, o;
+    v.load(z + off);
+    if (res) r.load(res + off);
+#pragma unroll
+    for (int j = 0; j < VN; ++j) {
+      const float u = fminf(fmaxf(fmaf(v.v[j], ksc[j], ksh[j]), lo), hi);
+      o.v[j] = res ? u + r.v[j] : u;
+    }
+    o.store(a + off);
   }
-  o.store(a + off);
 }
 
 // gradient of the activation evaluated at u = z*scale + shift
@@ -146,7 +163,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ z, const float* __restrict__ scale,
                      const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
-                     long long P, int C, int act, double* sg, double* sgx) {
+                     long long P, int C, int ppb, int act, double* sg, double* sgx) {
   using V = Vec16<T>;
   double* const outs[2] = {sg, sgx};
   // per-channel constants live in registers for the whole pixel loop (the channel vector of a thread is fixed)
@@ -160,7 +177,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ z, const fl
       kmu[j] = ok ? __ldg(mean + c0 + j) : 0.f;  kis[j] = ok ? __ldg(invstd + c0 + j) : 0.f;
     }
   }
-  channel_reduce<T, 2>(P, C, outs, [&](long long p, int c0, float (&acc)[2][V::N]) {
+  channel_reduce<T, 2>(P, C, ppb, outs, [&](long long p, int c0, float (&acc)[2][V::N]) {
     V d, v;
     d.load(da + p * C + c0);
     v.load(z + p * C + c0);
@@ -174,33 +191,41 @@ bn_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ z, const fl
   });
 }
 
-// dz = scale * (g - sum(g)/n - xhat * sum(g*xhat)/n)        (scale = gamma * invstd)
+// dz = scale * (g - mean(g) - xhat * mean(g*xhat))        (scale = gamma * invstd; sums passed as f32, mean = sum * inv_n)
 template <typename T>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const T* __restrict__ da, const T* __restrict__ z, const float* __restrict__ scale,
                     const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
-                    const double* __restrict__ sg, const double* __restrict__ sgx, long long n, T* __restrict__ dz,
-                    long long P, int C, int act) {
+                    const float* __restrict__ sg, const float* __restrict__ sgx, float inv_n, T* __restrict__ dz,
+                    long long P, int C, int ppb, int act) {
   using V = Vec16<T>;
   constexpr int VN = V::N;
-  const int cv = C / VN;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= P * cv) return;
-  const int c0 = (int)(idx % cv) * VN;
-  const long long off = (idx / cv) * C + c0;
-  V d, v, o;
-  d.load(da + off);
-  v.load(z + off);
-  const float inv_n = 1.f / (float)n;
+  const int TY = blockDim.y;
+  const int c0 = (blockIdx.y * blockDim.x + threadIdx.x) * VN;
+  if (c0 >= C) return;
+  float ksc[VN], ksh[VN], kmu[VN], kis[VN], kmg[VN], kmx[VN];
 #pragma unroll
   for (int j = 0; j < VN; ++j) {
-    const float sc = __ldg(scale + c0 + j);
-    const float u = fmaf(v.v[j], sc, __ldg(shift + c0 + j));
-    const float g = d.v[j] * act_grad(u, act);
-    const float xh = (v.v[j] - __ldg(mean + c0 + j)) * __ldg(invstd + c0 + j);
-    o.v[j] = sc * (g - (float)sg[c0 + j] * inv_n - xh * ((float)sgx[c0 + j] * inv_n));
+    ksc[j] = __ldg(scale + c0 + j); ksh[j] = __ldg(shift + c0 + j);
+    kmu[j] = __ldg(mean + c0 + j);  kis[j] = __ldg(invstd + c0 + j);
+    kmg[j] = __ldg(sg + c0 + j) * inv_n; kmx[j] = __ldg(sgx + c0 + j) * inv_n;
   }
-  o.store(dz + off);
+  const long long p0 = (long long)blockIdx.x * ppb, p1 = min(p0 + ppb, P);
+#pragma unroll 4
+  for (long long p = p0 + threadIdx.y; p < p1; p += TY) {
+    const long long off = p * C + c0;
+    V d, v, o;
+    d.load(da + off);
+    v.load(z + off);
+#pragma unroll
+    for (int j = 0; j < VN; ++j) {
+      const float u = fmaf(v.v[j], ksc[j], ksh[j]);
+      const float g = d.v[j] * act_grad(u, act);
+      const float xh = (v.v[j] - kmu[j]) * kis[j];
+      o.v[j] = ksc[j] * (g - kmg[j] - xh * kmx[j]);
+    }
+    o.store(dz + off);
+  }
 }
 
 // dz = da * act'(z + bias) for a conv+bias(+act) layer without BatchNorm; also used with act = NONE as a cast/copy
@@ -221,10 +246,10 @@ act_bwd_kernel(const T* __restrict__ da, const T* __restrict__ a_out, T* __restr
 // per-channel column sum (bias gradients)
 template <typename T>
 __global__ void __launch_bounds__(256)
-colsum_kernel(const T* __restrict__ x, long long P, int C, double* out) {
+colsum_kernel(const T* __restrict__ x, long long P, int C, int ppb, double* out) {
   using V = Vec16<T>;
   double* const outs[1] = {out};
-  channel_reduce<T, 1>(P, C, outs, [&](long long p, int c0, float (&acc)[1][V::N]) {
+  channel_reduce<T, 1>(P, C, ppb, outs, [&](long long p, int c0, float (&acc)[1][V::N]) {
     V v;
     v.load(x + p * C + c0);
 #pragma unroll
@@ -367,14 +392,14 @@ dw_dgrad_kernel(const T* __restrict__ dz, const float* __restrict__ w, const T* 
 template <typename T>
 __global__ void __launch_bounds__(256)
 dw_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dz, int B, int H, int W, int C, int Ho, int Wo, int S,
-                double* dw /* [9][C] */) {
+                int ppb, double* dw /* [9][C] */) {
   using V = Vec16<T>;
   constexpr int VN = V::N;
   const long long P = (long long)B * Ho * Wo;
   double* outs[9];
 #pragma unroll
   for (int t = 0; t < 9; ++t) outs[t] = dw + (long long)t * C;
-  channel_reduce<T, 9>(P, C, outs, [&](long long p, int c0, float (&acc)[9][VN]) {
+  channel_reduce<T, 9>(P, C, ppb, outs, [&](long long p, int c0, float (&acc)[9][VN]) {
     const int wo = (int)(p % Wo);
     const long long t = p / Wo;
     const int ho = (int)(t % Ho);
@@ -641,10 +666,11 @@ int b200seg_bn_stats(const void* z, int dtype, long long P, int C, double* sum, 
   const int vn = dtype == B200SEG_BF16 ? 8 : 4;
   B200_REQUIRE(P > 0 && C > 0 && C % vn == 0, "bn_stats: P=%lld C=%d (C must be a multiple of %d)", P, C, vn);
   const dim3 block = red_block(C / vn);
-  dim3 grid(cdiv(P, RED_PIX), cdiv(C / vn, block.x));
+  const int ppb = red_ppb(P, block, C / vn);
+  dim3 grid(cdiv(P, ppb), cdiv(C / vn, block.x));
   cudaStream_t st = (cudaStream_t)s;
-  DISPATCH_T(dtype, (bn_stats_kernel<float><<<grid, block, 0, st>>>((const float*)z, P, C, sum, sumsq)),
-             (bn_stats_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)z, P, C, sum, sumsq)), "bn_stats")
+  DISPATCH_T(dtype, (bn_stats_kernel<float><<<grid, block, 0, st>>>((const float*)z, P, C, ppb, sum, sumsq)),
+             (bn_stats_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)z, P, C, ppb, sum, sumsq)), "bn_stats")
   return check_launch("bn_stats");
 }
 
@@ -658,14 +684,19 @@ int b200seg_bn_finalize(const void* z, int dtype, const double* sum, const doubl
   return check_launch("bn_finalize");
 }
 
+// elementwise passes: same (channel-vector, pixel-lane) block shape as the reductions, 8 pixels per thread
+static inline int ew_ppb(const dim3& block) { return 8 * (int)block.y; }
+
 int b200seg_bn_apply(const void* z, const float* scale, const float* shift, const void* res, void* a, int dtype,
                      long long P, int C, int act, b200seg_stream_t s) {
   const int vn = dtype == B200SEG_BF16 ? 8 : 4;
   B200_REQUIRE(P > 0 && C > 0 && C % vn == 0, "bn_apply: P=%lld C=%d", P, C);
-  const unsigned g = cdiv(P * (C / vn), 256);
+  const dim3 block = red_block(C / vn);
+  const int ppb = ew_ppb(block);
+  dim3 grid(cdiv(P, ppb), cdiv(C / vn, block.x));
   cudaStream_t st = (cudaStream_t)s;
-  DISPATCH_T(dtype, (bn_apply_kernel<float><<<g, 256, 0, st>>>((const float*)z, scale, shift, (const float*)res, (float*)a, P, C, act)),
-             (bn_apply_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)z, scale, shift, (const bf16*)res, (bf16*)a, P, C, act)), "bn_apply")
+  DISPATCH_T(dtype, (bn_apply_kernel<float><<<grid, block, 0, st>>>((const float*)z, scale, shift, (const float*)res, (float*)a, P, C, ppb, act)),
+             (bn_apply_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)z, scale, shift, (const bf16*)res, (bf16*)a, P, C, ppb, act)), "bn_apply")
   return check_launch("bn_apply");
 }
 
@@ -675,22 +706,26 @@ int b200seg_bn_bwd_reduce(const void* da, const void* z, const float* scale, con
   const int vn = dtype == B200SEG_BF16 ? 8 : 4;
   B200_REQUIRE(P > 0 && C > 0 && C % vn == 0, "bn_bwd_reduce: P=%lld C=%d", P, C);
   const dim3 block = red_block(C / vn);
-  dim3 grid(cdiv(P, RED_PIX), cdiv(C / vn, block.x));
+  const int ppb = red_ppb(P, block, C / vn);
+  dim3 grid(cdiv(P, ppb), cdiv(C / vn, block.x));
   cudaStream_t st = (cudaStream_t)s;
-  DISPATCH_T(dtype, (bn_bwd_reduce_kernel<float><<<grid, block, 0, st>>>((const float*)da, (const float*)z, scale, shift, mean, invstd, P, C, act, sg, sgx)),
-             (bn_bwd_reduce_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)da, (const bf16*)z, scale, shift, mean, invstd, P, C, act, sg, sgx)), "bn_bwd_reduce")
+  DISPATCH_T(dtype, (bn_bwd_reduce_kernel<float><<<grid, block, 0, st>>>((const float*)da, (const float*)z, scale, shift, mean, invstd, P, C, ppb, act, sg, sgx)),
+             (bn_bwd_reduce_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)da, (const bf16*)z, scale, shift, mean, invstd, P, C, ppb, act, sg, sgx)), "bn_bwd_reduce")
   return check_launch("bn_bwd_reduce");
 }
 
 int b200seg_bn_bwd_apply(const void* da, const void* z, const float* scale, const float* shift, const float* mean,
-                         const float* invstd, const double* sg, const double* sgx, void* dz, int dtype, long long P,
+                         const float* invstd, const float* sg, const float* sgx, void* dz, int dtype, long long P,
                          int C, int act, b200seg_stream_t s) {
   const int vn = dtype == B200SEG_BF16 ? 8 : 4;
   B200_REQUIRE(P > 0 && C > 0 && C % vn == 0, "bn_bwd_apply: P=%lld C=%d", P, C);
-  const unsigned g = cdiv(P * (C / vn), 256);
+  const dim3 block = red_block(C / vn);
+  const int ppb = ew_ppb(block);
+  dim3 grid(cdiv(P, ppb), cdiv(C / vn, block.x));
+  const float inv_n = 1.f / (float)P;
   cudaStream_t st = (cudaStream_t)s;
-  DISPATCH_T(dtype, (bn_bwd_apply_kernel<float><<<g, 256, 0, st>>>((const float*)da, (const float*)z, scale, shift, mean, invstd, sg, sgx, P, (float*)dz, P, C, act)),
-             (bn_bwd_apply_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)da, (const bf16*)z, scale, shift, mean, invstd, sg, sgx, P, (bf16*)dz, P, C, act)), "bn_bwd_apply")
+  DISPATCH_T(dtype, (bn_bwd_apply_kernel<float><<<grid, block, 0, st>>>((const float*)da, (const float*)z, scale, shift, mean, invstd, sg, sgx, inv_n, (float*)dz, P, C, ppb, act)),
+             (bn_bwd_apply_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)da, (const bf16*)z, scale, shift, mean, invstd, sg, sgx, inv_n, (bf16*)dz, P, C, ppb, act)), "bn_bwd_apply")
   return check_launch("bn_bwd_apply");
 }
 
@@ -708,10 +743,11 @@ int b200seg_colsum(const void* x, int dtype, long long P, int C, double* out, b2
   const int vn = dtype == B200SEG_BF16 ? 8 : 4;
   B200_REQUIRE(P > 0 && C > 0 && C % vn == 0, "colsum: P=%lld C=%d", P, C);
   const dim3 block = red_block(C / vn);
-  dim3 grid(cdiv(P, RED_PIX), cdiv(C / vn, block.x));
+  const int ppb = red_ppb(P, block, C / vn);
+  dim3 grid(cdiv(P, ppb), cdiv(C / vn, block.x));
   cudaStream_t st = (cudaStream_t)s;
-  DISPATCH_T(dtype, (colsum_kernel<float><<<grid, block, 0, st>>>((const float*)x, P, C, out)),
-             (colsum_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)x, P, C, out)), "colsum")
+  DISPATCH_T(dtype, (colsum_kernel<float><<<grid, block, 0, st>>>((const float*)x, P, C, ppb, out)),
+             (colsum_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)x, P, C, ppb, out)), "colsum")
   return check_launch("colsum");
 }
 
@@ -765,10 +801,11 @@ int b200seg_dw_wgrad(const void* x, const void* dz, double* dw, int dtype, int B
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   const long long P = (long long)B * Ho * Wo;
   const dim3 block = red_block(C / vn);
-  dim3 grid(cdiv(P, RED_PIX), cdiv(C / vn, block.x));
+  const int ppb = red_ppb(P, block, C / vn);
+  dim3 grid(cdiv(P, ppb), cdiv(C / vn, block.x));
   cudaStream_t st = (cudaStream_t)s;
-  DISPATCH_T(dtype, (dw_wgrad_kernel<float><<<grid, block, 0, st>>>((const float*)x, (const float*)dz, B, H, W, C, Ho, Wo, stride, dw)),
-             (dw_wgrad_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)x, (const bf16*)dz, B, H, W, C, Ho, Wo, stride, dw)), "dw_wgrad")
+  DISPATCH_T(dtype, (dw_wgrad_kernel<float><<<grid, block, 0, st>>>((const float*)x, (const float*)dz, B, H, W, C, Ho, Wo, stride, ppb, dw)),
+             (dw_wgrad_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)x, (const bf16*)dz, B, H, W, C, Ho, Wo, stride, ppb, dw)), "dw_wgrad")
   return check_launch("dw_wgrad");
 }
 
