@@ -42,7 +42,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="infer", choices=["infer", "train"])
+    ap.add_argument("--workload", default="infer", choices=["infer", "train", "infer720", "unet_train"],
+                    help="infer = BASELINE config[1] (default); train = config[2]; infer720 = config[4] (3x720x1280 padded to 736, "
+                         "batch 8/GPU); unet_train = config[3] (plain UNet, 3x512x1024, bf16)")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default 64 infer / 32 train)")
     ap.add_argument("--breakdown", action="store_true", help="print the per-kernel table to stderr")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -161,11 +163,14 @@ def main():
     from b200seg import _cabi
     sms, cc = _cabi.device_info()
 
-    if args.workload == "train":
+    if args.workload in ("train", "unet_train"):
         from bench_train import run_train          # training step benchmark lives in its own file
         return run_train(args, dev, dist, world, rank, peaks())
 
-    B = args.batch or 64
+    global H, W
+    if args.workload == "infer720":
+        H, W = 736, 1280                            # 720 rows padded to a multiple of 32 (the reference fails on 720, SURVEY finding 8)
+    B = args.batch or (8 if args.workload == "infer720" else 64)
     torch.manual_seed(0)
     model = b200seg.MobileNetV2UNet(output_channels=NCLS).to(dev).bfloat16().eval()
     eng = model._get_engine()
@@ -288,7 +293,8 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"MobileNetV2UNet bf16 inference, batch {B}/GPU, 3x{H}x{W}, {NCLS} classes, random init "
-                                   "(BASELINE config[1]; frames sharded by rank, no collective)",
+                                   + ("(BASELINE config[4]: 720x1280 frames padded to 736 rows; " if args.workload == "infer720" else "(BASELINE config[1]; ")
+                                   + "frames sharded by rank, no collective)",
                        "global_batch": B * world, "l2": "4 rotating input batches; ~7 GB of activations per step >> 126 MB L2",
                        "sm_count": sms, "cc": cc},
             "e2e": {"value": B * world * args.steps / (ms_e2e * 1e-3), "unit": "images/s",

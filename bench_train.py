@@ -19,10 +19,14 @@ def run_train(args, dev, dist, world, rank, pk):
     import b200seg
     from b200seg import dp, train_path
     from bench import ClockSampler
-    B = args.batch or 32
+    global H, W
+    unet = args.workload == "unet_train"
+    if unet:
+        H, W = 512, 1024
+    B = args.batch or (4 if unet else 32)
     precision = os.environ.get("B200SEG_TRAIN_PRECISION", "bf16")     # bf16 activations + tcgen05 convs, fp32 master weights
     torch.manual_seed(0)
-    model = b200seg.MobileNetV2UNet(output_channels=NCLS).to(dev)
+    model = (b200seg.UNet(output_channels=NCLS) if unet else b200seg.MobileNetV2UNet(output_channels=NCLS)).to(dev)
     eng = model._get_engine()
     eng.precision = precision
     if dist is not None:
@@ -114,14 +118,14 @@ def run_train(args, dev, dist, world, rank, pk):
         return
     (top_phase, top_name), top_ms = rows[0]
     # algorithmic model of the whole step: 353 MB/img bf16 activations (706 MB fp32), 34.5 GFLOP/img
-    bytes_img = 353e6 if precision == "bf16" else 706e6
+    bytes_img = (4772e6 if unet else 353e6) * (1 if precision == "bf16" else 2)
     step_s = ms / args.steps * 1e-3
-    line = {"metric": "MobileNetV2UNet training images/s", "value": B * world * args.steps / (ms * 1e-3), "unit": "images/s",
+    line = {"metric": ("UNet" if unet else "MobileNetV2UNet") + " training images/s", "value": B * world * args.steps / (ms * 1e-3), "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": f"MobileNetV2UNet training step (fwd + pixel CE + bwd + Adam), batch {B}/GPU, 3x{H}x{W}, {NCLS} classes "
-                                   f"(BASELINE config[2]); activations {precision}, fp32 master weights, torch.optim.Adam(lr=1.5e-4); "
+            "config": {"workload": f"{'UNet' if unet else 'MobileNetV2UNet'} training step (fwd + pixel CE + bwd + Adam), batch {B}/GPU, 3x{H}x{W}, {NCLS} classes "
+                                   f"(BASELINE config[{3 if unet else 2}]); activations {precision}, fp32 master weights, torch.optim.Adam(lr=1.5e-4); "
                                    f"data parallel, per-replica BatchNorm, bucketed all-reduce overlapped with backward",
                        "global_batch": B * world, "l2": "~20 GB of activations per step >> 126 MB L2", "last_loss": last_loss,
                        "host_issue_ms_per_step": host_issue_ms},

@@ -346,81 +346,136 @@ conv_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dz, float* __re
 // depthwise 3x3 backward
 // ---------------------------------------------------------------------------------------------
 // dx[hi][wi][c] = sum over taps with (hi+1-kh) = S*ho, (wi+1-kw) = S*wo of dz[ho][wo][c] * w[kh*3+kw][c]
+// Block = TX channel vectors x TY pixel lanes; the 9 x (TX*VN) tap weights of the block's channels are staged in
+// shared memory once, every thread then walks `ppb/TY` input pixels (incremental (b,h,w) bookkeeping, no divisions).
 template <typename T>
 __global__ void __launch_bounds__(256)
 dw_dgrad_kernel(const T* __restrict__ dz, const float* __restrict__ w, const T* __restrict__ acc_in, T* __restrict__ dx,
-                int B, int H, int W, int C, int Ho, int Wo, int S) {
+                int B, int H, int W, int C, int Ho, int Wo, int S, int ppb) {
   using V = Vec16<T>;
   constexpr int VN = V::N;
-  const int cv = C / VN;
-  const long long total = (long long)B * H * W * cv;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int c0 = (int)(idx % cv) * VN;
-  long long p = idx / cv;
-  const int wi = (int)(p % W); p /= W;
-  const int hi = (int)(p % H);
-  const int b = (int)(p / H);
-  V o;
-  if (acc_in) o.load(acc_in + (((long long)b * H + hi) * W + wi) * C + c0);
-  else {
-#pragma unroll
-    for (int j = 0; j < VN; ++j) o.v[j] = 0.f;
+  __shared__ __align__(16) float sw[9][32 * VN];
+  const int TX = blockDim.x, TY = blockDim.y;
+  const int cbase = blockIdx.y * TX * VN;
+  for (int i = threadIdx.y * TX + threadIdx.x; i < 9 * TX * VN; i += 256) {
+    const int t = i / (TX * VN), c = i - t * (TX * VN);
+    sw[t][c] = (cbase + c < C) ? w[t * C + cbase + c] : 0.f;
   }
+  __syncthreads();
+  const int c0 = cbase + threadIdx.x * VN;
+  if (c0 >= C) return;
+  const long long P = (long long)B * H * W;
+  const long long p0 = (long long)blockIdx.x * ppb, p1 = min(p0 + ppb, P);
+  long long p = p0 + threadIdx.y;
+  if (p >= p1) return;
+  int wi = (int)(p % W);
+  long long t_ = p / W;
+  int hi = (int)(t_ % H), b = (int)(t_ / H);
+  for (; p < p1; p += TY) {
+    V o;
+    if (acc_in) o.load(acc_in + p * C + c0);
+    else {
 #pragma unroll
-  for (int kh = 0; kh < 3; ++kh) {
-    const int th = hi + 1 - kh;
-    if (th < 0 || th % S) continue;
-    const int ho = th / S;
-    if (ho >= Ho) continue;
-#pragma unroll
-    for (int kw = 0; kw < 3; ++kw) {
-      const int tw = wi + 1 - kw;
-      if (tw < 0 || tw % S) continue;
-      const int wo = tw / S;
-      if (wo >= Wo) continue;
-      V d;
-      d.load(dz + (((long long)b * Ho + ho) * Wo + wo) * C + c0);
-#pragma unroll
-      for (int j = 0; j < VN; ++j) o.v[j] = fmaf(d.v[j], __ldg(w + (kh * 3 + kw) * C + c0 + j), o.v[j]);
+      for (int j = 0; j < VN; ++j) o.v[j] = 0.f;
     }
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int th = hi + 1 - kh;
+      const int ho = S == 1 ? th : th >> 1;
+      const bool hok = th >= 0 && (S == 1 || !(th & 1)) && ho < Ho;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int tw = wi + 1 - kw;
+        const int wo = S == 1 ? tw : tw >> 1;
+        const bool ok = hok && tw >= 0 && (S == 1 || !(tw & 1)) && wo < Wo;
+        if (ok) {
+          V d;
+          d.load(dz + (((long long)b * Ho + ho) * Wo + wo) * C + c0);
+          const float* wp = &sw[kh * 3 + kw][threadIdx.x * VN];
+#pragma unroll
+          for (int j = 0; j < VN; j += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wp + j);
+            o.v[j] = fmaf(d.v[j], w4.x, o.v[j]); o.v[j + 1] = fmaf(d.v[j + 1], w4.y, o.v[j + 1]);
+            o.v[j + 2] = fmaf(d.v[j + 2], w4.z, o.v[j + 2]); o.v[j + 3] = fmaf(d.v[j + 3], w4.w, o.v[j + 3]);
+          }
+        }
+      }
+    }
+    o.store(dx + p * C + c0);
+    wi += TY;
+    while (wi >= W) { wi -= W; if (++hi == H) { hi = 0; ++b; } }
   }
-  o.store(dx + (((long long)b * H + hi) * W + wi) * C + c0);
 }
 
-// dw[tap][c] += sum_p dz[p][c] * x[p*S + tap - 1][c]
+// dw[tap][c] += sum_p dz[p][c] * x[p*S + tap - 1][c].  Same block shape; predicated (zero-filled) tap loads instead
+// of branches, incremental pixel bookkeeping; the 9 partial sums per channel go through the shared tree reduction.
 template <typename T>
 __global__ void __launch_bounds__(256)
 dw_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dz, int B, int H, int W, int C, int Ho, int Wo, int S,
                 int ppb, double* dw /* [9][C] */) {
   using V = Vec16<T>;
   constexpr int VN = V::N;
+  const int TX = blockDim.x, TY = blockDim.y;
+  const int c0 = (blockIdx.y * TX + threadIdx.x) * VN;
+  const bool active = c0 < C;
   const long long P = (long long)B * Ho * Wo;
-  double* outs[9];
+  float acc[9][VN];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) outs[t] = dw + (long long)t * C;
-  channel_reduce<T, 9>(P, C, ppb, outs, [&](long long p, int c0, float (&acc)[9][VN]) {
-    const int wo = (int)(p % Wo);
-    const long long t = p / Wo;
-    const int ho = (int)(t % Ho);
-    const int b = (int)(t / Ho);
-    V d;
-    d.load(dz + p * C + c0);
+  for (int t = 0; t < 9; ++t)
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const int hi = ho * S - 1 + kh;
-      if (hi < 0 || hi >= H) continue;
+    for (int j = 0; j < VN; ++j) acc[t][j] = 0.f;
+  const long long p0 = (long long)blockIdx.x * ppb, p1 = min(p0 + ppb, P);
+  long long p = p0 + threadIdx.y;
+  if (active && p < p1) {
+    int wo = (int)(p % Wo);
+    long long t_ = p / Wo;
+    int ho = (int)(t_ % Ho), b = (int)(t_ / Ho);
+    const long long rowC = (long long)W * C;
+    for (; p < p1; p += TY) {
+      V d;
+      d.load(dz + p * C + c0);
+      const int hi0 = ho * S - 1, wi0 = wo * S - 1;
+      const T* xb = x + (((long long)b * H + hi0) * W + wi0) * C + c0;
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int wi = wo * S - 1 + kw;
-        if (wi < 0 || wi >= W) continue;
-        V xv;
-        xv.load(x + (((long long)b * H + hi) * W + wi) * C + c0);
+      for (int kh = 0; kh < 3; ++kh) {
+        const bool hok = (unsigned)(hi0 + kh) < (unsigned)H;
 #pragma unroll
-        for (int j = 0; j < VN; ++j) acc[kh * 3 + kw][j] = fmaf(d.v[j], xv.v[j], acc[kh * 3 + kw][j]);
+        for (int kw = 0; kw < 3; ++kw) {
+          const bool ok = hok && (unsigned)(wi0 + kw) < (unsigned)W;
+          V xv;
+          if (ok) xv.load(xb + kh * rowC + kw * C);
+          else {
+#pragma unroll
+            for (int j = 0; j < VN; ++j) xv.v[j] = 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < VN; ++j) acc[kh * 3 + kw][j] = fmaf(d.v[j], xv.v[j], acc[kh * 3 + kw][j]);
+        }
       }
+      wo += TY;
+      while (wo >= Wo) { wo -= Wo; if (++ho == Ho) { ho = 0; ++b; } }
     }
-  });
+  }
+  __shared__ float red[256][VN + 1];
+  const int tid = threadIdx.y * TX + threadIdx.x;
+#pragma unroll
+  for (int o = 0; o < 9; ++o) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < VN; ++j) red[tid][j] = acc[o][j];
+    __syncthreads();
+    for (int stride = TY >> 1; stride >= 1; stride >>= 1) {
+      if (threadIdx.y < stride) {
+#pragma unroll
+        for (int j = 0; j < VN; ++j) red[tid][j] += red[tid + stride * TX][j];
+      }
+      __syncthreads();
+    }
+    if (threadIdx.y == 0 && active) {
+#pragma unroll
+      for (int j = 0; j < VN; ++j) atomicAdd(dw + (long long)o * C + c0 + j, (double)red[threadIdx.x][j]);
+    }
+  }
 }
 
 // stem / first conv weight gradient: x NCHW [B,Cin<=4,H,W], dz NHWC [B,Ho,Wo,Cout]; dw f32 [3][3][Cin][Cout]
@@ -786,10 +841,13 @@ int b200seg_dw_dgrad(const void* dz, const float* w, const void* acc_in, void* d
   B200_REQUIRE(C > 0 && C % vn == 0 && (stride == 1 || stride == 2), "dw_dgrad: C=%d stride=%d", C, stride);
   B200_REQUIRE(B > 0 && H > 0 && W > 0, "dw_dgrad: empty tensor");
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
-  const unsigned g = cdiv((long long)B * H * W * (C / vn), 256);
+  const long long P = (long long)B * H * W;
+  const dim3 block = red_block(C / vn);
+  const int ppb = 8 * (int)block.y;
+  dim3 grid(cdiv(P, ppb), cdiv(C / vn, block.x));
   cudaStream_t st = (cudaStream_t)s;
-  DISPATCH_T(dtype, (dw_dgrad_kernel<float><<<g, 256, 0, st>>>((const float*)dz, w, (const float*)acc_in, (float*)dx, B, H, W, C, Ho, Wo, stride)),
-             (dw_dgrad_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)dz, w, (const bf16*)acc_in, (bf16*)dx, B, H, W, C, Ho, Wo, stride)), "dw_dgrad")
+  DISPATCH_T(dtype, (dw_dgrad_kernel<float><<<grid, block, 0, st>>>((const float*)dz, w, (const float*)acc_in, (float*)dx, B, H, W, C, Ho, Wo, stride, ppb)),
+             (dw_dgrad_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)dz, w, (const bf16*)acc_in, (bf16*)dx, B, H, W, C, Ho, Wo, stride, ppb)), "dw_dgrad")
   return check_launch("dw_dgrad");
 }
 
