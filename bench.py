@@ -268,6 +268,14 @@ def main():
                 "unit": "TFLOP/s" if top["bound"] == "tensor" else "GB/s", "frac": top["frac"], "traffic": None,
                 "peak_source": pk["src"], "share_of_step": top["us"] / tot_us,
                 "algorithmic_per_launch": top["flops"] if top["bound"] == "tensor" else top["bytes"]}
+    try:                                   # DRAM traffic of the dominant kernel from the committed ncu capture, if it is the same kernel
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            ent = json.load(f).get(top["name"])
+        if ent and B == 64 and args.workload == "infer":
+            roofline["traffic"] = ent["traffic_bytes"]
+            roofline["traffic_source"] = ent["capture"]
+    except (OSError, ValueError):
+        pass
     tot_bytes = sum(r["bytes"] for r in rows)
     step_roofline = {"bound": "hbm", "algorithmic_bytes_per_step": tot_bytes,
                      "achieved": tot_bytes / (ms / args.steps * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",

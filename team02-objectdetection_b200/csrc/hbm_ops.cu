@@ -406,150 +406,6 @@ dwconv3x3_bf16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------
-// depthwise 3x3, bf16 NHWC, ROW-STREAMING: one thread owns TW output columns x 8 channels and walks
-// RH output rows downwards.  Every input row is loaded (16-byte loads) and converted to f32 exactly
-// once per thread and scattered into the (at most 3) output rows it feeds, which are held as rotating
-// f32 accumulators; a finished output row is clamped, packed and stored.  Compared with a per-output
-// gather this cuts loads + conversions per output element from 9 (or 4.5 with a 1-D strip) to
-// (TW*S+2)/TW * (RH+2)/RH ~ 2, and the L2->SM traffic of the vertical halo from 3x to (RH+2)/RH.
-// ------------------------------------------------------------------------------------------
-template <int S, int TW>
-struct DwRows {
-  static constexpr int NCOL = (TW - 1) * S + 3;
-  const __nv_bfloat16* xb;   // image base + channel offset
-  const float* w;            // [9][C] + channel offset
-  __nv_bfloat16* yb;
-  int H, W, C, Wo, wi0, wo0;
-  float lo, hi;
-  float bias8[8];
-
-  __device__ __forceinline__ void load_row(int hrow, float (&in)[NCOL][8]) const {
-    if (hrow < 0 || hrow >= H) {
-#pragma unroll
-      for (int i = 0; i < NCOL; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) in[i][j] = 0.f;
-      return;
-    }
-    const __nv_bfloat16* row = xb + (long long)hrow * W * C;
-    uint4 raw[NCOL];
-#pragma unroll
-    for (int i = 0; i < NCOL; ++i) {
-      const int wi = wi0 + i;
-      raw[i] = (wi >= 0 && wi < W) ? __ldg(reinterpret_cast<const uint4*>(row + (long long)wi * C)) : make_uint4(0, 0, 0, 0);
-    }
-#pragma unroll
-    for (int i = 0; i < NCOL; ++i) {
-      in[i][0] = bf16lo(raw[i].x); in[i][1] = bf16hi(raw[i].x); in[i][2] = bf16lo(raw[i].y); in[i][3] = bf16hi(raw[i].y);
-      in[i][4] = bf16lo(raw[i].z); in[i][5] = bf16hi(raw[i].z); in[i][6] = bf16lo(raw[i].w); in[i][7] = bf16hi(raw[i].w);
-    }
-  }
-  __device__ __forceinline__ void mac(float (&acc)[TW][8], const float (&in)[NCOL][8], int kh) const {
-#pragma unroll
-    for (int kw = 0; kw < 3; ++kw) {
-      // asm volatile: the 72 tap weights are loop invariant, but keeping them in registers would spill;
-      // they are re-read from L1 at every use instead
-      const float* wp = w + (kh * 3 + kw) * C;
-      float wv[8];
-      asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(wv[0]), "=f"(wv[1]), "=f"(wv[2]), "=f"(wv[3]) : "l"(wp));
-      asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(wv[4]), "=f"(wv[5]), "=f"(wv[6]), "=f"(wv[7]) : "l"(wp + 4));
-#pragma unroll
-      for (int t = 0; t < TW; ++t)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(in[t * S + kw][j], wv[j], acc[t][j]);
-    }
-  }
-  __device__ __forceinline__ void arm(float (&acc)[TW][8]) const {
-#pragma unroll
-    for (int t = 0; t < TW; ++t)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[t][j] = bias8[j];
-  }
-  // clamp + pack + store output row `ho` if it is inside [ho_lo, ho_hi)
-  __device__ __forceinline__ void store_row(const float (&acc)[TW][8], int ho, int ho_lo, int ho_hi) const {
-    if (ho >= ho_lo && ho < ho_hi) {
-      __nv_bfloat16* yrow = yb + (long long)ho * Wo * C;
-#pragma unroll
-      for (int t = 0; t < TW; ++t) {
-        if (wo0 + t < Wo) {
-          uint4 v;
-          float a[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) a[j] = fminf(fmaxf(acc[t][j], lo), hi);
-          v.x = pack_bf16x2(a[0], a[1]); v.y = pack_bf16x2(a[2], a[3]);
-          v.z = pack_bf16x2(a[4], a[5]); v.w = pack_bf16x2(a[6], a[7]);
-          *reinterpret_cast<uint4*>(yrow + (long long)(wo0 + t) * C) = v;
-        }
-      }
-    }
-  }
-};
-
-template <int S, int TW>
-__global__ void __launch_bounds__(256, 2)
-dwconv3x3_rows_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                      __nv_bfloat16* __restrict__ y, int B, int H, int W, int C, int Ho, int Wo, int RH, int act) {
-  using D = DwRows<S, TW>;
-  const int cv = C >> 3;
-  const int sw_ = (Wo + TW - 1) / TW, sh_ = (Ho + RH - 1) / RH;
-  const long long total = (long long)B * sh_ * sw_ * cv;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int c0 = (int)(idx % cv) << 3;
-  long long p = idx / cv;
-  const int tw = (int)(p % sw_); p /= sw_;
-  const int rc = (int)(p % sh_);
-  const int b = (int)(p / sh_);
-  D d;
-  d.xb = x + (long long)b * H * W * C + c0;
-  d.w = w + c0;
-  d.yb = y + (long long)b * Ho * Wo * C + c0;
-  d.H = H; d.W = W; d.C = C; d.Wo = Wo;
-  d.wo0 = tw * TW; d.wi0 = d.wo0 * S - 1;
-  d.lo = act != B200SEG_ACT_NONE ? 0.f : -INFINITY;
-  d.hi = act == B200SEG_ACT_RELU6 ? 6.f : INFINITY;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) d.bias8[j] = bias ? __ldg(bias + c0 + j) : 0.f;
-  const int ho_lo = rc * RH, ho_hi = min(ho_lo + RH, Ho);
-  const int n_out = ho_hi - ho_lo;
-  float in[D::NCOL][8];
-  if (S == 1) {
-    // input row r (absolute ho_lo - 1 + r) feeds output rows ho_lo+r (kh=0), +r-1 (kh=1), +r-2 (kh=2);
-    // A0/A1/A2 hold those three partial rows and rotate by one register move per step.
-    float A0[TW][8], A1[TW][8], A2[TW][8];
-    d.arm(A0); d.arm(A1); d.arm(A2);
-    const int hi0 = ho_lo - 1;
-#pragma unroll 1
-    for (int r = 0; r < n_out + 2; ++r) {
-      d.load_row(hi0 + r, in);
-      d.mac(A0, in, 0); d.mac(A1, in, 1); d.mac(A2, in, 2);
-      d.store_row(A2, ho_lo + r - 2, ho_lo, ho_hi);
-#pragma unroll
-      for (int t = 0; t < TW; ++t)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { A2[t][j] = A1[t][j]; A1[t][j] = A0[t][j]; A0[t][j] = d.bias8[j]; }
-    }
-  } else {
-    // stride 2: output row o consumes input rows 2o (kh=0), 2o+1 (kh=1), 2o+2 (kh=2); the even input row
-    // 2o also finishes output row o-1.
-    float A0[TW][8], A1[TW][8];
-    d.arm(A0); d.arm(A1);
-    const int hi0 = 2 * ho_lo - 1;
-#pragma unroll 1
-    for (int o = 0; o <= n_out; ++o) {
-      d.load_row(hi0 + 2 * o, in);
-      d.mac(A0, in, 0); d.mac(A1, in, 2);
-      d.store_row(A1, ho_lo + o - 1, ho_lo, ho_hi);
-      if (o < n_out) { d.load_row(hi0 + 2 * o + 1, in); d.mac(A0, in, 1); }
-#pragma unroll
-      for (int t = 0; t < TW; ++t)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { A1[t][j] = A0[t][j]; A0[t][j] = d.bias8[j]; }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 // y[b,ho,wo,0:Cs] = skip ; y[b,ho,wo,Cs:] = bilinear x2 (align_corners=False) of x.
 // One thread = one 16-byte channel vector of a 2x2 block of output pixels: the 3x3 source
 // neighbourhood is loaded and converted once (9 loads for 4 outputs instead of 16) and the
@@ -834,17 +690,6 @@ int b200seg_dwconv3x3(const void* x, const float* w, const float* b, void* y, in
     dwconv3x3_bf16_kernel<S, TW, TH><<<grid_for(total, threads), threads, 0, st>>>((const bf16*)x, w, b, (bf16*)y, \
                                                                                    B, H, W, C, Ho, Wo, act);      \
   }
-#define LAUNCH3(S, TW, RH)                                                                                       \
-  {                                                                                                               \
-    const long long total = (long long)B * ((Ho + RH - 1) / RH) * ((Wo + TW - 1) / TW) * (C / 8);                 \
-    dwconv3x3_rows_kernel<S, TW><<<grid_for(total, threads), threads, 0, st>>>((const bf16*)x, w, b, (bf16*)y, B, H, \
-                                                                               W, C, Ho, Wo, RH, act);            \
-  }
-    if (variant >= 10 && variant < 100) {      // row streaming: variant = 10*TW + log2(RH)  (e.g. 23 = TW 2, RH 8)
-      const int twv = variant / 10, rh = 1 << (variant % 10);
-      if (stride == 1) { if (twv == 1) LAUNCH3(1, 1, rh) else if (twv == 2) LAUNCH3(1, 2, rh) else LAUNCH3(1, 4, rh) }
-      else { if (twv == 1) LAUNCH3(2, 1, rh) else if (twv == 2) LAUNCH3(2, 2, rh) else LAUNCH3(2, 4, rh) }
-    } else
     if (stride == 1) {
       if (variant == 1) LAUNCH2(1, 2, 1) else if (variant == 2) LAUNCH2(1, 4, 1) else if (variant == 3) LAUNCH2(1, 4, 2)
       else if (variant == 9) LAUNCH(bf16, 1, 4) else if (variant == 4) LAUNCH2(1, 2, 2) else LAUNCH2(1, 4, 2)   // default: 4x2 block (measured best)
@@ -853,7 +698,6 @@ int b200seg_dwconv3x3(const void* x, const float* w, const float* b, void* y, in
       else if (variant == 9) LAUNCH(bf16, 2, 2) else if (variant == 4) LAUNCH2(2, 2, 2) else LAUNCH2(2, 4, 1)   // default: 4x1 strip (measured best)
     }
 #undef LAUNCH2
-#undef LAUNCH3
   } else {
     if (stride == 1) LAUNCH(float, 1, 4) else LAUNCH(float, 2, 2)
   }

@@ -196,3 +196,45 @@ def test_plain_unet_fp32_and_bf16():
     _note("unet_eval", err=e, err_vs_frozen_reference=e_frozen, err_bf16=e16)
     assert e < 1e-4 and e_frozen < 1e-4
     assert e16 < 3e-2
+
+
+def test_full_size_batch_properties_bf16():
+    """BASELINE config[1] at full size (batch 64, 3x256x512, bf16): size-independent properties instead of an oracle
+    run -- (1) deterministic: two passes are bit-identical; (2) frames are independent: image b of the batch equals
+    the same image run alone (eval-mode BN folds into the weights, each accumulator sums K in a fixed order);
+    (3) the fused mask equals the argmax of the fp32-interpolated logits wherever the top-2 margin exceeds the bf16
+    rounding of the logits; (4) sharding by frame (two half batches) reproduces the full batch."""
+    torch.manual_seed(0)
+    m = b200seg.MobileNetV2UNet(output_channels=10).to(DEV).bfloat16().eval()
+    x = torch.randn(64, 3, 256, 512, device=DEV).bfloat16()
+    with torch.no_grad():
+        y1 = m(x).clone()
+        y2 = m(x).clone()
+        assert y1.shape == (64, 10, 256, 512) and torch.equal(y1, y2)
+        for b in (0, 17, 63):
+            assert torch.equal(m(x[b:b + 1].contiguous())[0], y1[b]), b
+        halves = torch.cat([m(x[:32].contiguous()), m(x[32:].contiguous())], 0)
+        assert torch.equal(halves, y1)
+        mask = m.predict_mask(x)
+        top2 = y1.float().topk(2, dim=1).values
+        clear = (top2[:, 0] - top2[:, 1]) > 0.05 * top2[:, 0].abs().clamp_min(1e-3)
+        assert clear.float().mean() > 0.2
+        assert bool((mask.long() == y1.float().argmax(1))[clear].all())
+
+
+def test_padded_720p_frame_fp32_matches_oracle():
+    """BASELINE config[4] geometry: a 720x1280 frame must be padded to 736 rows (the reference itself fails on 720,
+    unet.py:103); the padded tensor through the CUDA path equals the oracle on the same padded tensor."""
+    sd = fixture_sd()
+    m = b200seg.MobileNetV2UNet(output_channels=10)
+    m.load_state_dict(expand_aliases(sd), strict=True)
+    m = m.to(DEV).eval()
+    frame = O.synth_input(1, 720, 1280, seed=4)
+    xp = torch.nn.functional.pad(frame, (0, 0, 0, 16))
+    with torch.no_grad():
+        ref = O.mobilenetv2_unet_forward(sd, xp)
+        y = m(xp.to(DEV)).cpu()
+    e = rel_err(y, ref)
+    agree = (y.argmax(1) == ref.argmax(1)).float().mean().item()
+    _note("fp32_eval_736x1280", err=e, argmax_agree=agree)
+    assert y.shape == (1, 10, 736, 1280) and e < 1e-4 and agree >= 0.999

@@ -365,37 +365,40 @@ def test_bf16_training_path_tracks_fp32():
 
 
 def test_train_step_cuda_graph_replay_matches_eager():
-    """From the third step on the fwd/bwd passes are replayed from CUDA graphs: same losses, same parameters as the
-    eager launches, running statistics and num_batches_tracked included."""
+    """The CUDA-graph replay computes the same step as the kernel-by-kernel launches.  Compared after ONE step from
+    identical state (graph captured on the first call): the forward is deterministic, so the loss and every BatchNorm
+    running statistic must be bit-identical; parameters agree up to the summation order of the float atomics in the
+    weight-gradient kernels.  A longer run then checks that replays keep advancing the state."""
     sd = fixture_sd()
 
-    def run(use_graphs):
+    def make(use_graphs, graph_after):
         m = b200seg.MobileNetV2UNet(output_channels=10)
         m.load_state_dict(expand_aliases(sd), strict=True)
         m = m.to(DEV).train()
-        m._get_engine().use_graphs = use_graphs
-        opt = torch.optim.Adam(m.parameters(), lr=1.5e-4)
-        crit = b200seg.CrossEntropyLoss()
-        losses = []
-        for i in range(6):
-            x, t = O.synth_input(2, 64, 64, seed=30 + i).to(DEV), O.synth_target(2, 64, 64, seed=30 + i).to(DEV)
-            opt.zero_grad()
-            loss = crit(m(x), t)
-            loss.backward()
-            opt.step()
-            losses.append(loss.item())
-        captured = any(getattr(e.get("graph"), "bwd", None) is not None for e in m._get_engine()._graphs.values())
-        return losses, {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}, captured
+        eng = m._get_engine()
+        eng.use_graphs, eng.graph_after = use_graphs, graph_after
+        return m, torch.optim.Adam(m.parameters(), lr=1.5e-4), b200seg.CrossEntropyLoss()
 
-    l_e, sd_e, cap_e = run(False)
-    l_g, sd_g, cap_g = run(True)
-    assert cap_g and not cap_e
-    # weight gradients use float atomics (summation order varies run to run), so agreement is tight but not bitwise
-    assert abs(l_e[0] - l_g[0]) < 1e-6 and max(abs(a - b) for a, b in zip(l_e, l_g)) < 5e-3, (l_e, l_g)
-    assert int(sd_g["outc.conv.1.num_batches_tracked"]) == 6
-    for k in ("outc.conv.3.weight", "up1.conv.conv.0.weight", "backbone.features.0.0.weight", "backbone.features.18.1.running_var"):
-        if "running" in k:        # statistics of two slightly diverged trajectories (float atomics reorder sums)
-            assert torch.allclose(sd_e[k], sd_g[k], rtol=1e-2, atol=1e-3), k
-            continue
-        assert torch.allclose(sd_e[k], sd_g[k], rtol=0, atol=4 * 6 * 1.5e-4), k
-        assert float((sd_e[k] - sd_g[k]).abs().mean()) < 8e-5 + (1e-4 if "running" in k else 0), k
+    def one(m, opt, crit, seed):
+        x, t = O.synth_input(2, 64, 64, seed=seed).to(DEV), O.synth_target(2, 64, 64, seed=seed).to(DEV)
+        opt.zero_grad()
+        loss = crit(m(x), t)
+        loss.backward()
+        opt.step()
+        return loss.item()
+
+    me, oe, ce = make(False, 2)
+    mg, og, cg = make(True, 0)
+    le, lg = one(me, oe, ce, 30), one(mg, og, cg, 30)
+    assert any(getattr(e.get("graph"), "bwd", None) is not None for e in mg._get_engine()._graphs.values()), "not captured"
+    assert le == lg
+    sde, sdg = me.state_dict(), mg.state_dict()
+    for k in sde:
+        if "running" in k or "num_batches" in k:
+            assert torch.equal(sde[k], sdg[k]), k
+    for k in ("outc.conv.3.weight", "up1.conv.conv.0.weight", "backbone.features.0.0.weight", "backbone.features.18.1.weight"):
+        d = (sde[k] - sdg[k]).abs()
+        assert float(d.max()) <= 2 * 1.5e-4 + 1e-7 and float(d.mean()) < 1e-6, (k, float(d.max()), float(d.mean()))
+    losses = [one(mg, og, cg, 31 + i) for i in range(5)]
+    assert all(l == l and l < 10 for l in losses)
+    assert int(mg.state_dict()["outc.conv.1.num_batches_tracked"]) == 6
