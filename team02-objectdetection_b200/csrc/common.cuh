@@ -17,6 +17,31 @@ int set_error(int code, const char* fmt, ...);
 int check_launch(const char* what);          // cudaPeekAtLastError -> code
 int sm_count();
 
+// Programmatic dependent launch: a kernel launched through launch_pdl may start (prologue: barrier init, TMEM
+// allocation, weight loads) while the previous kernel of the stream drains.  Every such kernel executes
+// pdl_wait() before it touches memory a previous kernel wrote (or that a previous kernel still reads and this
+// one writes), and pdl_trigger() as early as possible.  B200SEG_PDL=0 turns the launch attribute off.
+int pdl_mode();      // 0 off, 1 every forward kernel + early trigger, 2 conv_tc only, 3 all + late trigger in conv_tc
+template <typename... KA, typename... A>
+inline cudaError_t launch_pdl_if(bool on, void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = on ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KA(args)...);
+}
+template <typename... KA, typename... A>
+inline cudaError_t launch_pdl(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... args) {
+  const int m = pdl_mode();
+  return launch_pdl_if(m == 1 || m == 3, kern, grid, block, smem, st, args...);
+}
+
 #define B200_REQUIRE(cond, ...)                                   \
   do {                                                            \
     if (!(cond)) return ::b200::set_error(-1, __VA_ARGS__);       \
@@ -83,6 +108,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
 }
 
 // one lane of the (converged) warp; ptxas keeps the guarded code in the uniform datapath
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(

@@ -47,6 +47,7 @@ struct ConvTcArgs {
   int tmem_cols;
   int halo;          // A addressing mode (see above)
   int b_resident;    // weights loaded once per CTA
+  int pdl_early;     // trigger dependents at kernel start (else just before the final barrier)
   int n_sbuf;        // staging buffers (1 or 2)
   int halo_bo;       // HALO: put the swizzle phase of the shifted start address into descriptor.base_offset
   int dw;            // depthwise mode: B is block-diagonal, the only K chunk of N tile j is channel chunk j
@@ -92,6 +93,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* b_full = acc_empty + 2;    // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
 
+  if (a.pdl_early) pdl_trigger();      // the next kernel's prologue may overlap this kernel's tail
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -125,6 +127,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int c = 0; c < a.k_chunks; ++c)
           tma_load_3d(sB + (t * a.k_chunks + c) * b_tile_bytes, &tmB, b_full, c * 64, t, 0);
     }
+    pdl_wait();         // weights are static; activations come from the previous kernel
     int s = 0;
     uint32_t ph = 0;
     const int n_outer = a.halo ? a.k_chunks : a.taps;      // HALO: chunks x 3 rows;  TAP: taps x chunks
@@ -259,6 +262,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const float act_lo = (a.act != B200SEG_ACT_NONE) ? 0.f : -INFINITY;
     const float act_hi = (a.act == B200SEG_ACT_RELU6) ? 6.f : INFINITY;
     const bool vec32 = (a.Cout & 15) == 0;     // pixel pitch is a multiple of 32 B -> 256-bit accesses
+    pdl_wait();         // residual reads / output writes must follow the previous kernel
     int it = 0;
     int cur_n_tile = -1;
     for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
@@ -376,6 +380,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (a.tma_store && et == 0) tma_store_wait_all();
     tc_fence_before();
   }
+  if (!a.pdl_early) pdl_trigger();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -540,8 +545,9 @@ static int launch_conv_tc(const void* x, const void* w, const float* bias, const
   long long grid = (long long)sm_count() * per_sm;
   if ((flags >> 8) & 0xff) grid = (long long)((flags >> 8) & 0xff) * 4;
   if (grid > a.total_tiles) grid = a.total_tiles;
-  if (a.mpair == 2) conv_tc_kernel<2><<<(unsigned)grid, TC_THREADS, smem, stream>>>(tmA, tmB, tmC, a);
-  else conv_tc_kernel<1><<<(unsigned)grid, TC_THREADS, smem, stream>>>(tmA, tmB, tmC, a);
+  a.pdl_early = pdl_mode() != 3;
+  if (a.mpair == 2) launch_pdl_if(pdl_mode() > 0, conv_tc_kernel<2>, dim3((unsigned)grid), dim3(TC_THREADS), (size_t)smem, stream, tmA, tmB, tmC, a);
+  else launch_pdl_if(pdl_mode() > 0, conv_tc_kernel<1>, dim3((unsigned)grid), dim3(TC_THREADS), (size_t)smem, stream, tmA, tmB, tmC, a);
   return check_launch("conv_tc");
 }
 

