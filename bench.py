@@ -121,6 +121,29 @@ def cpu_reference_leg(seconds=12.0, warmup=2, fixed_iters=None):
                 ms_per_image=tot / len(times) * 1e3)
 
 
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """stdout carries exactly ONE JSON line: libraries that write to fd 1 (NCCL's version banner under NCCL_DEBUG) are
+    sent to stderr for the whole run and emit() writes the line to the original descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -138,11 +161,12 @@ def run_reference(args):
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": wall}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
     args = parse()
+    protect_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -312,7 +336,7 @@ def main():
             "roofline": roofline, "step_roofline": step_roofline, "clocks": clk}
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

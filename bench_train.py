@@ -138,6 +138,7 @@ def run_train(args, dev, dist, world, rank, pk):
                          "note": "whole-step algorithmic bytes / step time; per-layer shares in --breakdown",
                          "share_of_step": top_ms / tot},
             "gpu_launches": None, "clocks": clk}
-    print(json.dumps(line), flush=True)
+    from bench import emit
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
