@@ -53,12 +53,13 @@ def run_train(args, dev, dist, world, rank, pk):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        step(xs[i % nrot], ys[i % nrot])
-    barrier()
     clocks = ClockSampler(dev.index or 0)
     if rank == 0:
         clocks.start()
+    for i in range(args.warmup):
+        step(xs[i % nrot], ys[i % nrot])
+    barrier()
+    clocks.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     import time
     e0.record()

@@ -94,6 +94,17 @@ int b200seg_upsample2x_ac_nchw(const void* logits, int dtype, int ldc, void* out
 int b200seg_upsample2x_ac_argmax(const void* logits, int dtype, int ldc, uint8_t* mask, int B, int h,
                                  int w, int C, b200seg_stream_t s);
 
+/* One fused torchvision InvertedResidual block with expand ratio > 1, eval mode, BatchNorm folded, bf16
+ * (tv:models/mobilenetv2.py:38-62 -- ConvBNReLU6 1x1 expand, ConvBNReLU6 depthwise 3x3 stride s, ConvBN 1x1
+ * project, + x when stride 1 and Cin == Cout; reached through unet.py:15-19,34-42).  The expanded activation
+ * stays in shared memory / TMEM.
+ *   x [B,H,W,Cin] bf16;  w_exp [Ce][Cin] bf16;  w_proj [Cout][Ce] bf16;  y [B,Ho,Wo,Cout] bf16
+ *   b_exp, b_dw: f32 [ceil64(Ce)] zero padded;  w_dw: f32 [9][ceil64(Ce)] zero padded;  b_proj: f32 [ceil16(Cout)]
+ *   flags: tuning only (0 = heuristics). */
+int b200seg_mbconv(const void* x, const void* w_exp, const float* b_exp, const float* w_dw, const float* b_dw,
+                   const void* w_proj, const float* b_proj, int residual, void* y, int B, int H, int W, int Cin,
+                   int Ce, int Cout, int stride, int flags, b200seg_stream_t s);
+
 /* NHWC [B,H,W,ldc] (first C valid) -> NCHW [B,C,H,W] (UNet returns logits at input resolution). */
 int b200seg_nhwc_to_nchw(const void* x, int dtype, int ldc, void* out, int out_dtype, int B, int H, int W,
                          int C, b200seg_stream_t s);

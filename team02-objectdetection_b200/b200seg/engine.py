@@ -40,6 +40,7 @@ class Step:
     taps: int = 1
     res: Optional[str] = None    # residual source (dense) / skip source (upcat)
     pad_cout: int = 0            # pad output channels (logits 10 -> 16)
+    parts: Optional[tuple] = None   # op == "mbconv": the (expand, depthwise, project) steps it replaces
 
 
 def _double_conv_steps(prefix: str, dc, src: str, dst: str) -> List[Step]:
@@ -116,6 +117,9 @@ class Engine:
         self.precision: Optional[str] = None       # None = derive from module dtype / autocast
         self.dense_impl: Optional[str] = None       # None = "tc" for bf16, "simt" for fp32 (tests may force)
         self.dw_impl: Optional[str] = None          # None = per-layer choice; "tc" / "simt" force one kernel
+        self.mbconv_impl: Optional[str] = None      # None = per-block choice; "fused" / "unfused" force (eval bf16 only)
+        self.mbconv_flags = 0
+        self._eval_sched: Dict[tuple, List[Step]] = {}
         self.tc_flags = 0
         self._packed: Dict[str, dict] = {}
         self._packed_key = None
@@ -163,8 +167,60 @@ class Engine:
                         b = torch.cat([b, b.new_zeros(s.pad_cout - cout)], 0)
                     wk = wk.to(torch.bfloat16) if dense_impl == "tc" else wk
                     packed[s.name] = dict(w=wk.contiguous(), b=b.contiguous())
+            if mode == "bf16" and dense_impl == "tc":
+                # operands of the fused inverted-residual kernel: the three layers' packs, parameter vectors zero
+                # padded to the 64-channel chunks the kernel processes
+                for e, d, pj in self._mb_triples():
+                    packed[pj.name + "#mb"] = dict(
+                        w_exp=packed[e.name]["w"], b_exp=ops.pad_channels(packed[e.name]["b"], 64),
+                        w_dw=ops.pad_channels(packed[d.name]["w"], 64), b_dw=ops.pad_channels(packed[d.name]["b"], 64),
+                        w_proj=packed[pj.name]["w"], b_proj=ops.pad_channels(packed[pj.name]["b"], 16))
         self._packed, self._packed_key = packed, key
         return packed
+
+    # ------------------------------------------------------------------ fused inverted-residual blocks
+    def _mb_triples(self):
+        """(expand 1x1, depthwise 3x3, project 1x1) step triples of the encoder's expand-ratio-6 blocks."""
+        out = []
+        st = self.steps
+        for i in range(len(st) - 2):
+            e, d, pj = st[i], st[i + 1], st[i + 2]
+            if (e.op == "dense" and e.taps == 1 and e.act == ACT_RELU6 and e.res is None and d.op == "dw"
+                    and d.src == e.dst and pj.op == "dense" and pj.taps == 1 and pj.src == d.dst
+                    and pj.act == ACT_NONE and not pj.pad_cout and (pj.res is None or pj.res == e.src)):
+                out.append((e, d, pj))
+        return out
+
+    def _schedule(self, mode: str, dense_impl: str, H: int, W: int) -> List[Step]:
+        """Eval schedule for an input of H x W: self.steps with the inverted-residual triples replaced by one
+        fused step where the fused kernel is the faster one (measured, tools/kbench_mb.py: every block except the
+        stride-2 block at half resolution, whose 4x-larger expanded tile makes the CUDA-core phases dominate)."""
+        impl = self.mbconv_impl or "auto"
+        if mode != "bf16" or dense_impl != "tc" or impl == "unfused":
+            return self.steps
+        key = (impl, H, W)
+        if key not in self._eval_sched:
+            first = {id(e): (e, d, pj) for e, d, pj in self._mb_triples()}
+            out, skip = [], set()
+            scale = {}                       # schedule name -> downscale factor of its tensor w.r.t. the input
+            for st in self.steps:
+                scale[st.dst] = scale.get(st.src, 1) * (st.stride if st.op in ("stem", "dw") else 1)
+                if st.op == "upcat":
+                    scale[st.dst] = scale[st.src] // 2
+            for st in self.steps:
+                if id(st) in skip:
+                    continue
+                if id(st) in first:
+                    e, d, pj = first[id(st)]
+                    in_w = W // max(scale.get(e.src, 1), 1)
+                    if impl == "fused" or not (d.stride == 2 and in_w >= 256):
+                        out.append(Step("mbconv", pj.name.rsplit(".conv.", 1)[0], e.src, pj.dst, stride=d.stride,
+                                        res=pj.res, parts=(e, d, pj)))
+                        skip.update((id(d), id(pj)))
+                        continue
+                out.append(st)
+            self._eval_sched[key] = out
+        return self._eval_sched[key]
 
     # ------------------------------------------------------------------ helpers
     def _mode(self, x: torch.Tensor) -> str:
@@ -215,6 +271,10 @@ class Engine:
                 env[s.dst] = ops.conv_tc(env[s.src], p["w"], p["b"], s.taps, s.act, res, flags=self.tc_flags)
             else:
                 env[s.dst] = ops.conv_simt(env[s.src], p["w"], p["b"], s.taps, s.act, res)
+        elif s.op == "mbconv":
+            p = pk[s.parts[2].name + "#mb"]
+            env[s.dst] = ops.mbconv(env[s.src], p["w_exp"], p["b_exp"], p["w_dw"], p["b_dw"], p["w_proj"], p["b_proj"],
+                                    s.stride, s.res is not None, flags=self.mbconv_flags)
         elif s.op == "upcat":
             env[s.dst] = ops.upsample2x_concat(env[s.res], env[s.src])
         elif s.op == "pool":
@@ -253,9 +313,11 @@ class Engine:
         x = x.contiguous()
         out_dtype = x.dtype
         args = (pk, mode, sdt, dense_impl, out_dtype, want_mask)
+        steps = self._schedule(mode, dense_impl, x.shape[2], x.shape[3])
 
         if keep is None and profile is None and self.use_graphs and not torch.cuda.is_current_stream_capturing():
-            key = (tuple(x.shape), x.dtype, mode, dense_impl, self.dw_impl, self.tc_flags, self._packed_key, x.device)
+            key = (tuple(x.shape), x.dtype, mode, dense_impl, self.dw_impl, self.mbconv_impl, self.tc_flags,
+                   self.mbconv_flags, self._packed_key, x.device)
             ent = self._graphs.get(key)
             if ent is None:
                 if len(self._graphs) >= 3:
@@ -263,7 +325,7 @@ class Engine:
                 ent = self._graphs[key] = {"seen": 0, "graph": None}
             ent["seen"] += 1
             if ent["graph"] is None and ent["seen"] > self.graph_after:
-                self._capture(ent, x, args)
+                self._capture(ent, x, args, steps)
             if ent["graph"] is not None:
                 env = {"x": x, ent["head_dst"]: ent["head_out"]}
                 ops.conv3x3_smallcin(x, *ent["head_args"], out=ent["head_out"])
@@ -273,7 +335,7 @@ class Engine:
                 return env["out"]
 
         env: Dict[str, torch.Tensor] = {"x": x}
-        for s in self.steps:
+        for s in steps:
             if profile is not None:
                 ev0 = torch.cuda.Event(enable_timing=True); ev0.record()
             self._run_step(s, env, *args)
@@ -285,11 +347,11 @@ class Engine:
             keep.update(env)
         return env["out"]
 
-    def _capture(self, ent, x, args):
+    def _capture(self, ent, x, args, steps):
         """Capture steps[1:-1] into a CUDA graph.  Buffers allocated inside the capture come from the
         graph's private pool and stay valid for every replay."""
         pk, mode, sdt, dense_impl, out_dtype, want_mask = args
-        head, body, tail = self.steps[0], self.steps[1:-1], self.steps[-1]
+        head, body, tail = steps[0], steps[1:-1], steps[-1]
         assert head.op == "stem" and tail.op in ("final", "to_nchw")
         p = pk[head.name]
         ent["head_args"] = (p["w"], p["b"], head.stride, head.act, sdt)
@@ -313,6 +375,18 @@ class Engine:
         out = env[s.dst]
         nbytes = out.numel() * out.element_size() + env[s.src].numel() * env[s.src].element_size()
         flops = 0
+        if s.op == "mbconv":
+            # algorithmic bytes of the FUSED block: input, output, residual and the three weight sets once
+            e, d, pj = s.parts
+            p = pk[pj.name + "#mb"]
+            ce = e.conv.weight.shape[0]
+            npix_in = env[s.src].numel() // env[s.src].shape[-1]
+            npix_out = out.numel() // out.shape[-1]
+            if s.res:
+                nbytes += env[s.res].numel() * env[s.res].element_size()
+            nbytes += (p["w_exp"].numel() + p["w_proj"].numel() + 9 * ce) * 2 + (2 * ce + out.shape[-1]) * 4
+            flops = 2 * (npix_in * ce * env[s.src].shape[-1] + npix_out * ce * 9 + npix_out * ce * out.shape[-1])
+            return nbytes, flops
         if s.res:
             nbytes += env[s.res].numel() * env[s.res].element_size()
         if s.conv is not None:

@@ -118,6 +118,39 @@ def conv_simt(x, w, b, taps: int, act: int, res=None, out=None):
     return out
 
 
+def pad_channels(t: torch.Tensor, mult: int) -> torch.Tensor:
+    """Zero-pad the LAST dim of a parameter vector/matrix to a multiple of `mult` (fused-block operand layout)."""
+    c = t.shape[-1]
+    cp = (c + mult - 1) // mult * mult
+    if cp == c:
+        return t.contiguous()
+    out = torch.zeros((*t.shape[:-1], cp), device=t.device, dtype=t.dtype)
+    out[..., :c] = t
+    return out
+
+
+def mbconv(x, w_exp, b_exp, w_dw, b_dw, w_proj, b_proj, stride: int, residual: bool, out=None, flags: int = 0):
+    """Fused inverted-residual block (expand 1x1 + ReLU6 -> depthwise 3x3 + ReLU6 -> project 1x1 [+ x]), bf16 NHWC.
+    w_exp [Ce, Cin] bf16, w_proj [Cout, Ce] bf16; b_exp/b_dw f32 [ceil64(Ce)], w_dw f32 [9, ceil64(Ce)],
+    b_proj f32 [ceil16(Cout)] (see pad_channels)."""
+    _cuda(x, w_exp, b_exp, w_dw, b_dw, w_proj, b_proj)
+    if x.dtype != torch.bfloat16 or w_exp.dtype != torch.bfloat16 or w_proj.dtype != torch.bfloat16:
+        raise TypeError("mbconv is bf16-only")
+    B, H, W, Cin = x.shape
+    Ce, Cout = w_exp.shape[0], w_proj.shape[0]
+    cep, cop = (Ce + 63) // 64 * 64, (Cout + 15) // 16 * 16
+    if (tuple(w_exp.shape) != (Ce, Cin) or tuple(w_proj.shape) != (Cout, Ce) or tuple(w_dw.shape) != (9, cep)
+            or b_exp.numel() != cep or b_dw.numel() != cep or b_proj.numel() != cop):
+        raise ValueError(f"mbconv: operand shapes w_exp {tuple(w_exp.shape)} w_dw {tuple(w_dw.shape)} "
+                         f"w_proj {tuple(w_proj.shape)} b {b_exp.numel()},{b_dw.numel()},{b_proj.numel()}")
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    if out is None:
+        out = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=torch.bfloat16)
+    check(lib.b200seg_mbconv(ptr(x), ptr(w_exp), ptr(b_exp), ptr(w_dw), ptr(b_dw), ptr(w_proj), ptr(b_proj),
+                             1 if residual else 0, ptr(out), B, H, W, Cin, Ce, Cout, stride, flags, _stream()), "mbconv")
+    return out
+
+
 def upsample2x_concat(skip, x, out=None):
     """cat([skip, bilinear_x2(x, align_corners=False)], channel) in NHWC."""
     _cuda(skip, x)

@@ -157,6 +157,40 @@ def test_cuda_graph_replay_matches_eager_launches(model_and_sd):
         eng.precision = None
 
 
+def test_fused_inverted_residual_blocks_match_unfused_layers(model_and_sd):
+    """bf16 eval replaces each expand->depthwise->project triple of the encoder by one fused kernel that rounds the
+    two intermediate activations to bf16 at the same points: logits and every stage output must equal the
+    layer-by-layer path up to fp32 summation order inside the 1x1 convs (1e-2 of the range per stage)."""
+    m, _ = model_and_sd
+    eng = m._get_engine()
+    eng.precision = "bf16"
+    try:
+        x = O.synth_input(2, 128, 192, seed=21).to(DEV)
+        outs = {}
+        for impl in ("unfused", "fused", None):
+            eng.mbconv_impl = impl
+            keep = {}
+            with torch.no_grad():
+                y = eng.forward_eval(x, keep=keep)
+            outs[impl] = (y.float(), {k: keep[k].float() for k in ("f3", "f6", "f10", "f17", "f18", "up4")})
+        sched = eng._schedule("bf16", "tc", 128, 192)
+        eng.mbconv_impl = "fused"
+        n_fused = sum(st.op == "mbconv" for st in eng._schedule("bf16", "tc", 128, 192))
+        assert n_fused == 16, n_fused                        # features.2 .. features.17
+        assert any(st.op == "mbconv" for st in sched)
+        for impl in ("fused", None):
+            for k, ref in outs["unfused"][1].items():
+                e = rel_err(outs[impl][1][k], ref)
+                assert e < 2e-2, (impl, k, e)
+            e = rel_err(outs[impl][0], outs["unfused"][0])
+            agree = (outs[impl][0].argmax(1) == outs["unfused"][0].argmax(1)).float().mean().item()
+            _note("fused_mbconv_vs_unfused", impl=str(impl), err=e, argmax_agree=agree)
+            assert e < 2e-2 and agree > 0.97, (impl, e, agree)
+    finally:
+        eng.precision = None
+        eng.mbconv_impl = None
+
+
 def test_weight_update_invalidates_packed_weights(model_and_sd):
     m, sd = model_and_sd
     x = O.synth_input(1, 32, 64, seed=9).to(DEV)
