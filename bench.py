@@ -194,7 +194,7 @@ def main():
 
     if args.workload in ("train", "unet_train"):
         from bench_train import run_train          # training step benchmark lives in its own file
-        return run_train(args, dev, dist, world, rank, peaks())
+        return run_train(args, dev, dist, world, rank, peaks(), ClockSampler, emit)
 
     global H, W
     if args.workload == "infer720":

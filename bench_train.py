@@ -15,10 +15,9 @@ import torch
 H, W, NCLS = 256, 512, 10
 
 
-def run_train(args, dev, dist, world, rank, pk):
+def run_train(args, dev, dist, world, rank, pk, ClockSampler, emit):
     import b200seg
     from b200seg import dp, train_path
-    from bench import ClockSampler
     global H, W
     unet = args.workload == "unet_train"
     if unet:
@@ -139,7 +138,6 @@ def run_train(args, dev, dist, world, rank, pk):
                          "note": "whole-step algorithmic bytes / step time; per-layer shares in --breakdown",
                          "share_of_step": top_ms / tot},
             "gpu_launches": None, "clocks": clk}
-    from bench import emit
-    emit(line)
+    emit(line)                # bench.py's emitter: the ONE stdout line (bench.py runs as __main__, do not re-import it)
     if dist is not None:
         dist.destroy_process_group()

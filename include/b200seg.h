@@ -129,14 +129,18 @@ int b200seg_softmax_ce(const float* logits, const int64_t* target, float* loss_s
 /* ---------------------------------------------------------------------------------------------
  * Training path (train.py:35-39: model.train() forward, loss.backward()).  Activations NHWC viewed as
  * [P = B*H*W pixels, C]; per-channel statistics are accumulated across CTAs in f64 buffers the caller
- * zeroes.  dgrad of the dense convs reuses b200seg_conv_simt / b200seg_conv_tc with transposed weights.
+ * zeroes.  Reduction outputs come in `nslot` copies `slot_stride` doubles apart (CTA i adds into copy i % nslot;
+ * the consumer -- bn_finalize / f64_to_f32 -- sums the copies): one copy serialises ~1200 atomics per address.
+ * dgrad of the dense convs reuses b200seg_conv_simt / b200seg_conv_tc with transposed weights.
  * --------------------------------------------------------------------------------------------- */
 /* native_batch_norm (training): sum[c] += sum_p (z-k), sumsq[c] += sum_p (z-k)^2 with the per-channel shift k = z at
  * pixel 0 (shifted sums: no catastrophic cancellation for nearly constant channels); bn_finalize adds k back. */
-int b200seg_bn_stats(const void* z, int dtype, long long P, int C, double* sum, double* sumsq, b200seg_stream_t s);
+int b200seg_bn_stats(const void* z, int dtype, long long P, int C, double* sum, double* sumsq, int nslot,
+                     long long slot_stride, b200seg_stream_t s);
 /* mean/biased var -> invstd; scale = gamma*invstd, shift = beta - mean*scale; running stats updated with
  * momentum and the unbiased variance (nn.BatchNorm2d defaults); running_* may be NULL. */
-int b200seg_bn_finalize(const void* z, int dtype, const double* sum, const double* sumsq, long long n, const float* gamma,
+int b200seg_bn_finalize(const void* z, int dtype, const double* sum, const double* sumsq, int nslot,
+                        long long slot_stride, long long n, const float* gamma,
                         const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                         float* mean, float* invstd, float* scale, float* shift, int C, b200seg_stream_t s);
 /* a = act(z*scale + shift) (+ res)   -- BN apply + ReLU/ReLU6 (+ inverted-residual shortcut) */
@@ -146,7 +150,7 @@ int b200seg_bn_apply(const void* z, const float* scale, const float* shift, cons
  * g = da * act'(z*scale+shift), xhat = (z-mean)*invstd.   (d beta = sg, d gamma = sgx) */
 int b200seg_bn_bwd_reduce(const void* da, const void* z, const float* scale, const float* shift, const float* mean,
                           const float* invstd, int dtype, long long P, int C, int act, double* sg, double* sgx,
-                          b200seg_stream_t s);
+                          int nslot, long long slot_stride, b200seg_stream_t s);
 /* pass 2: dz = scale * (g - sg/P - xhat * sgx/P); sg/sgx are the pass-1 sums converted to f32 (f64 arithmetic in
  * the per-element loop would run at 1/64 rate) */
 int b200seg_bn_bwd_apply(const void* da, const void* z, const float* scale, const float* shift, const float* mean,
@@ -154,9 +158,11 @@ int b200seg_bn_bwd_apply(const void* da, const void* z, const float* scale, cons
                          int C, int act, b200seg_stream_t s);
 /* dz = da * act'(a_out) for a layer without BatchNorm */
 int b200seg_act_bwd(const void* da, const void* a_out, void* dz, int dtype, long long N, int act, b200seg_stream_t s);
-/* out[c] += sum_p x[p][c]  (bias gradients) ; f64 -> f32 with a scale */
-int b200seg_colsum(const void* x, int dtype, long long P, int C, double* out, b200seg_stream_t s);
-int b200seg_f64_to_f32(const double* in, float* out, int n, float scale, b200seg_stream_t s);
+/* out[slot][c] += sum_p x[p][c]  (bias gradients) ; out[i] = scale * sum_slot in[slot*slot_stride + i] as f32 */
+int b200seg_colsum(const void* x, int dtype, long long P, int C, double* out, int nslot, long long slot_stride,
+                   b200seg_stream_t s);
+int b200seg_f64_to_f32(const double* in, float* out, int n, int nslot, long long slot_stride, float scale,
+                       b200seg_stream_t s);
 /* convolution_backward (weight): dw f32 [Cout][taps][Cin] += sum_p dz[p][co] * x[p shifted by tap][ci]; caller zeroes dw */
 int b200seg_conv_wgrad(const void* x, const void* dz, float* dw, int dtype, int B, int H, int W, int Cin, int Cout,
                        int taps, b200seg_stream_t s);

@@ -36,14 +36,14 @@ _PROTOS = {
     "b200seg_maxpool2x2": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "b200seg_softmax_ce": [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _vp],
     # training path
-    "b200seg_bn_stats": [_vp, _i, _ll, _i, _vp, _vp, _vp],
-    "b200seg_bn_finalize": [_vp, _i, _vp, _vp, _ll, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+    "b200seg_bn_stats": [_vp, _i, _ll, _i, _vp, _vp, _i, _ll, _vp],
+    "b200seg_bn_finalize": [_vp, _i, _vp, _vp, _i, _ll, _ll, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "b200seg_bn_apply": [_vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _vp],
-    "b200seg_bn_bwd_reduce": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _vp, _vp, _vp],
+    "b200seg_bn_bwd_reduce": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _vp, _vp, _i, _ll, _vp],
     "b200seg_bn_bwd_apply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _vp],
     "b200seg_act_bwd": [_vp, _vp, _vp, _i, _ll, _i, _vp],
-    "b200seg_colsum": [_vp, _i, _ll, _i, _vp, _vp],
-    "b200seg_f64_to_f32": [_vp, _vp, _i, _f, _vp],
+    "b200seg_colsum": [_vp, _i, _ll, _i, _vp, _i, _ll, _vp],
+    "b200seg_f64_to_f32": [_vp, _vp, _i, _i, _ll, _f, _vp],
     "b200seg_conv_wgrad": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "b200seg_conv_wgrad_tc": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "b200seg_dw_dgrad": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],

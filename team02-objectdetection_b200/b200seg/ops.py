@@ -260,6 +260,37 @@ def softmax_ce(logits, target, want_grad: bool = True, grad_scale: Optional[floa
 # ------------------------------------------------------------------------------------------------
 # training-path wrappers (train.py:35-39).  Activations are NHWC [B,H,W,C]; P = B*H*W.
 # ------------------------------------------------------------------------------------------------
+# copies of every per-channel reduction output (see include/b200seg.h): CTA i adds into copy i % NSLOT
+NSLOT = 16
+
+
+class _ZeroPool:
+    """Zero-initialised f64 accumulators carved out of few large memsets (one fill kernel per 8 MB instead of one per
+    reduction: ~200 fewer launches per training step).  A slice is handed out once; ``reset()`` at the start of a
+    pass drops the current chunk so that a CUDA-graph capture never inherits memory zeroed outside the graph."""
+
+    def __init__(self, dtype=torch.float64, chunk=1 << 20):
+        self.buf, self.off, self.dtype, self.CHUNK = None, 0, dtype, chunk
+
+    def reset(self):
+        self.buf, self.off = None, 0
+
+    def take(self, shape, device) -> torch.Tensor:
+        n = 1
+        for d in shape:
+            n *= int(d)
+        if self.buf is None or self.buf.device != device or self.off + n > self.buf.numel():
+            self.buf = torch.zeros(max(n, self.CHUNK), device=device, dtype=self.dtype)
+            self.off = 0
+        t = self.buf[self.off:self.off + n].view(*shape)
+        self.off += (n + 3) // 4 * 4           # keep 16-byte alignment
+        return t
+
+
+zero_pool = _ZeroPool()
+zero_pool32 = _ZeroPool(torch.float32, 4 << 20)      # weight-gradient accumulators (26 MB per step)
+
+
 def _P(t):
     return t.shape[0] * t.shape[1] * t.shape[2]
 
@@ -269,10 +300,10 @@ def bn_train_forward(z, gamma, beta, running_mean, running_var, eps: float, mome
     Returns (a, saved) where saved = (mean, invstd, scale, shift) for the backward pass."""
     _cuda(z, gamma, beta, running_mean, running_var, res)
     C, P = z.shape[-1], _P(z)
-    st = torch.zeros(2, C, device=z.device, dtype=torch.float64)
-    check(lib.b200seg_bn_stats(ptr(z), _dt(z), P, C, ptr(st[0]), ptr(st[1]), _stream()), "bn_stats")
+    st = zero_pool.take((NSLOT, 2, C), z.device)                              # slot-major: [slot][sum | sumsq][C]
+    check(lib.b200seg_bn_stats(ptr(z), _dt(z), P, C, ptr(st[0, 0]), ptr(st[0, 1]), NSLOT, 2 * C, _stream()), "bn_stats")
     sv = torch.empty(4, C, device=z.device, dtype=torch.float32)
-    check(lib.b200seg_bn_finalize(ptr(z), _dt(z), ptr(st[0]), ptr(st[1]), P, ptr(gamma), ptr(beta), eps, momentum, ptr(running_mean),
+    check(lib.b200seg_bn_finalize(ptr(z), _dt(z), ptr(st[0, 0]), ptr(st[0, 1]), NSLOT, 2 * C, P, ptr(gamma), ptr(beta), eps, momentum, ptr(running_mean),
                                   ptr(running_var), ptr(sv[0]), ptr(sv[1]), ptr(sv[2]), ptr(sv[3]), C, _stream()),
           "bn_finalize")
     a = torch.empty_like(z)
@@ -284,11 +315,11 @@ def bn_train_backward(da, z, sv, act: int):
     """Returns (dz, dgamma f32[C], dbeta f32[C])."""
     _cuda(da, z, sv)
     C, P = z.shape[-1], _P(z)
-    red = torch.zeros(2, C, device=z.device, dtype=torch.float64)
+    red = zero_pool.take((NSLOT, 2, C), z.device)
     check(lib.b200seg_bn_bwd_reduce(ptr(da), ptr(z), ptr(sv[2]), ptr(sv[3]), ptr(sv[0]), ptr(sv[1]), _dt(z), P, C, act,
-                                    ptr(red[0]), ptr(red[1]), _stream()), "bn_bwd_reduce")
+                                    ptr(red[0, 0]), ptr(red[0, 1]), NSLOT, 2 * C, _stream()), "bn_bwd_reduce")
     g32 = torch.empty(2, C, device=z.device, dtype=torch.float32)
-    check(lib.b200seg_f64_to_f32(ptr(red), ptr(g32), 2 * C, 1.0, _stream()), "f64_to_f32")
+    check(lib.b200seg_f64_to_f32(ptr(red), ptr(g32), 2 * C, NSLOT, 2 * C, 1.0, _stream()), "f64_to_f32")
     dz = torch.empty_like(z)
     check(lib.b200seg_bn_bwd_apply(ptr(da), ptr(z), ptr(sv[2]), ptr(sv[3]), ptr(sv[0]), ptr(sv[1]), ptr(g32[0]), ptr(g32[1]),
                                    ptr(dz), _dt(z), P, C, act, _stream()), "bn_bwd_apply")
@@ -306,10 +337,10 @@ def colsum(x):
     """f32 [C] = sum over pixels of NHWC x."""
     _cuda(x)
     C = x.shape[-1]
-    acc = torch.zeros(C, device=x.device, dtype=torch.float64)
-    check(lib.b200seg_colsum(ptr(x), _dt(x), _P(x), C, ptr(acc), _stream()), "colsum")
+    acc = zero_pool.take((NSLOT, C), x.device)
+    check(lib.b200seg_colsum(ptr(x), _dt(x), _P(x), C, ptr(acc), NSLOT, C, _stream()), "colsum")
     out = torch.empty(C, device=x.device, dtype=torch.float32)
-    check(lib.b200seg_f64_to_f32(ptr(acc), ptr(out), C, 1.0, _stream()), "f64_to_f32")
+    check(lib.b200seg_f64_to_f32(ptr(acc), ptr(out), C, NSLOT, C, 1.0, _stream()), "f64_to_f32")
     return out
 
 
@@ -318,7 +349,7 @@ def conv_wgrad(x, dz, taps: int):
     _cuda(x, dz)
     B, H, W, Cin = x.shape
     Cout = dz.shape[-1]
-    dw = torch.zeros(Cout, taps * Cin, device=x.device, dtype=torch.float32)
+    dw = zero_pool32.take((Cout, taps * Cin), x.device)
     check(lib.b200seg_conv_wgrad(ptr(x), ptr(dz), ptr(dw), _dt(x), B, H, W, Cin, Cout, taps, _stream()), "conv_wgrad")
     return dw
 
@@ -330,7 +361,7 @@ def conv_wgrad_tc(x, dz, taps: int):
         raise TypeError("conv_wgrad_tc is bf16-only")
     B, H, W, Cin = x.shape
     Cout = dz.shape[-1]
-    dw = torch.zeros(Cout, taps * Cin, device=x.device, dtype=torch.float32)
+    dw = zero_pool32.take((Cout, taps * Cin), x.device)
     check(lib.b200seg_conv_wgrad_tc(ptr(x), ptr(dz), ptr(dw), B, H, W, Cin, Cout, taps, _stream()), "conv_wgrad_tc")
     return dw
 
@@ -347,10 +378,10 @@ def dw_wgrad(x, dz, stride: int):
     """f32 [9, C]."""
     _cuda(x, dz)
     B, H, W, Cc = x.shape
-    acc = torch.zeros(9, Cc, device=x.device, dtype=torch.float64)
+    acc = zero_pool.take((9, Cc), x.device)
     check(lib.b200seg_dw_wgrad(ptr(x), ptr(dz), ptr(acc), _dt(x), B, H, W, Cc, stride, _stream()), "dw_wgrad")
     out = torch.empty(9, Cc, device=x.device, dtype=torch.float32)
-    check(lib.b200seg_f64_to_f32(ptr(acc), ptr(out), 9 * Cc, 1.0, _stream()), "f64_to_f32")
+    check(lib.b200seg_f64_to_f32(ptr(acc), ptr(out), 9 * Cc, 1, 9 * Cc, 1.0, _stream()), "f64_to_f32")
     return out
 
 
@@ -359,7 +390,7 @@ def smallcin_wgrad(x_nchw, dz, stride: int):
     _cuda(x_nchw, dz)
     B, Cin, H, W = x_nchw.shape
     Cout = dz.shape[-1]
-    dw = torch.zeros(3, 3, Cin, Cout, device=dz.device, dtype=torch.float32)
+    dw = zero_pool32.take((3, 3, Cin, Cout), dz.device)
     check(lib.b200seg_smallcin_wgrad(ptr(x_nchw), _dt(x_nchw), ptr(dz), _dt(dz), ptr(dw), B, Cin, H, W, Cout, stride,
                                      _stream()), "smallcin_wgrad")
     return dw

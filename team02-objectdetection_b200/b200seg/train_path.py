@@ -57,6 +57,9 @@ def run_forward(engine, x: torch.Tensor, mode: str):
     tc = mode == "bf16" and (engine.dense_impl or "tc") == "tc"
     env: Dict[str, torch.Tensor] = {"x": x}
     saved: Dict[str, dict] = {}
+    ops.zero_pool.reset()
+    ops.zero_pool32.reset()
+    counters = []                          # BatchNorm.num_batches_tracked, bumped with one fused launch at the end
     for s in engine.steps:
         rec: dict = {}
         _e0 = _tick()
@@ -88,7 +91,7 @@ def run_forward(engine, x: torch.Tensor, mode: str):
                 a, sv = ops.bn_train_forward(z, s.bn.weight.detach().float(), s.bn.bias.detach().float(),
                                              s.bn.running_mean, s.bn.running_var, s.bn.eps,
                                              s.bn.momentum if s.bn.momentum is not None else 0.1, s.act, res)
-                s.bn.num_batches_tracked += 1
+                counters.append(s.bn.num_batches_tracked)
                 rec["sv"] = sv
                 env[s.dst] = a
             else:
@@ -106,6 +109,8 @@ def run_forward(engine, x: torch.Tensor, mode: str):
         saved[s.name] = rec
         if _e0 is not None:
             TRACE.append(("fwd", s.name, _e0, _tick()))
+    if counters:
+        torch._foreach_add_(counters, 1)
     return env, saved
 
 
@@ -115,6 +120,8 @@ def run_backward(engine, env, saved, mode: str, dout: torch.Tensor, emit) -> Non
     sdt = torch.bfloat16 if mode == "bf16" else torch.float32
     tc = mode == "bf16" and (engine.dense_impl or "tc") == "tc"
     g: Dict[str, torch.Tensor] = {"out": dout}
+    ops.zero_pool.reset()
+    ops.zero_pool32.reset()
     for s in reversed(engine.steps):
         rec = saved[s.name]
         _e0 = _tick()

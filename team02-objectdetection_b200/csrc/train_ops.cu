@@ -7,6 +7,7 @@
 // the same convolution with the weights transposed (and the 3x3 taps flipped), so the engine calls
 // b200seg_conv_simt / b200seg_conv_tc with a re-packed weight tensor; its "+residual" epilogue doubles
 // as the gradient accumulation for tensors with two consumers.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace b200 {
@@ -27,9 +28,19 @@ static inline dim3 red_block(int cvecs) {
 }
 // pixels per block: enough blocks (~8 per SM) to cover the memory latency even for the small deep layers, at least
 // 4 pixels per thread so the f64 atomics stay a minor cost
+static inline int red_blocks_per_sm() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("B200SEG_RED_BPS");
+    v = e ? atoi(e) : 4;
+    if (v < 1) v = 1;
+  }
+  return v;
+}
 static inline int red_ppb(long long P, const dim3& block, int cvecs) {
   const long long gy = (cvecs + block.x - 1) / block.x;
-  long long ppb = (P * gy + (long long)sm_count() * 8 - 1) / ((long long)sm_count() * 8);
+  const long long nb = (long long)sm_count() * red_blocks_per_sm();
+  long long ppb = (P * gy + nb - 1) / nb;
   const long long lo = 4LL * block.y;
   if (ppb < lo) ppb = lo;
   if (ppb > 8192) ppb = 8192;
@@ -37,7 +48,8 @@ static inline int red_ppb(long long P, const dim3& block, int cvecs) {
 }
 
 template <typename T, int NOUT, typename F>
-__device__ __forceinline__ void channel_reduce(long long P, int C, int ppb, double* const* out, F&& f) {
+__device__ __forceinline__ void channel_reduce(long long P, int C, int ppb, double* const* out, int nslot,
+                                               long long slot_stride, F&& f) {
   using V = Vec16<T>;
   constexpr int VN = V::N;
   const int TX = blockDim.x, TY = blockDim.y;
@@ -70,8 +82,12 @@ __device__ __forceinline__ void channel_reduce(long long P, int C, int ppb, doub
       __syncthreads();
     }
     if (threadIdx.y == 0 && active) {
+      // blocks spread their atomics over `nslot` copies of the output (summed by the consumer): with one copy
+      // every channel address received one f64 atomic per block (~1200), serialised in L2 -- 50 us per call on
+      // the mid-size layers, 10x the time of reading the tensor
+      double* dst = out[o] + (long long)(blockIdx.x % nslot) * slot_stride + c0;
 #pragma unroll
-      for (int j = 0; j < VN; ++j) atomicAdd(out[o] + c0 + j, (double)red[threadIdx.x][j]);
+      for (int j = 0; j < VN; ++j) atomicAdd(dst + j, (double)red[threadIdx.x][j]);
     }
   }
 }
@@ -79,16 +95,21 @@ __device__ __forceinline__ void channel_reduce(long long P, int C, int ppb, doub
 // sum and sum of squares (BatchNorm batch statistics)
 template <typename T>
 __global__ void __launch_bounds__(256)
-bn_stats_kernel(const T* __restrict__ z, long long P, int C, int ppb, double* sum, double* sumsq) {
+bn_stats_kernel(const T* __restrict__ z, long long P, int C, int ppb, double* sum, double* sumsq, int nslot,
+                long long slot_stride) {
   using V = Vec16<T>;
   double* const outs[2] = {sum, sumsq};
   // shifted sums: every channel is offset by its own value at pixel 0, so that sum((z-k)^2) - sum(z-k)^2/n does not
   // cancel catastrophically for channels whose spread is tiny compared with their mean (a nearly constant channel
   // otherwise gets a variance -- hence a d(gamma) -- that is pure rounding noise).
-  channel_reduce<T, 2>(P, C, ppb, outs, [&](long long p, int c0, float (&acc)[2][V::N]) {
-    V v, k;
+  V k;                                        // this thread's channels at pixel 0 (loop invariant)
+  {
+    const int c0 = (blockIdx.y * blockDim.x + threadIdx.x) * V::N;
+    if (c0 < C) k.load(z + c0);
+  }
+  channel_reduce<T, 2>(P, C, ppb, outs, nslot, slot_stride, [&](long long p, int c0, float (&acc)[2][V::N]) {
+    V v;
     v.load(z + p * C + c0);
-    k.load(z + c0);
 #pragma unroll
     for (int j = 0; j < V::N; ++j) { const float d = v.v[j] - k.v[j]; acc[0][j] += d; acc[1][j] = fmaf(d, d, acc[1][j]); }
   });
@@ -97,14 +118,17 @@ bn_stats_kernel(const T* __restrict__ z, long long P, int C, int ppb, double* su
 // one thread per channel: mean, biased var -> invstd, fused scale/shift, running-stat update
 // (momentum 0.1, unbiased variance), exactly nn.BatchNorm2d in training mode.
 template <typename T>
-__global__ void bn_finalize_kernel(const T* __restrict__ z0, const double* __restrict__ sum, const double* __restrict__ sumsq, long long n,
+__global__ void bn_finalize_kernel(const T* __restrict__ z0, const double* __restrict__ sum, const double* __restrict__ sumsq,
+                                   int nslot, long long slot_stride, long long n,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, float* running_mean, float* running_var, float* mean_out,
                                    float* invstd_out, float* scale_out, float* shift_out, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double ms = sum[c] / (double)n;                 // mean of (z - k), k = z at pixel 0
-  double var = sumsq[c] / (double)n - ms * ms;
+  double s1 = 0.0, s2 = 0.0;
+  for (int sl = 0; sl < nslot; ++sl) { s1 += sum[sl * slot_stride + c]; s2 += sumsq[sl * slot_stride + c]; }
+  const double ms = s1 / (double)n;                     // mean of (z - k), k = z at pixel 0
+  double var = s2 / (double)n - ms * ms;
   if (var < 0.0) var = 0.0;
   const double m = ms + (double)to_f32<T>(z0[c]);
   const float invstd = (float)(1.0 / sqrt(var + (double)eps));
@@ -163,7 +187,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ z, const float* __restrict__ scale,
                      const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
-                     long long P, int C, int ppb, int act, double* sg, double* sgx) {
+                     long long P, int C, int ppb, int act, double* sg, double* sgx, int nslot, long long slot_stride) {
   using V = Vec16<T>;
   double* const outs[2] = {sg, sgx};
   // per-channel constants live in registers for the whole pixel loop (the channel vector of a thread is fixed)
@@ -177,7 +201,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ z, const fl
       kmu[j] = ok ? __ldg(mean + c0 + j) : 0.f;  kis[j] = ok ? __ldg(invstd + c0 + j) : 0.f;
     }
   }
-  channel_reduce<T, 2>(P, C, ppb, outs, [&](long long p, int c0, float (&acc)[2][V::N]) {
+  channel_reduce<T, 2>(P, C, ppb, outs, nslot, slot_stride, [&](long long p, int c0, float (&acc)[2][V::N]) {
     V d, v;
     d.load(da + p * C + c0);
     v.load(z + p * C + c0);
@@ -246,10 +270,10 @@ act_bwd_kernel(const T* __restrict__ da, const T* __restrict__ a_out, T* __restr
 // per-channel column sum (bias gradients)
 template <typename T>
 __global__ void __launch_bounds__(256)
-colsum_kernel(const T* __restrict__ x, long long P, int C, int ppb, double* out) {
+colsum_kernel(const T* __restrict__ x, long long P, int C, int ppb, double* out, int nslot, long long slot_stride) {
   using V = Vec16<T>;
   double* const outs[1] = {out};
-  channel_reduce<T, 1>(P, C, ppb, outs, [&](long long p, int c0, float (&acc)[1][V::N]) {
+  channel_reduce<T, 1>(P, C, ppb, outs, nslot, slot_stride, [&](long long p, int c0, float (&acc)[1][V::N]) {
     V v;
     v.load(x + p * C + c0);
 #pragma unroll
@@ -257,9 +281,13 @@ colsum_kernel(const T* __restrict__ x, long long P, int C, int ppb, double* out)
   });
 }
 
-__global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, int n, float scale) {
+__global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, int n, int nslot,
+                                  long long slot_stride, float scale) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (float)in[i] * scale;
+  if (i >= n) return;
+  double v = 0.0;
+  for (int sl = 0; sl < nslot; ++sl) v += in[sl * slot_stride + i];
+  out[i] = (float)v * scale;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -490,10 +518,15 @@ smallcin_wgrad_kernel(const TI* __restrict__ x, const T* __restrict__ dz, float*
   const int KK = 9 * Cin;
   const long long P = (long long)B * Ho * Wo;
   const long long p_begin = (long long)blockIdx.x * pix_per_block, p_end = min(p_begin + pix_per_block, P);
-  const int npairs = KK * Cout;
-  float acc[8];                            // up to 8 (k, co) pairs per thread: KK*Cout <= 2048
+  // a thread owns up to 2 items = (k, 4 consecutive output channels): per pixel one broadcast read of the patch
+  // value and one 16-byte read of dz feed 4 FMAs (the scalar-pair version needed 2 shared loads per FMA)
+  const int c4n = Cout >> 2;
+  const int nitems = KK * c4n;               // <= 512
+  float acc[2][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   for (long long pb = p_begin; pb < p_end; pb += PIXB) {
     __syncthreads();
     for (int i = threadIdx.x; i < PIXB * Cout; i += blockDim.x) {
@@ -517,21 +550,29 @@ smallcin_wgrad_kernel(const TI* __restrict__ x, const T* __restrict__ dz, float*
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int pr = threadIdx.x + i * 256;
-      if (pr < npairs) {
-        const int k = pr / Cout, co = pr % Cout;
-        float s = 0.f;
+    for (int i = 0; i < 2; ++i) {
+      const int it = threadIdx.x + i * 256;
+      if (it < nitems) {
+        const int k = it / c4n, c4 = (it - k * c4n) * 4;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll 8
-        for (int q = 0; q < PIXB; ++q) s = fmaf(sx[q * KK + k], sd[q * Cout + co], s);
-        acc[i] += s;
+        for (int q = 0; q < PIXB; ++q) {
+          const float a = sx[q * KK + k];
+          const float4 d = *reinterpret_cast<const float4*>(sd + q * Cout + c4);
+          s0 = fmaf(a, d.x, s0); s1 = fmaf(a, d.y, s1); s2 = fmaf(a, d.z, s2); s3 = fmaf(a, d.w, s3);
+        }
+        acc[i][0] += s0; acc[i][1] += s1; acc[i][2] += s2; acc[i][3] += s3;
       }
     }
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int pr = threadIdx.x + i * 256;
-    if (pr < npairs) atomicAdd(dw + pr, acc[i]);     // layout [tap][c][co] == pr
+  for (int i = 0; i < 2; ++i) {
+    const int it = threadIdx.x + i * 256;
+    if (it < nitems) {
+      const int k = it / c4n, c4 = (it - k * c4n) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(dw + k * Cout + c4 + j, acc[i][j]);     // layout [tap][c][co]
+    }
   }
 }
 
@@ -717,25 +758,28 @@ typedef __nv_bfloat16 bf16;
 
 extern "C" {
 
-int b200seg_bn_stats(const void* z, int dtype, long long P, int C, double* sum, double* sumsq, b200seg_stream_t s) {
+int b200seg_bn_stats(const void* z, int dtype, long long P, int C, double* sum, double* sumsq, int nslot,
+                     long long slot_stride, b200seg_stream_t s) {
   const int vn = dtype == B200SEG_BF16 ? 8 : 4;
   B200_REQUIRE(P > 0 && C > 0 && C % vn == 0, "bn_stats: P=%lld C=%d (C must be a multiple of %d)", P, C, vn);
+  B200_REQUIRE(nslot >= 1 && (nslot == 1 || slot_stride >= C), "bn_stats: nslot=%d slot_stride=%lld", nslot, slot_stride);
   const dim3 block = red_block(C / vn);
   const int ppb = red_ppb(P, block, C / vn);
   dim3 grid(cdiv(P, ppb), cdiv(C / vn, block.x));
   cudaStream_t st = (cudaStream_t)s;
-  DISPATCH_T(dtype, (bn_stats_kernel<float><<<grid, block, 0, st>>>((const float*)z, P, C, ppb, sum, sumsq)),
-             (bn_stats_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)z, P, C, ppb, sum, sumsq)), "bn_stats")
+  DISPATCH_T(dtype, (bn_stats_kernel<float><<<grid, block, 0, st>>>((const float*)z, P, C, ppb, sum, sumsq, nslot, slot_stride)),
+             (bn_stats_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)z, P, C, ppb, sum, sumsq, nslot, slot_stride)), "bn_stats")
   return check_launch("bn_stats");
 }
 
-int b200seg_bn_finalize(const void* z, int dtype, const double* sum, const double* sumsq, long long n, const float* gamma,
+int b200seg_bn_finalize(const void* z, int dtype, const double* sum, const double* sumsq, int nslot,
+                        long long slot_stride, long long n, const float* gamma,
                         const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                         float* mean, float* invstd, float* scale, float* shift, int C, b200seg_stream_t s) {
-  B200_REQUIRE(C > 0 && n > 0 && z, "bn_finalize: C=%d n=%lld", C, n);
+  B200_REQUIRE(C > 0 && n > 0 && z && nslot >= 1, "bn_finalize: C=%d n=%lld nslot=%d", C, n, nslot);
   cudaStream_t st = (cudaStream_t)s;
-  DISPATCH_T(dtype, (bn_finalize_kernel<float><<<cdiv(C, 128), 128, 0, st>>>((const float*)z, sum, sumsq, n, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, scale, shift, C)),
-             (bn_finalize_kernel<bf16><<<cdiv(C, 128), 128, 0, st>>>((const bf16*)z, sum, sumsq, n, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, scale, shift, C)), "bn_finalize")
+  DISPATCH_T(dtype, (bn_finalize_kernel<float><<<cdiv(C, 128), 128, 0, st>>>((const float*)z, sum, sumsq, nslot, slot_stride, n, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, scale, shift, C)),
+             (bn_finalize_kernel<bf16><<<cdiv(C, 128), 128, 0, st>>>((const bf16*)z, sum, sumsq, nslot, slot_stride, n, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, scale, shift, C)), "bn_finalize")
   return check_launch("bn_finalize");
 }
 
@@ -757,15 +801,16 @@ int b200seg_bn_apply(const void* z, const float* scale, const float* shift, cons
 
 int b200seg_bn_bwd_reduce(const void* da, const void* z, const float* scale, const float* shift, const float* mean,
                           const float* invstd, int dtype, long long P, int C, int act, double* sg, double* sgx,
-                          b200seg_stream_t s) {
+                          int nslot, long long slot_stride, b200seg_stream_t s) {
   const int vn = dtype == B200SEG_BF16 ? 8 : 4;
   B200_REQUIRE(P > 0 && C > 0 && C % vn == 0, "bn_bwd_reduce: P=%lld C=%d", P, C);
+  B200_REQUIRE(nslot >= 1 && (nslot == 1 || slot_stride >= C), "bn_bwd_reduce: nslot=%d slot_stride=%lld", nslot, slot_stride);
   const dim3 block = red_block(C / vn);
   const int ppb = red_ppb(P, block, C / vn);
   dim3 grid(cdiv(P, ppb), cdiv(C / vn, block.x));
   cudaStream_t st = (cudaStream_t)s;
-  DISPATCH_T(dtype, (bn_bwd_reduce_kernel<float><<<grid, block, 0, st>>>((const float*)da, (const float*)z, scale, shift, mean, invstd, P, C, ppb, act, sg, sgx)),
-             (bn_bwd_reduce_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)da, (const bf16*)z, scale, shift, mean, invstd, P, C, ppb, act, sg, sgx)), "bn_bwd_reduce")
+  DISPATCH_T(dtype, (bn_bwd_reduce_kernel<float><<<grid, block, 0, st>>>((const float*)da, (const float*)z, scale, shift, mean, invstd, P, C, ppb, act, sg, sgx, nslot, slot_stride)),
+             (bn_bwd_reduce_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)da, (const bf16*)z, scale, shift, mean, invstd, P, C, ppb, act, sg, sgx, nslot, slot_stride)), "bn_bwd_reduce")
   return check_launch("bn_bwd_reduce");
 }
 
@@ -794,21 +839,24 @@ int b200seg_act_bwd(const void* da, const void* a_out, void* dz, int dtype, long
   return check_launch("act_bwd");
 }
 
-int b200seg_colsum(const void* x, int dtype, long long P, int C, double* out, b200seg_stream_t s) {
+int b200seg_colsum(const void* x, int dtype, long long P, int C, double* out, int nslot, long long slot_stride,
+                   b200seg_stream_t s) {
   const int vn = dtype == B200SEG_BF16 ? 8 : 4;
   B200_REQUIRE(P > 0 && C > 0 && C % vn == 0, "colsum: P=%lld C=%d", P, C);
+  B200_REQUIRE(nslot >= 1 && (nslot == 1 || slot_stride >= C), "colsum: nslot=%d slot_stride=%lld", nslot, slot_stride);
   const dim3 block = red_block(C / vn);
   const int ppb = red_ppb(P, block, C / vn);
   dim3 grid(cdiv(P, ppb), cdiv(C / vn, block.x));
   cudaStream_t st = (cudaStream_t)s;
-  DISPATCH_T(dtype, (colsum_kernel<float><<<grid, block, 0, st>>>((const float*)x, P, C, ppb, out)),
-             (colsum_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)x, P, C, ppb, out)), "colsum")
+  DISPATCH_T(dtype, (colsum_kernel<float><<<grid, block, 0, st>>>((const float*)x, P, C, ppb, out, nslot, slot_stride)),
+             (colsum_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)x, P, C, ppb, out, nslot, slot_stride)), "colsum")
   return check_launch("colsum");
 }
 
-int b200seg_f64_to_f32(const double* in, float* out, int n, float scale, b200seg_stream_t s) {
-  B200_REQUIRE(n > 0, "f64_to_f32: n=%d", n);
-  f64_to_f32_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)s>>>(in, out, n, scale);
+int b200seg_f64_to_f32(const double* in, float* out, int n, int nslot, long long slot_stride, float scale,
+                       b200seg_stream_t s) {
+  B200_REQUIRE(n > 0 && nslot >= 1 && (nslot == 1 || slot_stride >= n), "f64_to_f32: n=%d nslot=%d", n, nslot);
+  f64_to_f32_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)s>>>(in, out, n, nslot, slot_stride, scale);
   return check_launch("f64_to_f32");
 }
 
@@ -869,7 +917,7 @@ int b200seg_dw_wgrad(const void* x, const void* dz, double* dw, int dtype, int B
 
 int b200seg_smallcin_wgrad(const void* x, int x_dtype, const void* dz, int dtype, float* dw, int B, int Cin, int H,
                            int W, int Cout, int stride, b200seg_stream_t s) {
-  B200_REQUIRE(Cin >= 1 && Cin <= 4 && Cout > 0 && 9 * Cin * Cout <= 2048, "smallcin_wgrad: Cin=%d Cout=%d", Cin, Cout);
+  B200_REQUIRE(Cin >= 1 && Cin <= 4 && Cout > 0 && Cout % 4 == 0 && 9 * Cin * Cout <= 2048, "smallcin_wgrad: Cin=%d Cout=%d (Cout % 4 == 0, 9*Cin*Cout <= 2048)", Cin, Cout);
   B200_REQUIRE(stride == 1 || stride == 2, "smallcin_wgrad: stride=%d", stride);
   B200_REQUIRE(B > 0 && H > 0 && W > 0, "smallcin_wgrad: empty tensor");
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;

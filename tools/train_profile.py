@@ -25,3 +25,8 @@ tot = sum(r[2] for r in rows)
 print(f"total device time {tot/1e3:.2f} ms over {sum(r[1] for r in rows)} launches")
 for k, n, t in rows[:40]:
     print(f"{t/1e3:9.3f} ms {t/tot:6.1%} x{n:4d}  {k[:100]}")
+# per-launch durations of the reduction kernels (which layers are far from the roofline)
+if os.environ.get("TP_DETAIL"):
+    evs = [e for e in prof.events() if e.device_time_total > 0 and any(k in e.name for k in os.environ["TP_DETAIL"].split(","))]
+    for e in evs:
+        print(f"  {e.device_time_total:8.1f} us  {e.name[:60]}")
