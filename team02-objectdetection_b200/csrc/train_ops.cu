@@ -22,6 +22,14 @@ static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b
 //   f32 over RED_PIX/TY pixels, tree over y in shared memory, one f64 atomic per channel per block.
 // ---------------------------------------------------------------------------------------------
 static inline dim3 red_block(int cvecs) {
+  // x = exactly the channel vectors of one pixel (any count up to 256, not rounded to a power of two: MobileNetV2's
+  // widths 24, 96, 144, 160, 192, 320, 576 left 25-45 % of the lanes idle), y = as many pixels as fit in 256 threads.
+  // Consecutive threads read consecutive 16-byte vectors whatever the warp/pixel alignment.
+  const int tx = cvecs < 256 ? cvecs : 256;
+  return dim3(tx, 256 / tx);
+}
+// the depthwise backward kernels stage their taps for at most 32 channel vectors and assume 256 threads
+static inline dim3 red_block_pow2(int cvecs) {
   int tx = 1;
   while (tx < cvecs && tx < 32) tx <<= 1;
   return dim3(tx, 256 / tx);
@@ -74,8 +82,10 @@ __device__ __forceinline__ void channel_reduce(long long P, int C, int ppb, doub
 #pragma unroll
     for (int j = 0; j < VN; ++j) red[tid][j] = acc[o][j];
     __syncthreads();
-    for (int stride = TY >> 1; stride >= 1; stride >>= 1) {      // tree over the pixel lanes
-      if (threadIdx.y < stride) {
+    int top = 1;
+    while (top < TY) top <<= 1;
+    for (int stride = top >> 1; stride >= 1; stride >>= 1) {     // tree over the pixel lanes (TY need not be 2^k)
+      if (threadIdx.y < stride && threadIdx.y + stride < TY) {
 #pragma unroll
         for (int j = 0; j < VN; ++j) red[tid][j] += red[tid + stride * TX][j];
       }
@@ -890,7 +900,7 @@ int b200seg_dw_dgrad(const void* dz, const float* w, const void* acc_in, void* d
   B200_REQUIRE(B > 0 && H > 0 && W > 0, "dw_dgrad: empty tensor");
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   const long long P = (long long)B * H * W;
-  const dim3 block = red_block(C / vn);
+  const dim3 block = red_block_pow2(C / vn);
   const int ppb = 8 * (int)block.y;
   dim3 grid(cdiv(P, ppb), cdiv(C / vn, block.x));
   cudaStream_t st = (cudaStream_t)s;
@@ -906,7 +916,7 @@ int b200seg_dw_wgrad(const void* x, const void* dz, double* dw, int dtype, int B
   B200_REQUIRE(B > 0 && H > 0 && W > 0, "dw_wgrad: empty tensor");
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   const long long P = (long long)B * Ho * Wo;
-  const dim3 block = red_block(C / vn);
+  const dim3 block = red_block_pow2(C / vn);
   const int ppb = red_ppb(P, block, C / vn);
   dim3 grid(cdiv(P, ppb), cdiv(C / vn, block.x));
   cudaStream_t st = (cudaStream_t)s;
