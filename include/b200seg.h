@@ -173,8 +173,8 @@ int b200seg_conv_wgrad_tc(const void* x, const void* dz, float* dw, int B, int H
 /* depthwise backward: dx (+= acc_in) from dz with taps w f32 [9][C]; dw f64 [9][C] += ... (caller zeroes) */
 int b200seg_dw_dgrad(const void* dz, const float* w, const void* acc_in, void* dx, int dtype, int B, int H, int W,
                      int C, int stride, b200seg_stream_t s);
-int b200seg_dw_wgrad(const void* x, const void* dz, double* dw, int dtype, int B, int H, int W, int C, int stride,
-                     b200seg_stream_t s);
+int b200seg_dw_wgrad(const void* x, const void* dz, double* dw, int nslot, int dtype, int B, int H, int W, int C,
+                     int stride, b200seg_stream_t s);   /* dw: nslot copies of [9][C], summed by f64_to_f32 */
 /* stem / first-conv weight gradient: x NCHW, dz NHWC, dw f32 [3][3][Cin][Cout] += ... (caller zeroes) */
 int b200seg_smallcin_wgrad(const void* x, int x_dtype, const void* dz, int dtype, float* dw, int B, int Cin, int H,
                            int W, int Cout, int stride, b200seg_stream_t s);

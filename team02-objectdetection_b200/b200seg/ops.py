@@ -378,10 +378,10 @@ def dw_wgrad(x, dz, stride: int):
     """f32 [9, C]."""
     _cuda(x, dz)
     B, H, W, Cc = x.shape
-    acc = zero_pool.take((9, Cc), x.device)
-    check(lib.b200seg_dw_wgrad(ptr(x), ptr(dz), ptr(acc), _dt(x), B, H, W, Cc, stride, _stream()), "dw_wgrad")
+    acc = zero_pool.take((NSLOT, 9, Cc), x.device)
+    check(lib.b200seg_dw_wgrad(ptr(x), ptr(dz), ptr(acc), NSLOT, _dt(x), B, H, W, Cc, stride, _stream()), "dw_wgrad")
     out = torch.empty(9, Cc, device=x.device, dtype=torch.float32)
-    check(lib.b200seg_f64_to_f32(ptr(acc), ptr(out), 9 * Cc, 1, 9 * Cc, 1.0, _stream()), "f64_to_f32")
+    check(lib.b200seg_f64_to_f32(ptr(acc), ptr(out), 9 * Cc, NSLOT, 9 * Cc, 1.0, _stream()), "f64_to_f32")
     return out
 
 

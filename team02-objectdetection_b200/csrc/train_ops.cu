@@ -450,7 +450,7 @@ dw_dgrad_kernel(const T* __restrict__ dz, const float* __restrict__ w, const T* 
 template <typename T>
 __global__ void __launch_bounds__(256)
 dw_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dz, int B, int H, int W, int C, int Ho, int Wo, int S,
-                int ppb, double* dw /* [9][C] */) {
+                int ppb, double* dw /* [nslot][9][C] */, int nslot) {
   using V = Vec16<T>;
   constexpr int VN = V::N;
   const int TX = blockDim.x, TY = blockDim.y;
@@ -502,16 +502,19 @@ dw_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dz, int B, int H,
 #pragma unroll
     for (int j = 0; j < VN; ++j) red[tid][j] = acc[o][j];
     __syncthreads();
-    for (int stride = TY >> 1; stride >= 1; stride >>= 1) {
-      if (threadIdx.y < stride) {
+    int top = 1;
+    while (top < TY) top <<= 1;
+    for (int stride = top >> 1; stride >= 1; stride >>= 1) {
+      if (threadIdx.y < stride && threadIdx.y + stride < TY) {
 #pragma unroll
         for (int j = 0; j < VN; ++j) red[tid][j] += red[tid + stride * TX][j];
       }
       __syncthreads();
     }
     if (threadIdx.y == 0 && active) {
+      double* dst = dw + ((long long)(blockIdx.x % nslot) * 9 + o) * C + c0;      // one of nslot copies (see channel_reduce)
 #pragma unroll
-      for (int j = 0; j < VN; ++j) atomicAdd(dw + (long long)o * C + c0 + j, (double)red[threadIdx.x][j]);
+      for (int j = 0; j < VN; ++j) atomicAdd(dst + j, (double)red[threadIdx.x][j]);
     }
   }
 }
@@ -909,19 +912,20 @@ int b200seg_dw_dgrad(const void* dz, const float* w, const void* acc_in, void* d
   return check_launch("dw_dgrad");
 }
 
-int b200seg_dw_wgrad(const void* x, const void* dz, double* dw, int dtype, int B, int H, int W, int C, int stride,
-                     b200seg_stream_t s) {
+int b200seg_dw_wgrad(const void* x, const void* dz, double* dw, int nslot, int dtype, int B, int H, int W, int C,
+                     int stride, b200seg_stream_t s) {
+  B200_REQUIRE(nslot >= 1, "dw_wgrad: nslot=%d", nslot);
   const int vn = dtype == B200SEG_BF16 ? 8 : 4;
   B200_REQUIRE(C > 0 && C % vn == 0 && (stride == 1 || stride == 2), "dw_wgrad: C=%d stride=%d", C, stride);
   B200_REQUIRE(B > 0 && H > 0 && W > 0, "dw_wgrad: empty tensor");
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   const long long P = (long long)B * Ho * Wo;
-  const dim3 block = red_block_pow2(C / vn);
+  const dim3 block = red_block(C / vn);
   const int ppb = red_ppb(P, block, C / vn);
   dim3 grid(cdiv(P, ppb), cdiv(C / vn, block.x));
   cudaStream_t st = (cudaStream_t)s;
-  DISPATCH_T(dtype, (dw_wgrad_kernel<float><<<grid, block, 0, st>>>((const float*)x, (const float*)dz, B, H, W, C, Ho, Wo, stride, ppb, dw)),
-             (dw_wgrad_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)x, (const bf16*)dz, B, H, W, C, Ho, Wo, stride, ppb, dw)), "dw_wgrad")
+  DISPATCH_T(dtype, (dw_wgrad_kernel<float><<<grid, block, 0, st>>>((const float*)x, (const float*)dz, B, H, W, C, Ho, Wo, stride, ppb, dw, nslot)),
+             (dw_wgrad_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)x, (const bf16*)dz, B, H, W, C, Ho, Wo, stride, ppb, dw, nslot)), "dw_wgrad")
   return check_launch("dw_wgrad");
 }
 
