@@ -307,7 +307,10 @@ def main():
     except (OSError, ValueError):
         pass
     tot_bytes = sum(r["bytes"] for r in rows)
+    survey_bytes = 115.7e6 * B if args.workload == "infer" else None      # SURVEY 8d per-image figure of the UNFUSED op list
     step_roofline = {"bound": "hbm", "algorithmic_bytes_per_step": tot_bytes,
+                     "note": "bytes of the schedule actually run (fused inverted-residual blocks count input+output only)",
+                     "frac_vs_survey_unfused_bytes": (survey_bytes / (ms / args.steps * 1e-3) / 1e9 / pk["hbm"]) if survey_bytes else None,
                      "achieved": tot_bytes / (ms / args.steps * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                      "frac": tot_bytes / (ms / args.steps * 1e-3) / 1e9 / pk["hbm"]}
 
