@@ -13,6 +13,7 @@
 // red.global.add.v4.f32 (the pixel axis is split over CTAs to fill the GPU).
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace b200 {
@@ -25,12 +26,15 @@ struct WgradArgs {
   int n_boxes;             // 64-channel cin boxes per N tile (N = 64 * n_boxes <= 256)
   int n_tiles, m_tiles;
   int stages;
+  int rowmode;             // 3x3 on rows >= 128 px: one CTA owns a tap ROW (dh) -- the dz tile and one 130-pixel x tile
+                           // feed the three horizontal taps (B descriptor start advanced by one 128-byte pixel row)
   long long pix_tiles, tiles_per_split;
   int tmem_cols;
 };
 
 constexpr int WG_THREADS = 192;
 constexpr int WG_BOX = 128 * 128;     // one 128-pixel x 64-channel box
+constexpr int WG_XBOX = 17 * 1024;    // row mode: one 130-pixel x 64-channel box (16640 B), padded to the swizzle atom
 
 // MN-major operand, 128-byte swizzle: 64 channels (128 B) contiguous, next 64-channel group LBO bytes away,
 // 8 pixel rows per swizzle atom, next atom SBO = 1024 bytes away (cute::UMMA::make_umma_desc<Major::MN>).
@@ -50,7 +54,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int stage_bytes = (2 + a.n_boxes) * WG_BOX;
+  const int xbox = a.rowmode ? WG_XBOX : WG_BOX;
+  const int stage_bytes = 2 * WG_BOX + a.n_boxes * xbox;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + a.stages * stage_bytes);
   uint64_t* empty = full + 8;
   uint64_t* acc_full = empty + 8;
@@ -60,8 +65,9 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_const
   int bid = blockIdx.x;
   const int m_tile = bid % a.m_tiles; bid /= a.m_tiles;
   const int n_tile = bid % a.n_tiles; bid /= a.n_tiles;
-  const int tap = bid % a.taps;
-  const int split = bid / a.taps;
+  const int tap_items = a.rowmode ? 3 : a.taps;
+  const int tap = bid % tap_items;           // row mode: tap = dh + 1
+  const int split = bid / tap_items;
   const long long t_begin = (long long)split * a.tiles_per_split;
   const long long t_end = min(t_begin + a.tiles_per_split, a.pix_tiles);
   const int co0 = m_tile * 128, ci0 = n_tile * a.n_boxes * 64;
@@ -70,7 +76,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_const
   const int a_boxes = (co0 + 64 < a.Cout) ? 2 : 1;
   const int umma_n = boxes * 64;
   int dh = 0, dwv = 0;
-  if (a.taps == 9) { dh = tap / 3 - 1; dwv = tap % 3 - 1; }
+  if (a.rowmode) { dh = tap - 1; dwv = -1; }
+  else if (a.taps == 9) { dh = tap / 3 - 1; dwv = tap % 3 - 1; }
   const int rows = a.BW * a.BH;
 
   // pixel rows >= BW*BH of every stage are never written by TMA but ARE read by the MMA (the pixel axis is the
@@ -99,7 +106,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_const
     // ================= TMA producer =================
     int s = 0;
     uint32_t ph = 0;
-    const uint32_t tx = (uint32_t)((a_boxes + boxes) * rows * 128);
+    const uint32_t tx = (uint32_t)(a_boxes * rows * 128 + boxes * (a.rowmode ? 130 : rows) * 128);
     for (long long t = t_begin; t < t_end; ++t) {
       long long mt = t;
       const int tw = (int)(mt % a.tiles_w); mt /= a.tiles_w;
@@ -112,7 +119,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_const
         mbar_arrive_expect_tx(&full[s], tx);
         for (int j = 0; j < a_boxes; ++j) tma_load_4d(st + j * WG_BOX, &tmD, &full[s], co0 + j * 64, w0, h0, bb);
         for (int j = 0; j < boxes; ++j)
-          tma_load_4d(st + (2 + j) * WG_BOX, &tmX, &full[s], ci0 + j * 64, w0 + dwv, h0 + dh, bb);
+          tma_load_4d(st + 2 * WG_BOX + j * xbox, &tmX, &full[s], ci0 + j * 64, w0 + dwv, h0 + dh, bb);
       }
       __syncwarp();
       if (++s == a.stages) { s = 0; ph ^= 1u; }
@@ -123,6 +130,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_const
     const uint32_t idesc = umma_idesc_bf16(128, umma_n) | (1u << 15) | (1u << 16);
     const uint32_t desc_hi = (uint32_t)(umma_desc_mn128(0, WG_BOX) >> 32);
     const uint32_t lbo_bits = (uint32_t)((WG_BOX >> 4) & 0x3FFF) << 16;
+    const uint32_t lbo_bits_x = (uint32_t)((xbox >> 4) & 0x3FFF) << 16;
+    const int n_acc = a.rowmode ? 3 : 1;
     int s = 0;
     uint32_t ph = 0;
     uint32_t first = 0;
@@ -131,12 +140,14 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_const
       tc_fence_after();
       if (elect_one()) {
         const uint32_t a_lo = ((smem_u32(smem + s * stage_bytes) & 0x3FFFF) >> 4) | lbo_bits;
-        const uint32_t b_lo = ((smem_u32(smem + s * stage_bytes + 2 * WG_BOX) & 0x3FFFF) >> 4) | lbo_bits;
+        const uint32_t b_lo = ((smem_u32(smem + s * stage_bytes + 2 * WG_BOX) & 0x3FFFF) >> 4) | lbo_bits_x;
+        for (int j = 0; j < n_acc; ++j) {      // row mode: tap dw = j - 1 reads the x tile one pixel row (128 B) further
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {          // 16 pixel rows = 2048 bytes per MMA
-          umma_bf16_lohi(tmem_base, a_lo + 128u * k, b_lo + 128u * k, desc_hi, idesc, first);
-          first = 1u;
+          for (int k = 0; k < 8; ++k)          // 16 pixel rows = 2048 bytes per MMA
+            umma_bf16_lohi(tmem_base + (uint32_t)(j * umma_n), a_lo + 128u * k, b_lo + 8u * j + 128u * k, desc_hi, idesc,
+                           (first | (uint32_t)(k > 0)));
         }
+        first = 1u;
         umma_commit(&empty[s]);
         if (t == t_end - 1) umma_commit(acc_full);
       }
@@ -149,8 +160,10 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_const
     const int co = co0 + q * 32 + lane;
     mbar_wait(acc_full, 0, 13);
     tc_fence_after();
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    float* drow = a.dw + ((long long)co * a.taps + tap) * a.Cin + ci0;
+    const int n_acc = a.rowmode ? 3 : 1;
+    for (int j = 0; j < n_acc; ++j) {
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * umma_n);
+    float* drow = a.dw + ((long long)co * a.taps + (a.rowmode ? tap * 3 + j : tap)) * a.Cin + ci0;
     for (int c0 = 0; c0 < umma_n; c0 += 16) {
       uint32_t v[16];
       tmem_ld16(trow + (uint32_t)c0, v);
@@ -165,6 +178,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_const
           }
         }
       }
+    }
     }
     tc_fence_before();
   }
@@ -209,22 +223,29 @@ extern "C" int b200seg_conv_wgrad_tc(const void* x, const void* dz, float* dw, i
     }
     a.BW = bwb; a.BH = bhb;
   }
+  {
+    static int row_ok = -1;
+    if (row_ok < 0) { const char* e = getenv("B200SEG_WGRAD_ROW"); row_ok = (e && e[0] == '0') ? 0 : 1; }
+    a.rowmode = (taps == 9 && W >= 128 && row_ok) ? 1 : 0;
+  }
+  if (a.rowmode) { a.BW = 128; a.BH = 1; }
   a.tiles_w = (a.W + a.BW - 1) / a.BW;
   a.tiles_h = (a.H + a.BH - 1) / a.BH;
   a.pix_tiles = (long long)a.tiles_w * a.tiles_h * a.B;
   const int cin_boxes = (Cin + 63) / 64;
-  a.n_boxes = cin_boxes < 4 ? cin_boxes : 4;
+  const int max_boxes = a.rowmode ? 2 : 4;           // row mode keeps three accumulators: 3 * N <= 512 TMEM columns
+  a.n_boxes = cin_boxes < max_boxes ? cin_boxes : max_boxes;
   a.n_tiles = (cin_boxes + a.n_boxes - 1) / a.n_boxes;
   a.m_tiles = (Cout + 127) / 128;
   a.tmem_cols = 32;
-  while (a.tmem_cols < a.n_boxes * 64) a.tmem_cols <<= 1;
-  const int stage_bytes = (2 + a.n_boxes) * WG_BOX;
+  while (a.tmem_cols < (a.rowmode ? 3 : 1) * a.n_boxes * 64) a.tmem_cols <<= 1;
+  const int stage_bytes = 2 * WG_BOX + a.n_boxes * (a.rowmode ? WG_XBOX : WG_BOX);
   int stages = (227 * 1024 - 2048) / stage_bytes;
   if (stages > 4) stages = 4;
   B200_REQUIRE(stages >= 1, "conv_wgrad_tc: stage does not fit");
   a.stages = stages;
   const int smem = stages * stage_bytes + 1024 + 256;
-  const long long mn = (long long)a.m_tiles * a.n_tiles * taps;
+  const long long mn = (long long)a.m_tiles * a.n_tiles * (a.rowmode ? 3 : taps);
   long long splits = ((long long)sm_count() * 2 + mn - 1) / mn;
   if (splits > a.pix_tiles) splits = a.pix_tiles;
   if (splits < 1) splits = 1;
@@ -244,7 +265,7 @@ extern "C" int b200seg_conv_wgrad_tc(const void* x, const void* dz, float* dw, i
   {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
     uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)Cin * 2 * a.W, (uint64_t)Cin * 2 * a.W * a.H};
-    uint32_t box[4] = {64, (uint32_t)a.BW, (uint32_t)a.BH, 1};
+    uint32_t box[4] = {64, (uint32_t)(a.rowmode ? 130 : a.BW), (uint32_t)a.BH, 1};
     int rc = make_tmap_bf16(&tmX, x, 4, dims, str, box, 1, nullptr);
     if (rc) return rc;
   }

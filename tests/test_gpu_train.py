@@ -99,7 +99,9 @@ def test_conv_wgrad_and_dgrad(dt, B, H, W, Cin, Cout, taps):
 @pytest.mark.parametrize("B,H,W,Cin,Cout,taps", [
     (2, 16, 32, 64, 64, 1), (2, 16, 32, 64, 128, 1), (4, 32, 64, 16, 96, 1), (2, 16, 16, 144, 24, 1), (2, 8, 16, 320, 1280, 1),
     (1, 7, 9, 40, 72, 1), (2, 16, 32, 64, 64, 9), (2, 16, 32, 1344, 256, 9), (1, 32, 64, 288, 128, 9), (2, 64, 128, 80, 32, 9),
-    (1, 23, 40, 64, 64, 9), (2, 5, 7, 24, 40, 9), (4, 128, 256, 32, 16, 1)])
+    (1, 23, 40, 64, 64, 9), (2, 5, 7, 24, 40, 9), (4, 128, 256, 32, 16, 1),
+    # rows >= 128 px: tap-row mode (one CTA per dh, three accumulators, x tile with a 1-pixel halo)
+    (1, 32, 256, 32, 32, 9), (1, 20, 200, 48, 40, 9), (1, 16, 160, 200, 64, 9), (1, 9, 130, 16, 136, 9)])
 def test_conv_wgrad_tensor_core(B, H, W, Cin, Cout, taps):
     """tcgen05 weight gradient (MN-major operands, pixels as the reduction axis) vs float64 autograd."""
     k = 3 if taps == 9 else 1
