@@ -55,7 +55,7 @@ static inline int red_ppb(long long P, const dim3& block, int cvecs) {
   return (int)ppb;
 }
 
-template <typename T, int NOUT, typename F>
+template <typename T, int NOUT, int UNROLL = 4, typename F>
 __device__ __forceinline__ void channel_reduce(long long P, int C, int ppb, double* const* out, int nslot,
                                                long long slot_stride, F&& f) {
   using V = Vec16<T>;
@@ -71,7 +71,7 @@ __device__ __forceinline__ void channel_reduce(long long P, int C, int ppb, doub
     for (int j = 0; j < VN; ++j) acc[o][j] = 0.f;
   if (active) {
     const long long p0 = (long long)blockIdx.x * ppb, p1 = min(p0 + ppb, P);
-#pragma unroll 4
+#pragma unroll UNROLL
     for (long long p = p0 + threadIdx.y; p < p1; p += TY) f(p, c0, acc);
   }
   __shared__ float red[256][VN + 1];
@@ -227,7 +227,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ z, const fl
 
 // dz = scale * (g - mean(g) - xhat * mean(g*xhat))        (scale = gamma * invstd; sums passed as f32, mean = sum * inv_n)
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_apply_kernel(const T* __restrict__ da, const T* __restrict__ z, const float* __restrict__ scale,
                     const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
                     const float* __restrict__ sg, const float* __restrict__ sgx, float inv_n, T* __restrict__ dz,
@@ -245,7 +245,7 @@ bn_bwd_apply_kernel(const T* __restrict__ da, const T* __restrict__ z, const flo
     kmg[j] = __ldg(sg + c0 + j) * inv_n; kmx[j] = __ldg(sgx + c0 + j) * inv_n;
   }
   const long long p0 = (long long)blockIdx.x * ppb, p1 = min(p0 + ppb, P);
-#pragma unroll 4
+#pragma unroll 2
   for (long long p = p0 + threadIdx.y; p < p1; p += TY) {
     const long long off = p * C + c0;
     V d, v, o;

@@ -3,7 +3,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "team02-objectdetection_b200"))
 import torch
 from b200seg import ops
-DEV = "cuda"; B = 16
+DEV = "cuda"; B = 32
 def rnd(*s, dt=torch.bfloat16): return torch.randn(*s, device=DEV).to(dt)
 x = rnd(B, 64, 128, 144); dz = rnd(B, 64, 128, 144); w9 = rnd(9, 144, dt=torch.float32)
 for _ in range(2):
