@@ -32,7 +32,9 @@ def run_train(args, dev, dist, world, rank, pk, ClockSampler, emit):
         dp.broadcast_model(model)
         dp.attach(model)
     criterion = b200seg.CrossEntropyLoss()
-    optimizer = torch.optim.Adam(model.parameters(), lr=1.5e-4)       # main.py:100
+    fused_adam = os.environ.get("B200SEG_BENCH_ADAM", "fused") == "fused"
+    # main.py:100 -- same constructor call; b200seg.Adam is the one-launch multi-tensor drop-in for optim.Adam
+    optimizer = (b200seg.Adam if fused_adam else torch.optim.Adam)(model.parameters(), lr=1.5e-4)
     model.train()
     g = torch.Generator(device="cpu").manual_seed(rank)
     nrot = 2
@@ -125,7 +127,7 @@ def run_train(args, dev, dist, world, rank, pk, ClockSampler, emit):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": f"{'UNet' if unet else 'MobileNetV2UNet'} training step (fwd + pixel CE + bwd + Adam), batch {B}/GPU, 3x{H}x{W}, {NCLS} classes "
-                                   f"(BASELINE config[{3 if unet else 2}]); activations {precision}, fp32 master weights, torch.optim.Adam(lr=1.5e-4); "
+                                   f"(BASELINE config[{3 if unet else 2}]); activations {precision}, fp32 master weights, {'b200seg.Adam (fused multi-tensor)' if fused_adam else 'torch.optim.Adam'}(lr=1.5e-4); "
                                    f"data parallel, per-replica BatchNorm, bucketed all-reduce overlapped with backward",
                        "global_batch": B * world, "l2": "~20 GB of activations per step >> 126 MB L2", "last_loss": last_loss,
                        "host_issue_ms_per_step": host_issue_ms},

@@ -189,6 +189,17 @@ int b200seg_nchw_to_nhwc_pad(const float* x, void* y, int dtype, int B, int C, i
 int b200seg_maxpool_bwd(const void* x, const void* dy, const void* acc_in, void* dx, int dtype, int B, int H, int W,
                         int C, b200seg_stream_t s);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused multi-tensor Adam: torch.optim.Adam(params, lr) of main.py:100 / train.py:39 for all tensors
+ * in one launch.  table: device array of {float* p; const float* g; float* m; float* v; long long n;} (40 bytes
+ * each); block b updates elements [chunk_index[b]*CHUNK, +CHUNK) of tensor chunk_tensor[b], CHUNK =
+ * b200seg_adam_chunk().  bias_corr1/2 = 1 - beta^t for the step count t >= 1 (host side, as torch computes them).
+ * --------------------------------------------------------------------------------------------- */
+int b200seg_adam_multi(const void* table, const int* chunk_tensor, const int* chunk_index, int n_chunks, float lr,
+                       double one_minus_beta1, float beta2, double one_minus_beta2, float eps, float weight_decay,
+                       double bias_corr1, double bias_corr2, b200seg_stream_t s);
+int b200seg_adam_chunk(void);
+
 #ifdef __cplusplus
 }
 #endif

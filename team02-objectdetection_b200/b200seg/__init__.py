@@ -8,6 +8,7 @@ It raises ImportError if the library has not been built -- there is no eager / C
 from . import _cabi  # noqa: F401  (fail loudly if the CUDA library is missing)
 from .unet import LightUNet, MobileNetV2UNet, UNet  # noqa: F401
 from .loss import CrossEntropyLoss  # noqa: F401
+from .optim import Adam  # noqa: F401
 
-__all__ = ["MobileNetV2UNet", "UNet", "LightUNet", "CrossEntropyLoss"]
+__all__ = ["MobileNetV2UNet", "UNet", "LightUNet", "CrossEntropyLoss", "Adam"]
 __version__ = "0.1.0"

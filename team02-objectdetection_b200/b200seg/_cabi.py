@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libb200seg.so")
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
 
-_vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+_vp, _i, _f, _ll, _d = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_double
 
 # name -> argtypes (restype is always int unless noted)
 _PROTOS = {
@@ -52,6 +52,8 @@ _PROTOS = {
     "b200seg_upcat_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "b200seg_final_bwd": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "b200seg_nchw_to_nhwc_pad": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "b200seg_adam_multi": [_vp, _vp, _vp, _i, _f, _d, _f, _d, _f, _f, _d, _d, _vp],
+    "b200seg_adam_chunk": [],
     "b200seg_maxpool_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
 }
 EXPORTS = sorted(list(_PROTOS) + ["b200seg_last_error"])

@@ -407,3 +407,65 @@ def test_train_step_cuda_graph_replay_matches_eager():
     losses = [one(mg, og, cg, 31 + i) for i in range(5)]
     assert all(l == l and l < 10 for l in losses)
     assert int(mg.state_dict()["outc.conv.1.num_batches_tracked"]) == 6
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fused multi-tensor Adam against torch.optim.Adam
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("wd", [0.0, 1e-2])
+def test_fused_adam_matches_torch_adam(wd):
+    """Same update rule as torch/optim/adam.py on tensors of awkward sizes (unaligned views, < 4 elements, > 1 chunk),
+    5 steps with fresh gradients; state_dict layouts are interchangeable."""
+    g = torch.Generator(device="cpu").manual_seed(3)
+    shapes = [(1,), (3,), (7, 5), (32, 3, 3, 3), (96, 16, 1, 1), (1280, 320, 1, 1), (10,), (4099,)]
+    base = [torch.randn(*s, generator=g).to(DEV) for s in shapes]
+    big = torch.randn(1000 + 3, generator=g).to(DEV)
+    base.append(big[3:])                                          # 12-byte offset: not 16-byte aligned -> scalar path
+    pa = [b.clone().requires_grad_(True) for b in base[:-1]] + [base[-1].clone().requires_grad_(True)]
+    pb = [b.clone().requires_grad_(True) for b in base[:-1]] + [big.clone()[3:].requires_grad_(True)]
+    oa = torch.optim.Adam(pa, lr=1.5e-4, weight_decay=wd)
+    ob = b200seg.Adam(pb, lr=1.5e-4, weight_decay=wd)
+    for step in range(5):
+        for x, y in zip(pa, pb):
+            gr = torch.randn(x.shape, generator=g).to(DEV) * (10.0 ** (step - 2))
+            x.grad = gr.clone()
+            y.grad = gr.clone()
+        oa.step()
+        ob.step()
+    for x, y in zip(pa, pb):
+        d = (x.detach() - y.detach()).abs().max().item()
+        assert d <= 1e-6, d                                        # a few fp32 ulps of O(1) parameters; the update itself is 7.5e-4
+    sa, sb = oa.state_dict(), ob.state_dict()
+    assert sa["state"].keys() == sb["state"].keys()
+    for k in sa["state"]:
+        assert set(sa["state"][k].keys()) == set(sb["state"][k].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+        assert float(sa["state"][k]["step"]) == float(sb["state"][k]["step"]) == 5.0
+        torch.testing.assert_close(sa["state"][k]["exp_avg"], sb["state"][k]["exp_avg"], rtol=1e-5, atol=1e-12)
+        torch.testing.assert_close(sa["state"][k]["exp_avg_sq"], sb["state"][k]["exp_avg_sq"], rtol=1e-5, atol=1e-20)
+    ob2 = b200seg.Adam(pb, lr=1.5e-4, weight_decay=wd)
+    ob2.load_state_dict(sa)                                       # torch's optimizer state resumes in the fused one
+
+
+def test_fused_adam_trains_the_model_like_torch_adam():
+    """Two steps of the reference loop body with b200seg.Adam vs torch.optim.Adam from identical state (fp32 path)."""
+    sd = fixture_sd()
+
+    def run(opt_cls):
+        m = b200seg.MobileNetV2UNet(output_channels=10)
+        m.load_state_dict(expand_aliases(sd), strict=True)
+        m = m.to(DEV).train()
+        m._get_engine().use_graphs = False
+        opt, crit = opt_cls(m.parameters(), lr=1.5e-4), b200seg.CrossEntropyLoss()
+        for seed in (40, 41):
+            x, t = O.synth_input(2, 64, 64, seed=seed).to(DEV), O.synth_target(2, 64, 64, seed=seed).to(DEV)
+            opt.zero_grad()
+            loss = crit(m(x), t)
+            loss.backward()
+            opt.step()
+        return {k: v.detach().clone() for k, v in m.named_parameters()}
+
+    a, b = run(torch.optim.Adam), run(b200seg.Adam)
+    for k in a:
+        d = (a[k] - b[k]).abs()
+        # identical gradients up to atomics order; Adam turns rounding noise of ~zero gradients into +-lr steps
+        assert float(d.max()) <= 4 * 1.5e-4 and float(d.mean()) < 0.15 * 1.5e-4, (k, float(d.max()), float(d.mean()))
