@@ -200,6 +200,15 @@ int b200seg_adam_multi(const void* table, const int* chunk_tensor, const int* ch
                        double bias_corr1, double bias_corr2, b200seg_stream_t s);
 int b200seg_adam_chunk(void);
 
+/* ---------------------------------------------------------------------------------------------
+ * Frame pre-processing of inference.py:28-46 for a batch: uint8 HWC BGR frames [B,Hs,Ws,3] ->
+ * cv2.resize(INTER_LINEAR, bit-exact fixed point) to HxW -> RGB -> /255 -> (x - mean) / std -> NCHW [B,3,H,W] of
+ * out_dtype; rgb (nullable) receives the resized RGB uint8 image [B,H,W,3] (the function's second return value).
+ * --------------------------------------------------------------------------------------------- */
+int b200seg_preprocess_u8(const uint8_t* frames, int B, int Hs, int Ws, void* out, int out_dtype, uint8_t* rgb, int H,
+                          int W, float mean0, float mean1, float mean2, float std0, float std1, float std2,
+                          b200seg_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

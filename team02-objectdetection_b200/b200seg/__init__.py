@@ -9,6 +9,7 @@ from . import _cabi  # noqa: F401  (fail loudly if the CUDA library is missing)
 from .unet import LightUNet, MobileNetV2UNet, UNet  # noqa: F401
 from .loss import CrossEntropyLoss  # noqa: F401
 from .optim import Adam  # noqa: F401
+from .preprocess import preprocess_image  # noqa: F401
 
-__all__ = ["MobileNetV2UNet", "UNet", "LightUNet", "CrossEntropyLoss", "Adam"]
+__all__ = ["MobileNetV2UNet", "UNet", "LightUNet", "CrossEntropyLoss", "Adam", "preprocess_image"]
 __version__ = "0.1.0"

@@ -1,0 +1,82 @@
+// Frame pre-processing of the inference script on the GPU (inference.py:28-46):
+//   cv2.resize(frame, (W, H)) -> BGR2RGB -> ToTensor (/255) -> Normalize(mean, std) -> [B,3,H,W]
+// for a batch of uint8 HWC BGR frames.  The resize is OpenCV's fixed-point INTER_LINEAR restated bit for bit
+// (oracle/preprocess_oracle.py explains the algorithm and is checked against cv2 itself): 11-bit coefficients from
+// fx = (float)((dx + 0.5) * scale - 0.5), horizontally a clamped tap zeroes its fraction, vertically the two source rows
+// are clamped individually; the vertical pass is ((b0 * (S0 >> 4) >> 16) + (b1 * (S1 >> 4) >> 16) + 2) >> 2.
+// One thread = one output pixel (3 channels): it derives its own coefficients (no tables, no host work), so the entry
+// point neither allocates nor synchronises.
+#include "common.cuh"
+
+namespace b200 {
+
+__device__ __forceinline__ void lin_coeff(int d, double scale, int ssize, bool zero_clamped, int* s_out, int* a0, int* a1) {
+  // separate multiply and subtract (no fma contraction): this is how the host library evaluates it
+  float f = (float)__dadd_rn(__dmul_rn((double)d + 0.5, scale), -0.5);
+  int s = (int)floorf(f);
+  f = __fsub_rn(f, (float)s);
+  if (zero_clamped) {
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= ssize - 1) { f = 0.f; s = ssize - 1; }
+  }
+  *s_out = s;
+  *a0 = __float2int_rn(__fsub_rn(1.f, f) * 2048.f);      // cvRound: round half to even
+  *a1 = __float2int_rn(f * 2048.f);
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(256)
+preprocess_u8_kernel(const uint8_t* __restrict__ frames, TO* __restrict__ out, uint8_t* __restrict__ rgb, int B, int Hs,
+                     int Ws, int H, int W, float m0, float m1, float m2, float s0, float s1, float s2) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * H * W;
+  if (idx >= total) return;
+  const int dx = (int)(idx % W);
+  const long long t = idx / W;
+  const int dy = (int)(t % H);
+  const int b = (int)(t / H);
+  int sx, ax0, ax1, sy, by0, by1;
+  lin_coeff(dx, (double)Ws / (double)W, Ws, true, &sx, &ax0, &ax1);
+  lin_coeff(dy, (double)Hs / (double)H, Hs, false, &sy, &by0, &by1);
+  const int x1 = min(sx + 1, Ws - 1);
+  const int y0 = min(max(sy, 0), Hs - 1), y1 = min(max(sy + 1, 0), Hs - 1);
+  const uint8_t* base = frames + (long long)b * Hs * Ws * 3;
+  const uint8_t* r0 = base + (long long)y0 * Ws * 3;
+  const uint8_t* r1 = base + (long long)y1 * Ws * 3;
+  const float mean[3] = {m0, m1, m2}, stdv[3] = {s0, s1, s2};
+  const long long plane = (long long)H * W;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {           // k = RGB channel = BGR channel 2 - k
+    const int c = 2 - k;
+    const int S0 = (int)r0[sx * 3 + c] * ax0 + (int)r0[x1 * 3 + c] * ax1;
+    const int S1 = (int)r1[sx * 3 + c] * ax0 + (int)r1[x1 * 3 + c] * ax1;
+    int v = (((by0 * (S0 >> 4)) >> 16) + ((by1 * (S1 >> 4)) >> 16) + 2) >> 2;
+    v = min(max(v, 0), 255);
+    if (rgb) rgb[idx * 3 + k] = (uint8_t)v;
+    const float f = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.f), mean[k]), stdv[k]);   // ToTensor, Normalize
+    out[((long long)b * 3 + k) * plane + (long long)dy * W + dx] = from_f32<TO>(f);
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200seg_preprocess_u8(const uint8_t* frames, int B, int Hs, int Ws, void* out, int out_dtype,
+                                     uint8_t* rgb, int H, int W, float mean0, float mean1, float mean2, float std0,
+                                     float std1, float std2, b200seg_stream_t s) {
+  B200_REQUIRE(frames && out, "preprocess_u8: null pointer");
+  B200_REQUIRE(B > 0 && Hs > 0 && Ws > 0 && H > 0 && W > 0, "preprocess_u8: empty tensor");
+  B200_REQUIRE(std0 != 0.f && std1 != 0.f && std2 != 0.f, "preprocess_u8: zero std");
+  const long long total = (long long)B * H * W;
+  B200_REQUIRE((total + 255) / 256 < (1ll << 31), "preprocess_u8: too many pixels");
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  cudaStream_t st = (cudaStream_t)s;
+  if (out_dtype == B200SEG_F32)
+    preprocess_u8_kernel<float><<<grid, 256, 0, st>>>(frames, (float*)out, rgb, B, Hs, Ws, H, W, mean0, mean1, mean2, std0, std1, std2);
+  else if (out_dtype == B200SEG_BF16)
+    preprocess_u8_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(frames, (__nv_bfloat16*)out, rgb, B, Hs, Ws, H, W, mean0, mean1, mean2, std0, std1, std2);
+  else
+    return set_error(-1, "preprocess_u8: bad out dtype %d", out_dtype);
+  return check_launch("preprocess_u8");
+}

@@ -122,3 +122,17 @@ def test_bilinear_sanity_values():
     assert torch.allclose(a, torch.tensor([0, .25, .75, 1.25, 1.75, 2.25, 2.75, 3.]))
     b = F.interpolate(v, scale_factor=2, mode="bilinear", align_corners=True)[0, 0, 0]
     assert torch.allclose(b, torch.arange(8.) * 3 / 7)
+
+
+def test_preprocess_oracle_matches_reference_bit_for_bit():
+    """oracle/preprocess_oracle.py (cv2.resize fixed-point bilinear + BGR2RGB + ToTensor + Normalize, inference.py:28-46)
+    against outputs of the reference's own preprocess_image() frozen by oracle/make_golden_preprocess.py: the resized
+    uint8 image AND the float32 tensor are identical, for down-scaling, up-scaling, odd sizes and no resize."""
+    from oracle import preprocess_oracle as P
+    g = gold("preprocess.npz")
+    for name in ("down", "odd", "up", "same"):
+        ts = tuple(int(v) for v in g[f"{name}_target_size"])
+        t, img = P.preprocess_image(g[f"{name}_frame"], ts)
+        assert t.shape == (1, 3, ts[1], ts[0]) and t.dtype == np.float32
+        assert np.array_equal(img, g[f"{name}_rgb"]), name
+        assert np.array_equal(t, g[f"{name}_tensor"]), name
