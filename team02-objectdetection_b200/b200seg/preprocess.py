@@ -19,7 +19,8 @@ MEAN = (0.485, 0.456, 0.406)      # inference.py:37
 STD = (0.229, 0.224, 0.225)       # inference.py:38
 
 
-def preprocess_image(image, target_size=(256, 128), device=None, dtype=torch.float32, mean=MEAN, std=STD, out=None):
+def preprocess_image(image, target_size=(256, 128), device=None, dtype=torch.float32, mean=MEAN, std=STD, out=None,
+                     want_rgb: bool = True):
     if not torch.is_tensor(image):
         import numpy as np
         image = torch.from_numpy(np.ascontiguousarray(image))
@@ -37,9 +38,9 @@ def preprocess_image(image, target_size=(256, 128), device=None, dtype=torch.flo
     W, H = int(target_size[0]), int(target_size[1])             # cv2 order: (width, height)
     if out is None:
         out = torch.empty((B, 3, H, W), device=frames.device, dtype=dtype)
-    rgb = torch.empty((B, H, W, 3), device=frames.device, dtype=torch.uint8)
+    rgb = torch.empty((B, H, W, 3), device=frames.device, dtype=torch.uint8) if want_rgb else None
     f = ctypes.c_float
     check(lib.b200seg_preprocess_u8(ptr(frames), B, Hs, Ws, ptr(out), BF16 if out.dtype == torch.bfloat16 else F32, ptr(rgb),
                                     H, W, f(mean[0]), f(mean[1]), f(mean[2]), f(std[0]), f(std[1]), f(std[2]),
                                     torch.cuda.current_stream().cuda_stream), "preprocess_u8")
-    return out, (rgb[0] if single else rgb)
+    return out, (None if rgb is None else rgb[0] if single else rgb)

@@ -48,6 +48,16 @@ def test_preprocess_bf16_output_feeds_the_model():
     assert mask.shape == (2, 64, 128) and mask.dtype == torch.uint8
 
 
+def test_preprocess_same_size_fast_path_bf16_and_no_rgb():
+    rng = np.random.default_rng(9)
+    frames = rng.integers(0, 256, (2, 64, 128, 3), dtype=np.uint8)
+    t16, rgb = b200seg.preprocess_image(torch.from_numpy(frames), target_size=(128, 64), dtype=torch.bfloat16, want_rgb=False)
+    assert rgb is None
+    for b in range(2):
+        tr, _ = P.preprocess_image(frames[b], (128, 64))
+        assert torch.equal(t16[b].cpu(), torch.from_numpy(tr[0]).bfloat16())
+
+
 def test_preprocess_rejects_bad_input():
     with pytest.raises(ValueError):
         b200seg.preprocess_image(torch.zeros(4, 4, 3))                       # not uint8
