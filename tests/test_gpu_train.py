@@ -467,5 +467,10 @@ def test_fused_adam_trains_the_model_like_torch_adam():
     a, b = run(torch.optim.Adam), run(b200seg.Adam)
     for k in a:
         d = (a[k] - b[k]).abs()
-        # identical gradients up to atomics order; Adam turns rounding noise of ~zero gradients into +-lr steps
-        assert float(d.max()) <= 4 * 1.5e-4 and float(d.mean()) < 0.15 * 1.5e-4, (k, float(d.max()), float(d.mean()))
+        # identical gradients up to atomics order; Adam turns rounding noise of ~zero gradients into +-lr steps, and
+        # the 9 conv biases in front of a train-mode BatchNorm have an analytically zero gradient (pure noise): for
+        # those only the step size bounds the difference, run to run, with ANY optimizer implementation
+        zero_grad_bias = k.endswith(".bias") and (".conv.conv.0." in k or ".conv.conv.3." in k or k.startswith("outc.conv.0."))
+        assert float(d.max()) <= 4 * 1.5e-4, (k, float(d.max()))
+        if not zero_grad_bias:
+            assert float(d.mean()) < 0.15 * 1.5e-4, (k, float(d.max()), float(d.mean()))
