@@ -473,4 +473,7 @@ def test_fused_adam_trains_the_model_like_torch_adam():
         zero_grad_bias = k.endswith(".bias") and (".conv.conv.0." in k or ".conv.conv.3." in k or k.startswith("outc.conv.0."))
         assert float(d.max()) <= 4 * 1.5e-4, (k, float(d.max()))
         if not zero_grad_bias:
-            assert float(d.mean()) < 0.15 * 1.5e-4, (k, float(d.max()), float(d.mean()))
+            # the two runs differ by the atomics order of the reductions; at steps 1-2 Adam's update is ~lr*sign(g), so
+            # the handful of near-zero gradients that flip sign move by up to 2*lr (exact arithmetic agreement of the two
+            # optimizers on identical gradients is test_fused_adam_matches_torch_adam)
+            assert float(d.mean()) < 0.5 * 1.5e-4, (k, float(d.max()), float(d.mean()))
