@@ -199,6 +199,14 @@ int b200seg_adam_multi(const void* table, const int* chunk_tensor, const int* ch
                        double one_minus_beta1, float beta2, double one_minus_beta2, float eps, float weight_decay,
                        double bias_corr1, double bias_corr2, b200seg_stream_t s);
 int b200seg_adam_chunk(void);
+/* Weight repack of the training step for all layers in one launch (csrc/adam.cu).  table: device array of
+ * {const float* w (OIHW); void* fwd; void* dgrad; int cout, cin, kk (= taps), cout_pad, kind, pad;} (48 bytes);
+ * kind 0: bf16 fwd [cout_pad][kk][cin] + dgrad [cin][kk flipped][cout_pad]; 1: the same in f32; 2: stem f32
+ * [kk][cin][cout]; 3: depthwise f32 [kk][cout].  Block b handles elements [chunk_index[b]*CHUNK, +CHUNK) of the padded
+ * OIHW tensor chunk_tensor[b], CHUNK = b200seg_pack_chunk(). */
+int b200seg_pack_weights_multi(const void* table, const int* chunk_tensor, const int* chunk_index, int n_chunks,
+                               b200seg_stream_t s);
+int b200seg_pack_chunk(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Frame pre-processing of inference.py:28-46 for a batch: uint8 HWC BGR frames [B,Hs,Ws,3] ->

@@ -55,6 +55,8 @@ _PROTOS = {
     "b200seg_preprocess_u8": [_vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _f, _f, _f, _f, _f, _f, _vp],
     "b200seg_adam_multi": [_vp, _vp, _vp, _i, _f, _d, _f, _d, _f, _f, _d, _d, _vp],
     "b200seg_adam_chunk": [],
+    "b200seg_pack_weights_multi": [_vp, _vp, _vp, _i, _vp],
+    "b200seg_pack_chunk": [],
     "b200seg_maxpool_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
 }
 EXPORTS = sorted(list(_PROTOS) + ["b200seg_last_error"])

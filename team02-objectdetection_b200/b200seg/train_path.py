@@ -50,6 +50,74 @@ def _train_params(engine) -> List[torch.nn.Parameter]:
 
 
 # ----------------------------------------------------------------------------------------------------
+# weight repack: all layers in one launch (b200seg_pack_weights_multi) into persistent operand buffers
+# ----------------------------------------------------------------------------------------------------
+def _train_packs(engine, tc: bool):
+    """Persistent packed-weight buffers of the training step + the device table that fills them.  Returns
+    {step name: dict(wp=..., wk=..., wt=...)} after launching the repack for the CURRENT parameter values.
+    (before, every layer cost 3-6 tiny permute/cast/flip kernels per step, ~280 launches.)"""
+    import ctypes
+    from ._cabi import check, lib, ptr
+    convs = [s for s in engine.steps if s.op in ("stem", "dw", "dense")]
+    dev = convs[0].conv.weight.device
+    key = (tc, dev, tuple(s.conv.weight.data_ptr() for s in convs))
+    plan = getattr(engine, "_train_pack_plan", None)
+    if plan is None or plan["key"] != key:
+        chunk = int(lib.b200seg_pack_chunk())
+        rows, views, ct, ci = [], {}, [], []
+        n16 = n32 = 0
+        metas = []
+        for s in convs:
+            w = s.conv.weight
+            if not w.is_contiguous() or w.dtype != torch.float32:
+                raise TypeError("training keeps contiguous fp32 master weights")
+            cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
+            kk = k * k
+            if s.op == "stem":
+                kind, cp, nf, nd = 2, cout, kk * cin * cout, 0
+            elif s.op == "dw":
+                kind, cp, nf, nd = 3, cout, kk * cout, 0
+            else:
+                kind = 0 if tc else 1
+                cp = max(cout, s.pad_cout) if s.pad_cout else cout
+                nf = nd = cp * kk * cin
+            metas.append((s, kind, cout, cin, kk, cp, nf, nd))
+            if kind == 0:
+                n16 += (nf + 7) // 8 * 8 + (nd + 7) // 8 * 8
+            else:
+                n32 += (nf + 3) // 4 * 4 + (nd + 3) // 4 * 4
+        buf16 = torch.zeros(max(n16, 8), device=dev, dtype=torch.bfloat16)
+        buf32 = torch.zeros(max(n32, 4), device=dev, dtype=torch.float32)
+        o16 = o32 = 0
+        for ti, (s, kind, cout, cin, kk, cp, nf, nd) in enumerate(metas):
+            if kind == 0:
+                fwd = buf16[o16:o16 + nf]; o16 += (nf + 7) // 8 * 8
+                dg = buf16[o16:o16 + nd]; o16 += (nd + 7) // 8 * 8
+            else:
+                fwd = buf32[o32:o32 + nf]; o32 += (nf + 3) // 4 * 4
+                dg = buf32[o32:o32 + nd] if nd else None; o32 += (nd + 3) // 4 * 4
+            if s.op == "stem":
+                views[s.name] = dict(wp=fwd.view(s.conv.weight.shape[2], s.conv.weight.shape[3], cin, cout))
+            elif s.op == "dw":
+                views[s.name] = dict(wp=fwd.view(kk, cout))
+            else:
+                views[s.name] = dict(wk=fwd.view(cp, kk * cin), wt=dg.view(cin, kk * cp))
+            # struct PackEntry {w, fwd, dgrad (8 bytes each); cout, cin, kk, cout_pad, kind, pad (4 bytes each)}
+            rows += [s.conv.weight.data_ptr(), fwd.data_ptr(), dg.data_ptr() if dg is not None else 0,
+                     (cin << 32) | cout, (cp << 32) | kk, kind]
+            n = cp * cin * kk
+            for c in range((n + chunk - 1) // chunk):
+                ct.append(ti); ci.append(c)
+        plan = dict(key=key, views=views, buf16=buf16, buf32=buf32, n=len(ct),
+                    table=torch.tensor(rows, dtype=torch.int64, device=dev),
+                    ct=torch.tensor(ct, dtype=torch.int32, device=dev), ci=torch.tensor(ci, dtype=torch.int32, device=dev))
+        engine._train_pack_plan = plan
+    check(lib.b200seg_pack_weights_multi(ptr(plan["table"]), ptr(plan["ct"]), ptr(plan["ci"]), plan["n"],
+                                         torch.cuda.current_stream().cuda_stream), "pack_weights_multi")
+    return plan["views"]
+
+
+# ----------------------------------------------------------------------------------------------------
 # the two passes as plain functions over tensors (no autograd): used eagerly and under graph capture
 # ----------------------------------------------------------------------------------------------------
 def run_forward(engine, x: torch.Tensor, mode: str):
@@ -59,30 +127,28 @@ def run_forward(engine, x: torch.Tensor, mode: str):
     saved: Dict[str, dict] = {}
     ops.zero_pool.reset()
     ops.zero_pool32.reset()
+    packs = _train_packs(engine, tc)       # every layer's operand layouts from the current fp32 weights, one launch
     counters = []                          # BatchNorm.num_batches_tracked, bumped with one fused launch at the end
     for s in engine.steps:
         rec: dict = {}
         _e0 = _tick()
         if s.op in ("stem", "dw", "dense"):
-            w = s.conv.weight.detach().float()
-            cout = w.shape[0]
+            cout = s.conv.weight.shape[0]
             bias = s.conv.bias.detach().float() if s.conv.bias is not None else None
             src = env[s.src]
+            pk = packs[s.name]
             if s.op == "stem":
-                rec["wp"] = w.permute(2, 3, 1, 0).contiguous()
+                rec["wp"] = pk["wp"]
                 z = ops.conv3x3_smallcin(src, rec["wp"], bias, s.stride, ACT_NONE, sdt)
             elif s.op == "dw":
-                rec["wp"] = w.reshape(cout, 9).t().contiguous()
+                rec["wp"] = pk["wp"]
                 z = ops.dwconv3x3(src, rec["wp"], bias, s.stride, ACT_NONE)
             else:
-                wk = w.permute(0, 2, 3, 1).reshape(cout, -1)
-                if s.pad_cout and cout < s.pad_cout:
-                    wk = torch.cat([wk, wk.new_zeros(s.pad_cout - cout, wk.shape[1])], 0)
-                    if bias is not None:
-                        bias = torch.cat([bias, bias.new_zeros(s.pad_cout - cout)], 0)
-                rec["wk"] = wk.contiguous()
+                if s.pad_cout and cout < s.pad_cout and bias is not None:
+                    bias = torch.cat([bias, bias.new_zeros(s.pad_cout - cout)], 0)
+                rec["wk"], rec["wt"] = pk["wk"], pk["wt"]     # [Cout_pad, taps*Cin] and its transposed/tap-flipped twin
                 if tc:
-                    z = ops.conv_tc(src, rec["wk"].to(torch.bfloat16), bias, s.taps, ACT_NONE, None, flags=engine.tc_flags)
+                    z = ops.conv_tc(src, rec["wk"], bias, s.taps, ACT_NONE, None, flags=engine.tc_flags)
                 else:
                     z = ops.conv_simt(src, rec["wk"], bias, s.taps, ACT_NONE, None)
             rec["z"] = z
@@ -167,13 +233,10 @@ def run_backward(engine, env, saved, mode: str, dout: torch.Tensor, emit) -> Non
                 k = 3 if s.taps == 9 else 1
                 dwk = ops.conv_wgrad_tc(src, dz, s.taps) if tc else ops.conv_wgrad(src, dz, s.taps)   # [Cout_pad, taps*Cin]
                 emit(w, dwk[:cout].reshape(cout, k, k, cin).permute(0, 3, 1, 2).contiguous())
-                # dgrad = the same conv with W transposed (and the 3x3 taps flipped)
-                wk = rec["wk"]                                          # [Cout_pad, taps*Cin]
-                cp = wk.shape[0]
-                wt = wk.reshape(cp, k, k, cin).flip(1, 2).permute(3, 1, 2, 0).reshape(cin, -1).contiguous()
+                # dgrad = the same conv with W transposed (and the 3x3 taps flipped): packed with the forward operand
+                wt = rec["wt"]                                          # [Cin, taps*Cout_pad]
                 if tc:
-                    g[s.src] = ops.conv_tc(dz, wt.to(torch.bfloat16), None, s.taps, ACT_NONE, g.get(s.src),
-                                           flags=engine.tc_flags)
+                    g[s.src] = ops.conv_tc(dz, wt, None, s.taps, ACT_NONE, g.get(s.src), flags=engine.tc_flags)
                 else:
                     g[s.src] = ops.conv_simt(dz, wt, None, s.taps, ACT_NONE, g.get(s.src))
         if _e0 is not None:
@@ -191,6 +254,8 @@ class _StepGraph:
         self.x.copy_(x)
         # torch.cuda.graph() does not run the captured work, but BatchNorm's num_batches_tracked bump is captured
         # like any other kernel, so nothing is double counted.
+        # build the persistent repack plan (allocations, table upload) OUTSIDE the capture
+        _train_packs(engine, mode == "bf16" and (engine.dense_impl or "tc") == "tc")
         torch.cuda.synchronize()
         self.fwd = torch.cuda.CUDAGraph()
         with torch.no_grad(), torch.cuda.graph(self.fwd):

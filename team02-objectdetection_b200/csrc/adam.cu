@@ -81,3 +81,61 @@ extern "C" int b200seg_adam_multi(const void* table, const int* chunk_tensor, co
 }
 
 extern "C" int b200seg_adam_chunk(void) { return ADAM_CHUNK; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight repack for the training step (second half): every conv weight (fp32 OIHW master copy that
+// Adam updates) -> the operand layouts the kernels read, for ALL layers in one launch:
+//   kind 0  dense, tensor-core path: bf16 [Cout_pad][taps][Cin] (forward / wgrad view) and bf16 [Cin][taps flipped][Cout_pad]
+//           (the transposed, tap-flipped weights of the data gradient)
+//   kind 1  dense, fp32 path: the same two layouts in f32
+//   kind 2  stem: f32 [kh][kw][Cin][Cout]          kind 3  depthwise: f32 [9][C]
+// One thread per element of the padded OIHW tensor (coalesced reads; rows >= Cout are written as zeros).
+// ---------------------------------------------------------------------------------------------------------------
+namespace b200 {
+
+struct PackEntry {       // 48 bytes
+  const float* w;
+  void* fwd;
+  void* dgrad;
+  int cout, cin, kk, cout_pad, kind, pad_;
+};
+
+constexpr int PACK_CHUNK = 2048;
+
+__global__ void __launch_bounds__(256)
+pack_weights_kernel(const PackEntry* __restrict__ table, const int* __restrict__ chunk_tensor,
+                    const int* __restrict__ chunk_index) {
+  const PackEntry t = table[chunk_tensor[blockIdx.x]];
+  const long long per_o = (long long)t.cin * t.kk;
+  const long long n = (long long)t.cout_pad * per_o;
+  const long long base = (long long)chunk_index[blockIdx.x] * PACK_CHUNK;
+  for (long long e = base + threadIdx.x; e < min(base + PACK_CHUNK, n); e += 256) {
+    const int o = (int)(e / per_o);
+    const int r = (int)(e - (long long)o * per_o);
+    const int i = r / t.kk, tap = r - i * t.kk;
+    const float v = o < t.cout ? __ldg(t.w + e) : 0.f;          // same linear index: the padding rows come last
+    if (t.kind == 0) {
+      reinterpret_cast<__nv_bfloat16*>(t.fwd)[((long long)o * t.kk + tap) * t.cin + i] = __float2bfloat16_rn(v);
+      reinterpret_cast<__nv_bfloat16*>(t.dgrad)[((long long)i * t.kk + (t.kk - 1 - tap)) * t.cout_pad + o] = __float2bfloat16_rn(v);
+    } else if (t.kind == 1) {
+      reinterpret_cast<float*>(t.fwd)[((long long)o * t.kk + tap) * t.cin + i] = v;
+      reinterpret_cast<float*>(t.dgrad)[((long long)i * t.kk + (t.kk - 1 - tap)) * t.cout_pad + o] = v;
+    } else if (t.kind == 2) {
+      reinterpret_cast<float*>(t.fwd)[((long long)tap * t.cin + i) * t.cout + o] = v;
+    } else {
+      reinterpret_cast<float*>(t.fwd)[(long long)tap * t.cout + o] = v;
+    }
+  }
+}
+
+}  // namespace b200
+
+extern "C" int b200seg_pack_weights_multi(const void* table, const int* chunk_tensor, const int* chunk_index,
+                                          int n_chunks, b200seg_stream_t s) {
+  B200_REQUIRE(table && chunk_tensor && chunk_index && n_chunks > 0, "pack_weights_multi: bad arguments");
+  b200::pack_weights_kernel<<<(unsigned)n_chunks, 256, 0, (cudaStream_t)s>>>((const b200::PackEntry*)table, chunk_tensor,
+                                                                              chunk_index);
+  return b200::check_launch("pack_weights_multi");
+}
+
+extern "C" int b200seg_pack_chunk(void) { return b200::PACK_CHUNK; }
