@@ -69,8 +69,14 @@ class ClockSampler:
         self.rows, self.proc, self.index, self.first = [], None, index, 0
 
     def mark(self):
-        """Start of the timed region: only samples taken from here on are reported.  (nvidia-smi itself is started
-        before the warm-up so that its NVML initialisation, which can stall launches for tens of ms, is outside.)"""
+        """Start of the timed region: only samples taken from here on are reported.  nvidia-smi is started at process start
+        and we WAIT here until it has delivered its first sample: on a fresh box its first start (binary paged in from the
+        image, NVML initialisation) takes seconds and stalls kernel launches for tens of milliseconds while it lasts --
+        measured: the first bench on a box read 3.7-4.3 ms/step instead of 2.62 when that overlapped the timed region."""
+        if self.proc is not None:
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 20.0 and self.proc.poll() is None:
+                time.sleep(0.05)
         self.first = len(self.rows)
 
     def start(self):
@@ -192,9 +198,14 @@ def main():
     from b200seg import _cabi
     sms, cc = _cabi.device_info()
 
+    # nvidia-smi is started NOW, seconds before the timed region: its NVML initialisation stalls kernel launches for tens of
+    # milliseconds on a fresh box (measured: a 54 ms timed region read 4.0-4.3 ms/step instead of 2.66 when it overlapped)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     if args.workload in ("train", "unet_train"):
         from bench_train import run_train          # training step benchmark lives in its own file
-        return run_train(args, dev, dist, world, rank, peaks(), ClockSampler, emit)
+        return run_train(args, dev, dist, world, rank, peaks(), clocks, emit)
 
     global H, W
     if args.workload == "infer720":
@@ -214,9 +225,6 @@ def main():
 
     # ---------------- value leg: inputs resident in HBM ----------------
     with torch.no_grad():
-        clocks = ClockSampler(local)
-        if rank == 0:
-            clocks.start()
         for i in range(args.warmup):
             model(xs[i % nrot])
         barrier()

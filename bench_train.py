@@ -15,7 +15,7 @@ import torch
 H, W, NCLS = 256, 512, 10
 
 
-def run_train(args, dev, dist, world, rank, pk, ClockSampler, emit):
+def run_train(args, dev, dist, world, rank, pk, clocks, emit):
     import b200seg
     from b200seg import dp, train_path
     global H, W
@@ -54,10 +54,7 @@ def run_train(args, dev, dist, world, rank, pk, ClockSampler, emit):
             dist.barrier()
         torch.cuda.synchronize()
 
-    clocks = ClockSampler(dev.index or 0)
-    if rank == 0:
-        clocks.start()
-    for i in range(args.warmup):
+    for i in range(args.warmup):        # (the nvidia-smi sampler was started by bench.py, seconds ago)
         step(xs[i % nrot], ys[i % nrot])
     barrier()
     clocks.mark()
