@@ -422,7 +422,7 @@ dwconv3x3_bf16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restri
 // 0.25*a + 0.75*a == a exactly in one fma.
 // ------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256, 5)
+__global__ void __launch_bounds__(256)
 upsample2x_concat_kernel(const T* __restrict__ skip, const T* __restrict__ x, T* __restrict__ y, int B, int h,
                          int w, int Cs, int Cu) {
   pdl_trigger();
