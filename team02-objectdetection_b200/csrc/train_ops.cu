@@ -589,6 +589,102 @@ smallcin_wgrad_kernel(const TI* __restrict__ x, const T* __restrict__ dz, float*
   }
 }
 
+// Row-tile version for Cin == 3 (the stems): a job = one output row segment of 128 pixels.  The 9 (channel, kh) input
+// rows it touches are staged in shared memory with coalesced loads (as the forward stem kernel does), dz of the segment
+// as f32 [128][Cout].  Thread = (pixel quarter, 4 consecutive k = (tap, c) x 4 consecutive output channels): per pixel
+// 4 patch reads + one 16-byte dz read feed 16 FMAs; the 16 partial sums stay in registers across all jobs of the block
+// and are reduced over the four pixel quarters and added to dw once at the end.
+template <typename TI, typename T, int S>
+__global__ void __launch_bounds__(256)
+smallcin3_wgrad_tile_kernel(const TI* __restrict__ x, const T* __restrict__ dz, float* __restrict__ dw, int B, int H, int W,
+                            int Cout, int Ho, int Wo) {
+  constexpr int NCOL = 127 * S + 3;
+  constexpr int PITCH = NCOL + 3;
+  extern __shared__ float sm[];
+  float* tile = sm;                               // [9][PITCH]   row = c*3 + kh, column j <-> input column wo0*S - 1 + j
+  float* sd = sm + ((9 * PITCH + 3) & ~3);        // [128][Cout], 16-byte aligned for the float4 reads
+  const int c4n = Cout >> 2;
+  const int nitems = 7 * c4n;                     // 7 groups of 4 k (27 -> 28)
+  const int pq = threadIdx.x >> 6, r = threadIdx.x & 63;
+  int toff[2][4], c4v[2];
+  bool act[2];
+  float acc[2][4][4];
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int item = r + it * 64;
+    act[it] = item < nitems;
+    const int kq = item / c4n;
+    c4v[it] = (item - kq * c4n) * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = kq * 4 + j;                   // k = tap*3 + c  (matches dw's [kh][kw][c][co] layout)
+      const int tap = k / 3, c = k - tap * 3, kh = tap / 3, kw = tap - kh * 3;
+      toff[it][j] = (k < 27) ? (c * 3 + kh) * PITCH + kw : -1;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[it][j][q] = 0.f;
+    }
+  }
+  const int segs = (Wo + 127) / 128;
+  const long long total = (long long)B * Ho * segs;
+  const long long HW = (long long)H * W;
+  for (long long job = blockIdx.x; job < total; job += gridDim.x) {
+    const int sg = (int)(job % segs);
+    long long p = job / segs;
+    const int ho = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    const int wo0 = sg * 128;
+    const TI* xb = x + (long long)b * 3 * HW;
+    const int wi0 = wo0 * S - 1, hi0 = ho * S - 1;
+    __syncthreads();                              // previous job's reads are done
+    for (int i = threadIdx.x; i < 9 * NCOL; i += 256) {
+      const int rowi = i / NCOL, col = i - rowi * NCOL;
+      const int c = rowi / 3, kh = rowi - c * 3;
+      const int hi = hi0 + kh, wi = wi0 + col;
+      float v = 0.f;
+      if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = to_f32<TI>(xb[(long long)c * HW + (long long)hi * W + wi]);
+      tile[rowi * PITCH + col] = v;
+    }
+    const T* dzr = dz + (((long long)b * Ho + ho) * Wo + wo0) * Cout;
+    for (int i = threadIdx.x; i < 128 * Cout; i += 256) {
+      const int px = i / Cout;
+      sd[i] = (wo0 + px < Wo) ? to_f32<T>(dzr[i]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      if (!act[it]) continue;
+      const float* sdp = sd + c4v[it];
+#pragma unroll 4
+      for (int i = 0; i < 32; ++i) {
+        const int px = pq * 32 + i;
+        const float4 d = *reinterpret_cast<const float4*>(sdp + px * Cout);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float a = toff[it][j] >= 0 ? tile[toff[it][j] + px * S] : 0.f;
+          acc[it][j][0] = fmaf(a, d.x, acc[it][j][0]); acc[it][j][1] = fmaf(a, d.y, acc[it][j][1]);
+          acc[it][j][2] = fmaf(a, d.z, acc[it][j][2]); acc[it][j][3] = fmaf(a, d.w, acc[it][j][3]);
+        }
+      }
+    }
+  }
+  // reduce the four pixel quarters through shared memory, then one atomic per (k, co) per block
+  __syncthreads();
+  float* red = sm;                                // [4][28 * Cout] <= 4 * 28 * 64 floats = 28 KB (tile + sd are >= that)
+  const int stride_q = 28 * Cout;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    if (!act[it]) continue;
+    const int item = r + it * 64, kq = item / c4n;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) red[pq * stride_q + (kq * 4 + j) * Cout + c4v[it] + q] = acc[it][j][q];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 27 * Cout; i += 256)
+    atomicAdd(dw + i, red[i] + red[stride_q + i] + red[2 * stride_q + i] + red[3 * stride_q + i]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // adjoints of the bilinear upsamplings.  Gather form: every source pixel enumerates the few output
 // pixels that read it and re-evaluates PyTorch's forward index/weight formula for each, so clamped
@@ -936,6 +1032,28 @@ int b200seg_smallcin_wgrad(const void* x, int x_dtype, const void* dz, int dtype
   B200_REQUIRE(B > 0 && H > 0 && W > 0, "smallcin_wgrad: empty tensor");
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   const long long P = (long long)B * Ho * Wo;
+  cudaStream_t st0 = (cudaStream_t)s;
+  if (Cin == 3 && Cout <= 64) {                  // the two stems of the path: row-tile kernel
+    const long long jobs = (long long)B * Ho * ((Wo + 127) / 128);
+    long long gb = (long long)sm_count() * 4;
+    if (gb > jobs) gb = jobs;
+    const int ncol = 127 * stride + 3;
+    size_t smem_t = (size_t)(((9 * (ncol + 3) + 3) & ~3) + 128 * Cout) * sizeof(float);
+    const size_t red_b = (size_t)4 * 28 * Cout * sizeof(float);
+    if (smem_t < red_b) smem_t = red_b;
+#define LAUNCH_T(TI, T)                                                                                                   \
+  {                                                                                                                     \
+    if (stride == 2) smallcin3_wgrad_tile_kernel<TI, T, 2><<<(unsigned)gb, 256, smem_t, st0>>>((const TI*)x, (const T*)dz, dw, B, H, W, Cout, Ho, Wo); \
+    else smallcin3_wgrad_tile_kernel<TI, T, 1><<<(unsigned)gb, 256, smem_t, st0>>>((const TI*)x, (const T*)dz, dw, B, H, W, Cout, Ho, Wo);             \
+  }
+    if (x_dtype == B200SEG_F32 && dtype == B200SEG_F32) LAUNCH_T(float, float)
+    else if (x_dtype == B200SEG_F32 && dtype == B200SEG_BF16) LAUNCH_T(float, bf16)
+    else if (x_dtype == B200SEG_BF16 && dtype == B200SEG_BF16) LAUNCH_T(bf16, bf16)
+    else if (x_dtype == B200SEG_BF16 && dtype == B200SEG_F32) LAUNCH_T(bf16, float)
+    else return set_error(-1, "smallcin_wgrad: bad dtypes");
+#undef LAUNCH_T
+    return check_launch("smallcin_wgrad");
+  }
   long long blocks = (long long)sm_count() * 4;
   long long ppb = (P + blocks - 1) / blocks;
   ppb = (ppb + 31) / 32 * 32;
