@@ -76,7 +76,7 @@ def _train_packs(engine, tc: bool):
             if s.op == "stem":
                 kind, cp, nf, nd = 2, cout, kk * cin * cout, 0
             elif s.op == "dw":
-                kind, cp, nf, nd = 3, cout, kk * cout, 0
+                kind, cp, nf, nd = 3, cout, kk * cout, kk * cout
             else:
                 kind = 0 if tc else 1
                 cp = max(cout, s.pad_cout) if s.pad_cout else cout
@@ -99,7 +99,7 @@ def _train_packs(engine, tc: bool):
             if s.op == "stem":
                 views[s.name] = dict(wp=fwd.view(s.conv.weight.shape[2], s.conv.weight.shape[3], cin, cout))
             elif s.op == "dw":
-                views[s.name] = dict(wp=fwd.view(kk, cout))
+                views[s.name] = dict(wp=fwd.view(kk, cout), wpf=dg.view(kk, cout))
             else:
                 views[s.name] = dict(wk=fwd.view(cp, kk * cin), wt=dg.view(cin, kk * cp))
             # struct PackEntry {w, fwd, dgrad (8 bytes each); cout, cin, kk, cout_pad, kind, pad (4 bytes each)}
@@ -141,7 +141,7 @@ def run_forward(engine, x: torch.Tensor, mode: str):
                 rec["wp"] = pk["wp"]
                 z = ops.conv3x3_smallcin(src, rec["wp"], bias, s.stride, ACT_NONE, sdt)
             elif s.op == "dw":
-                rec["wp"] = pk["wp"]
+                rec["wp"], rec["wpf"] = pk["wp"], pk["wpf"]
                 z = ops.dwconv3x3(src, rec["wp"], bias, s.stride, ACT_NONE)
             else:
                 if s.pad_cout and cout < s.pad_cout and bias is not None:
@@ -227,7 +227,12 @@ def run_backward(engine, env, saved, mode: str, dout: torch.Tensor, emit) -> Non
             elif s.op == "dw":
                 dw9 = ops.dw_wgrad(src, dz, s.stride)                  # [9,C]
                 emit(w, dw9.t().reshape(cout, 1, 3, 3).contiguous())
-                g[s.src] = ops.dw_dgrad(dz, rec["wp"], tuple(src.shape), s.stride, g.get(s.src))
+                if s.stride == 1 and g.get(s.src) is None:
+                    # stride 1: the data gradient IS the forward depthwise conv of dz with the taps flipped -> the
+                    # register-blocked forward kernel (2.5x faster than the generic gather kernel)
+                    g[s.src] = ops.dwconv3x3(dz, rec["wpf"], None, 1, ACT_NONE)
+                else:
+                    g[s.src] = ops.dw_dgrad(dz, rec["wp"], tuple(src.shape), s.stride, g.get(s.src))
             else:
                 cin = src.shape[-1]
                 k = 3 if s.taps == 9 else 1

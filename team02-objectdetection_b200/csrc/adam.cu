@@ -88,7 +88,7 @@ extern "C" int b200seg_adam_chunk(void) { return ADAM_CHUNK; }
 //   kind 0  dense, tensor-core path: bf16 [Cout_pad][taps][Cin] (forward / wgrad view) and bf16 [Cin][taps flipped][Cout_pad]
 //           (the transposed, tap-flipped weights of the data gradient)
 //   kind 1  dense, fp32 path: the same two layouts in f32
-//   kind 2  stem: f32 [kh][kw][Cin][Cout]          kind 3  depthwise: f32 [9][C]
+//   kind 2  stem: f32 [kh][kw][Cin][Cout]          kind 3  depthwise: f32 [9][C] (+ the tap-flipped [9][C] for the data gradient)
 // One thread per element of the padded OIHW tensor (coalesced reads; rows >= Cout are written as zeros).
 // ---------------------------------------------------------------------------------------------------------------
 namespace b200 {
@@ -124,6 +124,8 @@ pack_weights_kernel(const PackEntry* __restrict__ table, const int* __restrict__
       reinterpret_cast<float*>(t.fwd)[((long long)tap * t.cin + i) * t.cout + o] = v;
     } else {
       reinterpret_cast<float*>(t.fwd)[(long long)tap * t.cout + o] = v;
+      // tap-flipped twin: the stride-1 data gradient of a depthwise conv is the same depthwise conv with flipped taps
+      if (t.dgrad) reinterpret_cast<float*>(t.dgrad)[(long long)(t.kk - 1 - tap) * t.cout + o] = v;
     }
   }
 }
