@@ -106,6 +106,42 @@ def test_no_cpu_fallback_and_containers_refuse_to_run():
         b200seg.CrossEntropyLoss()(torch.zeros(1, 10, 4, 4), torch.zeros(1, 4, 4, dtype=torch.long))
 
 
+def test_optimizer_and_preprocess_have_no_cpu_fallback_either():
+    """b200seg.Adam takes torch.optim.Adam's constructor arguments and refuses CPU parameters; preprocess_image validates
+    its frame before touching the GPU."""
+    p = torch.nn.Parameter(torch.zeros(4))
+    opt = b200seg.Adam([p], lr=1.5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)
+    assert opt.defaults["lr"] == 1.5e-4 and opt.defaults["betas"] == (0.9, 0.999)
+    p.grad = torch.ones(4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        opt.step()
+    with pytest.raises(ValueError):
+        b200seg.Adam([p], lr=-1.0)
+    with pytest.raises(ValueError):
+        b200seg.preprocess_image(torch.zeros(8, 8, 3))                       # float frame
+    with pytest.raises(ValueError):
+        b200seg.preprocess_image(torch.zeros(8, 8, 1, dtype=torch.uint8))    # not 3 channels
+
+
+def test_fused_schedule_replaces_the_inverted_residual_triples():
+    """Eval bf16 schedule: the 16 expand-ratio-6 blocks are one step each where the policy fuses them (everything but the
+    stride-2 block at half resolution for a 256x512 input), 62 convs stay covered exactly once."""
+    from b200seg import engine
+    m = b200seg.MobileNetV2UNet(output_channels=10)
+    eng = m._get_engine()
+    assert len(eng._mb_triples()) == 16
+    sched = eng._schedule("bf16", "tc", 256, 512)
+    fused = [s for s in sched if s.op == "mbconv"]
+    assert len(fused) == 15 and len(sched) == 37
+    assert all(s.parts[1].stride in (1, 2) and s.parts[0].src == s.src and s.parts[2].dst == s.dst for s in fused)
+    assert "backbone.features.2" not in {s.name for s in fused}               # 16->96->24 stride 2 at 128x256 stays unfused
+    n_convs = sum(3 if s.op == "mbconv" else 1 for s in sched if s.op in ("stem", "dw", "dense", "mbconv"))
+    assert n_convs == 62
+    assert eng._schedule("fp32", "simt", 256, 512) is eng.steps               # the exact path is never fused
+    eng.mbconv_impl = "fused"
+    assert sum(s.op == "mbconv" for s in eng._schedule("bf16", "tc", 256, 512)) == 16
+
+
 def test_schedule_covers_every_used_parameter():
     """Every parameter except the dead classifier is consumed by exactly one fused step."""
     from b200seg import engine
