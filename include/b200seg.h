@@ -217,6 +217,10 @@ int b200seg_preprocess_u8(const uint8_t* frames, int B, int Hs, int Ws, void* ou
                           int W, float mean0, float mean1, float mean2, float std0, float std1, float std2,
                           b200seg_stream_t s);
 
+/* Diagnostic (not on the product path): cycles for `iters` back-to-back tcgen05.mma kind::f16 of shape M x N x 16 issued
+ * by one thread per CTA, `ctas_per_sm` CTAs resident per SM; cycles_out[cta] (device, long long). tools/mma_probe.py. */
+int b200seg_probe_mma(int M, int N, int iters, int ctas_per_sm, long long* cycles_out, b200seg_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

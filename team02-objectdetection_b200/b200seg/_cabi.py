@@ -53,6 +53,7 @@ _PROTOS = {
     "b200seg_final_bwd": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "b200seg_nchw_to_nhwc_pad": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "b200seg_preprocess_u8": [_vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _f, _f, _f, _f, _f, _f, _vp],
+    "b200seg_probe_mma": [_i, _i, _i, _i, _vp, _vp],
     "b200seg_adam_multi": [_vp, _vp, _vp, _i, _f, _d, _f, _d, _f, _f, _d, _d, _vp],
     "b200seg_adam_chunk": [],
     "b200seg_pack_weights_multi": [_vp, _vp, _vp, _i, _vp],
