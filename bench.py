@@ -293,7 +293,8 @@ def main():
             if it < 3:
                 continue
             for s, a, b, nbytes, flops in prof:
-                r = acc.setdefault(s.name, dict(op=s.op, taps=s.taps, ms=0.0, bytes=nbytes, flops=flops, n=0))
+                r = acc.setdefault(s.name, dict(op=s.op, taps=s.taps, ms=0.0, bytes=nbytes, flops=flops, n=0,
+                                                shape=(tuple(s.conv.weight.shape) if s.op == "dense" else None)))
                 r["ms"] += a.elapsed_time(b); r["n"] += 1
     rows = []
     for name, r in acc.items():
@@ -301,6 +302,7 @@ def main():
         gbs, tfs = r["bytes"] / t / 1e9, r["flops"] / t / 1e12
         bound = "tensor" if (r["flops"] / max(r["bytes"], 1)) > pk["tc"] * 1e3 / pk["hbm"] else "hbm"
         rows.append(dict(name=name, op=r["op"], us=t * 1e6, gbs=gbs, tfs=tfs, bound=bound, bytes=r["bytes"], flops=r["flops"],
+                         shape=r["shape"], taps=r["taps"],
                          frac=(tfs / pk["tc_burst"]) if bound == "tensor" else gbs / pk["hbm"]))
     rows.sort(key=lambda r: -r["us"])
     tot_us = sum(r["us"] for r in rows)
@@ -317,6 +319,21 @@ def main():
                 "unit": "TFLOP/s" if top["bound"] == "tensor" else "GB/s", "frac": top["frac"], "traffic": None,
                 "peak_source": pk["src"], "share_of_step": top["us"] / tot_us,
                 "algorithmic_per_launch": top["flops"] if top["bound"] == "tensor" else top["bytes"]}
+    if top.get("shape"):
+        # third bound of a small-N implicit GEMM: the tcgen05.mma issue floor measured by tools/mma_probe.py
+        # (profiles/r01_mma_probe.txt): cycles per M=128, K=16 instruction as a function of N, per SM
+        cout, cin, taps = top["shape"][0], top["shape"][1], top["taps"]
+        n_tile = min((cout + 15) // 16 * 16, 256)
+        table = [(16, 39.0), (32, 40.0), (64, 48.0), (128, 64.0), (256, 128.0)]
+        cyc = next(c for n, c in table if n_tile <= n)
+        ksteps = sum((min(64, cin - c0) + 15) // 16 for c0 in range(0, cin, 64))
+        pixels = top["flops"] / (2.0 * cout * taps * cin)
+        n_mma = (pixels / 128.0) * taps * ksteps * ((cout + n_tile - 1) // n_tile)
+        floor_us = n_mma * cyc / sms / ((clk or {}).get("sm_mhz") or 1965.0)
+        roofline["mma_issue_floor_us"] = floor_us
+        roofline["frac_of_mma_issue_floor"] = floor_us / top["us"]
+        roofline["note"] = ("small-N implicit GEMM: bound by the tcgen05.mma issue floor (cycles per instruction do not shrink "
+                            "below ~40 for N < 96), not by HBM; see DESIGN.md finding 8")
     try:                                   # DRAM traffic of the dominant kernel from the committed ncu capture, if it is the same kernel
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             ent = json.load(f).get(top["name"])
