@@ -105,12 +105,11 @@ int b200seg_mbconv(const void* x, const void* w_exp, const float* b_exp, const f
                    const void* w_proj, const float* b_proj, int residual, void* y, int B, int H, int W, int Cin,
                    int Ce, int Cout, int stride, int flags, b200seg_stream_t s);
 
-/* Same block, depthwise stencil on the tensor cores as well (9 taps x diagonal 16x16 weight blocks; see
- * csrc/mbconv_tc.cu).  w_dwdiag: bf16 [ceil64(Ce)/64][9][16][64], element [c][t][n][16*g+n] = w_dw[t][64c+16g+n],
- * zero elsewhere (b200seg.ops.pack_dw_diag16).  Other operands as b200seg_mbconv. */
-int b200seg_mbconv_tc(const void* x, const void* w_exp, const float* b_exp, const void* w_dwdiag,
-                      const float* b_dw, const void* w_proj, const float* b_proj, int residual, void* y, int B,
-                      int H, int W, int Cin, int Ce, int Cout, int stride, int flags, b200seg_stream_t s);
+/* Same block and the same operands, depthwise stencil on the tensor cores as well (9 taps x diagonal 16x16 weight
+ * blocks, written into shared memory by the kernel from w_dw, rounded to bf16; see csrc/mbconv_tc.cu). */
+int b200seg_mbconv_tc(const void* x, const void* w_exp, const float* b_exp, const float* w_dw, const float* b_dw,
+                      const void* w_proj, const float* b_proj, int residual, void* y, int B, int H, int W, int Cin,
+                      int Ce, int Cout, int stride, int flags, b200seg_stream_t s);
 
 /* NHWC [B,H,W,ldc] (first C valid) -> NCHW [B,C,H,W] (UNet returns logits at input resolution). */
 int b200seg_nhwc_to_nchw(const void* x, int dtype, int ldc, void* out, int out_dtype, int B, int H, int W,

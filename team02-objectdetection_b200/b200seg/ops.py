@@ -151,38 +151,23 @@ def mbconv(x, w_exp, b_exp, w_dw, b_dw, w_proj, b_proj, stride: int, residual: b
     return out
 
 
-def pack_dw_diag16(w9c: torch.Tensor) -> torch.Tensor:
-    """f32 [9, C] depthwise taps -> bf16 [ceil(C/64), 9, 16, 64] diagonal blocks for mbconv_tc: row n of tap t in
-    chunk c carries w[t, 64c+16g+n] at column 16g+n (g = 0..3) and zeros elsewhere."""
-    C = w9c.shape[1]
-    nch = (C + 63) // 64
-    wp = torch.zeros(9, nch * 64, device=w9c.device, dtype=torch.float32)
-    wp[:, :C] = w9c
-    wp = wp.reshape(9, nch, 4, 16)                                   # [t][c][g][n]
-    out = torch.zeros(nch, 9, 16, 4, 16, device=w9c.device, dtype=torch.float32)   # [c][t][n][g][n']
-    idx = torch.arange(16, device=w9c.device)
-    out[:, :, idx, :, idx] = wp.permute(3, 1, 0, 2)                  # -> [n][c][t][g]
-    return out.reshape(nch, 9, 16, 64).to(torch.bfloat16).contiguous()
-
-
-def mbconv_tc(x, w_exp, b_exp, w_dwdiag, b_dw, w_proj, b_proj, stride: int, residual: bool, out=None, flags: int = 0):
-    """Fused inverted-residual block with the depthwise stencil on the tensor cores (see mbconv); w_dwdiag from
-    pack_dw_diag16, b_exp/b_dw f32 [ceil64(Ce)], b_proj f32 [ceil16(Cout)]."""
-    _cuda(x, w_exp, b_exp, w_dwdiag, b_dw, w_proj, b_proj)
-    if (x.dtype != torch.bfloat16 or w_exp.dtype != torch.bfloat16 or w_proj.dtype != torch.bfloat16
-            or w_dwdiag.dtype != torch.bfloat16):
+def mbconv_tc(x, w_exp, b_exp, w_dw, b_dw, w_proj, b_proj, stride: int, residual: bool, out=None, flags: int = 0):
+    """Fused inverted-residual block with the depthwise stencil on the tensor cores; same operands as mbconv (the
+    depthwise taps are rounded to bf16 inside the kernel)."""
+    _cuda(x, w_exp, b_exp, w_dw, b_dw, w_proj, b_proj)
+    if x.dtype != torch.bfloat16 or w_exp.dtype != torch.bfloat16 or w_proj.dtype != torch.bfloat16:
         raise TypeError("mbconv_tc is bf16-only")
     B, H, W, Cin = x.shape
     Ce, Cout = w_exp.shape[0], w_proj.shape[0]
     cep, cop = (Ce + 63) // 64 * 64, (Cout + 15) // 16 * 16
-    if (tuple(w_exp.shape) != (Ce, Cin) or tuple(w_proj.shape) != (Cout, Ce) or tuple(w_dwdiag.shape) != (cep // 64, 9, 16, 64)
-            or b_exp.numel() != cep or b_dw.numel() != cep or b_proj.numel() != cop):
-        raise ValueError(f"mbconv_tc: operand shapes w_exp {tuple(w_exp.shape)} w_dwdiag {tuple(w_dwdiag.shape)} "
+    if (tuple(w_exp.shape) != (Ce, Cin) or tuple(w_proj.shape) != (Cout, Ce) or tuple(w_dw.shape) != (9, cep)
+            or w_dw.dtype != torch.float32 or b_exp.numel() != cep or b_dw.numel() != cep or b_proj.numel() != cop):
+        raise ValueError(f"mbconv_tc: operand shapes w_exp {tuple(w_exp.shape)} w_dw {tuple(w_dw.shape)} "
                          f"w_proj {tuple(w_proj.shape)} b {b_exp.numel()},{b_dw.numel()},{b_proj.numel()}")
     Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
     if out is None:
         out = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=torch.bfloat16)
-    check(lib.b200seg_mbconv_tc(ptr(x), ptr(w_exp), ptr(b_exp), ptr(w_dwdiag), ptr(b_dw), ptr(w_proj), ptr(b_proj),
+    check(lib.b200seg_mbconv_tc(ptr(x), ptr(w_exp), ptr(b_exp), ptr(w_dw), ptr(b_dw), ptr(w_proj), ptr(b_proj),
                                 1 if residual else 0, ptr(out), B, H, W, Cin, Ce, Cout, stride, flags, _stream()),
           "mbconv_tc")
     return out

@@ -20,8 +20,10 @@
 //             columns; r = oh*17 + ow and tap (dh, dw) reads plane (dh&1, dw&1) at rows r + (dh>>1)*17 + (dw>>1).
 // The project GEMM and the output epilogue use the same row index r.
 //
-// Roles: warp 0 TMA producer (halo tile of x once per tile; per chunk We[64][Cin], the 9 diagonal tap blocks,
-// Wp[Cout][64]); warp 1 issues every tcgen05.mma; warps 2..9 do the two accumulator hand-offs and the output.
+// Roles: warp 0 TMA producer (halo tile of x once per tile; per chunk We[64][Cin] and Wp[Cout][64]); warp 1 issues every
+// tcgen05.mma; warps 2..9 do the two accumulator hand-offs and the output, and write the 9 x 64 diagonal entries of the
+// depthwise B tiles of each chunk (the tiles are zeroed once; streaming them by TMA cost 18 KB per chunk, which left room
+// for a single weight stage and serialised expand(c+1) behind project(c)).
 #include "common.cuh"
 
 namespace b200 {
@@ -36,6 +38,7 @@ struct MtArgs {
   const __nv_bfloat16* x;    // [B][H][W][Cin]
   __nv_bfloat16* y;          // [B][Ho][Wo][Cout]
   const float* b_exp;        // [ce_chunks*64]
+  const float* w_dw;         // [9][ce_chunks*64] f32 (rounded to bf16 when written into the B tiles)
   const float* b_dw;         // [ce_chunks*64]
   const float* b_proj;       // [cout_pad]
   int B, H, W, Ho, Wo, Cin, Ce, Cout;
@@ -142,7 +145,7 @@ __device__ __forceinline__ void load_bias32(const float* p, float (&b)[32]) {
 template <int MINB, int S, int TH>
 __global__ void __launch_bounds__(MT_THREADS, MINB)
 mbconv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWe,
-                 const __grid_constant__ CUtensorMap tmWd, const __grid_constant__ CUtensorMap tmWp, const MtArgs a) {
+                 const __grid_constant__ CUtensorMap tmWp, const MtArgs a) {
   using G = GeoT<S, TH>;
   constexpr int MX = G::MX;
   extern __shared__ uint8_t smem_raw[];
@@ -154,8 +157,9 @@ mbconv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint8_t* sX = smem;                                         // kcn chunks x [halo px][64] bf16
   uint8_t* sE = sX + a.kcn * a.x_chunk_stride;                // expanded tile (planes), 64 channels
   uint8_t* sD = sE + G::E_BYTES;                              // nbuf_d x [128][64] bf16
-  uint8_t* sW = sD + a.nbuf_d * 16384;                        // nws x (We chunk | 9 diagonal tap blocks | Wp chunk)
-  const int w_stage = a.we_bytes + WD_BYTES + a.wp_bytes;
+  uint8_t* sWd = sD + a.nbuf_d * 16384;                       // 9 diagonal tap blocks [16 rows][64 k] (written in place)
+  uint8_t* sW = sWd + WD_BYTES;                               // nws x (We chunk | Wp chunk)
+  const int w_stage = a.we_bytes + a.wp_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + a.nws * w_stage);
   uint64_t* x_full = bars;           // [1] TMA
   uint64_t* x_empty = bars + 1;      // [1] commit (last expand of the tile)
@@ -172,10 +176,10 @@ mbconv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint64_t* p_empty = bars + 18;     // [1] 8 warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
+  for (int i = threadIdx.x; i < WD_BYTES / 16; i += MT_THREADS) reinterpret_cast<uint4*>(sWd)[i] = make_uint4(0, 0, 0, 0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmWe);
-    tma_prefetch_desc(&tmWd);
     tma_prefetch_desc(&tmWp);
     mbar_init(x_full, 1);
     mbar_init(x_empty, 1);
@@ -228,9 +232,8 @@ mbconv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           uint8_t* st = sW + wr.i * w_stage;
           mbar_arrive_expect_tx(&w_full[wr.i], (uint32_t)w_stage);
           for (int kc = 0; kc < a.kcn; ++kc) tma_load_3d(st + kc * 8192, &tmWe, &w_full[wr.i], kc * 64, 0, c * 64);
-          tma_load_3d(st + a.we_bytes, &tmWd, &w_full[wr.i], 0, 0, c * 144);
           for (int j = 0; j < a.n_proj; ++j)
-            tma_load_3d(st + a.we_bytes + WD_BYTES + j * a.proj_n * 128, &tmWp, &w_full[wr.i], c * 64, 0, j * a.proj_n);
+            tma_load_3d(st + a.we_bytes + j * a.proj_n * 128, &tmWp, &w_full[wr.i], c * 64, 0, j * a.proj_n);
         }
         __syncwarp();
         wr.next(a.nws);
@@ -246,9 +249,9 @@ mbconv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const uint32_t e_lo0 = (uint32_t)umma_desc_k128(smem_u32(sE));
     const uint32_t d_lo0 = (uint32_t)umma_desc_k128(smem_u32(sD));
     const uint32_t w_lo0 = (uint32_t)umma_desc_k128(smem_u32(sW));
+    const uint32_t wd_lo0 = (uint32_t)umma_desc_k128(smem_u32(sWd));
     const uint32_t x_chunk16 = (uint32_t)a.x_chunk_stride >> 4;
     const uint32_t w_stage16 = (uint32_t)w_stage >> 4, we16 = (uint32_t)a.we_bytes >> 4;
-    const uint32_t wd16 = (uint32_t)WD_BYTES >> 4;
     uint32_t tph = 0, uph = 0;                       // tile phase, unit phase (es_full / dwa_empty flip every chunk)
     RingT we_r = {0, 0u}, e_r = {0, 0u};            // expand side (runs one chunk ahead)
     RingT wc_r = {0, 0u}, d_r = {0, 0u};            // depthwise / project side
@@ -285,7 +288,7 @@ mbconv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       tc_fence_after();
       if (elect_one()) {
         const int ks = (min(64, a.Ce - c * 64) + 15) >> 4;      // 16-channel groups that exist in this chunk
-        const uint32_t bl0 = w_lo0 + (uint32_t)wc_r.i * w_stage16 + we16;
+        const uint32_t bl0 = wd_lo0;
 #pragma unroll
         for (int dh = 0; dh < 3; ++dh)
 #pragma unroll
@@ -310,7 +313,7 @@ mbconv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       if (elect_one()) {
         const int ks = (min(64, a.Ce - c * 64) + 15) >> 4;
         const uint32_t al = d_lo0 + (uint32_t)d_r.i * (16384u >> 4);
-        const uint32_t bl = w_lo0 + (uint32_t)wc_r.i * w_stage16 + we16 + wd16;
+        const uint32_t bl = w_lo0 + (uint32_t)wc_r.i * w_stage16 + we16;
         for (int j = 0; j < a.n_proj; ++j)
           for (int k = 0; k < ks; ++k)
             umma_bf16_lohi(tmem_base + pcol0 + (uint32_t)(j * a.proj_n), al + 2u * k,
@@ -348,6 +351,18 @@ mbconv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       const int bb = t / a.tiles_h;
       for (int c = 0; c < nc; ++c, uph ^= 1u) {
         float bias[32];
+        // ---- diagonal entries of this chunk's 9 depthwise B tiles (the previous chunk's depthwise MMAs are complete:
+        // every thread passed dw_done before its last D hand-off) ----
+        {
+          const int ct = threadIdx.x - 64;
+          const int cstride = a.ce_chunks * 64;
+          for (int idx = ct; idx < 9 * 64; idx += MT_CWARPS * 32) {
+            const int tap = idx >> 6, ch = idx & 63;
+            const int row = ch & 15, j = ch >> 3;
+            const __nv_bfloat16 v = __float2bfloat16_rn(__ldg(a.w_dw + tap * cstride + c * 64 + ch));
+            *reinterpret_cast<__nv_bfloat16*>(sWd + tap * 2048 + row * 128 + ((j ^ (row & 7)) << 4) + (ch & 7) * 2) = v;
+          }
+        }
         // ---- accumulator E -> smem E (zero outside the image: the depthwise conv pads the EXPANDED tensor) ----
         load_bias32(a.b_exp + c * 64 + half * 32, bias);
         mt_wait(&e_full[e_r.i], e_r.ph, 30);
@@ -450,8 +465,7 @@ mbconv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 }
 
 template <int S, int TH>
-int launch_mt(MtArgs a, const void* x, const void* w_exp, const void* w_dwd, const void* w_proj, int flags,
-              cudaStream_t st) {
+int launch_mt(MtArgs a, const void* x, const void* w_exp, const void* w_proj, int flags, cudaStream_t st) {
   using G = GeoT<S, TH>;
   a.x_bytes = G::NHALO * 128;
   a.x_chunk_stride = (a.x_bytes + 1023) / 1024 * 1024;
@@ -462,8 +476,8 @@ int launch_mt(MtArgs a, const void* x, const void* w_exp, const void* w_dwd, con
   a.total_tiles = (int)tiles;
 
   const int cap = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
-  const int stage = a.we_bytes + WD_BYTES + a.wp_bytes;
-  auto smem_for = [&](int nd, int nw) { return a.kcn * a.x_chunk_stride + G::E_BYTES + nd * 16384 + nw * stage; };
+  const int stage = a.we_bytes + a.wp_bytes;
+  auto smem_for = [&](int nd, int nw) { return a.kcn * a.x_chunk_stride + G::E_BYTES + nd * 16384 + WD_BYTES + nw * stage; };
   // two CTAs per SM when both fit (<= 256 TMEM columns, half the shared memory): one CTA's accumulator hand-offs
   // overlap the other's MMAs
   const int half_cap = cap / 2 - 1024;
@@ -498,7 +512,7 @@ int launch_mt(MtArgs a, const void* x, const void* w_exp, const void* w_dwd, con
   if (a.tmem_cols > 256 || smem > cap / 2) per_sm = 1;
   if (per_sm == 1 && smem < 116 * 1024) smem = 116 * 1024;      // a >256-column CTA must own the SM
 
-  CUtensorMap tmX, tmWe, tmWd, tmWp;
+  CUtensorMap tmX, tmWe, tmWp;
   {
     uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
     uint64_t str[3] = {(uint64_t)a.Cin * 2, (uint64_t)a.Cin * 2 * a.W, (uint64_t)a.Cin * 2 * a.W * a.H};
@@ -511,13 +525,6 @@ int launch_mt(MtArgs a, const void* x, const void* w_exp, const void* w_dwd, con
     uint64_t str[2] = {(uint64_t)a.Cin * 2, (uint64_t)a.Cin * 2};
     uint32_t box[3] = {64, 1, 64};
     int rc = make_tmap_bf16(&tmWe, w_exp, 3, dims, str, box, 1, nullptr);
-    if (rc) return rc;
-  }
-  {
-    uint64_t dims[3] = {64, 1, (uint64_t)a.ce_chunks * 144};
-    uint64_t str[2] = {128, 128};
-    uint32_t box[3] = {64, 1, 144};
-    int rc = make_tmap_bf16(&tmWd, w_dwd, 3, dims, str, box, 1, nullptr);
     if (rc) return rc;
   }
   {
@@ -539,9 +546,9 @@ int launch_mt(MtArgs a, const void* x, const void* w_exp, const void* w_dwd, con
   if ((flags >> 8) & 0xff) grid = (long long)((flags >> 8) & 0xff) * 4;
   if (grid > a.total_tiles) grid = a.total_tiles;
   if (per_sm == 2)
-    mbconv_tc_kernel<2, S, TH><<<(unsigned)grid, MT_THREADS, (size_t)smem, st>>>(tmX, tmWe, tmWd, tmWp, a);
+    mbconv_tc_kernel<2, S, TH><<<(unsigned)grid, MT_THREADS, (size_t)smem, st>>>(tmX, tmWe, tmWp, a);
   else
-    mbconv_tc_kernel<1, S, TH><<<(unsigned)grid, MT_THREADS, (size_t)smem, st>>>(tmX, tmWe, tmWd, tmWp, a);
+    mbconv_tc_kernel<1, S, TH><<<(unsigned)grid, MT_THREADS, (size_t)smem, st>>>(tmX, tmWe, tmWp, a);
   return check_launch("mbconv_tc");
 }
 
@@ -553,11 +560,11 @@ using namespace b200;
 
 // flags: bits 0-1 expand accumulator buffers (0 = auto), bits 2-3 D buffers, bits 4-5 weight stages,
 //        bits 6-7 CTAs per SM (1 = force one), bits 8-15 grid/4, bits 16-17 tile rows (1 = 7, 2 = 4)
-extern "C" int b200seg_mbconv_tc(const void* x, const void* w_exp, const float* b_exp, const void* w_dwdiag,
+extern "C" int b200seg_mbconv_tc(const void* x, const void* w_exp, const float* b_exp, const float* w_dw,
                                  const float* b_dw, const void* w_proj, const float* b_proj, int residual, void* y,
                                  int B, int H, int W, int Cin, int Ce, int Cout, int stride, int flags,
                                  b200seg_stream_t s) {
-  B200_REQUIRE(x && w_exp && b_exp && w_dwdiag && b_dw && w_proj && b_proj && y, "mbconv_tc: null pointer");
+  B200_REQUIRE(x && w_exp && b_exp && w_dw && b_dw && w_proj && b_proj && y, "mbconv_tc: null pointer");
   B200_REQUIRE(B > 0 && H > 0 && W > 0, "mbconv_tc: empty tensor");
   B200_REQUIRE(stride == 1 || stride == 2, "mbconv_tc: stride=%d (1 or 2)", stride);
   B200_REQUIRE(Cin > 0 && Cin % 8 == 0 && Cin <= 192, "mbconv_tc: Cin=%d must be a multiple of 8, <= 192", Cin);
@@ -566,7 +573,7 @@ extern "C" int b200seg_mbconv_tc(const void* x, const void* w_exp, const float* 
   B200_REQUIRE(!residual || (stride == 1 && Cin == Cout), "mbconv_tc: residual needs stride 1 and Cin == Cout");
   MtArgs a;
   a.x = (const __nv_bfloat16*)x; a.y = (__nv_bfloat16*)y;
-  a.b_exp = b_exp; a.b_dw = b_dw; a.b_proj = b_proj;
+  a.b_exp = b_exp; a.w_dw = w_dw; a.b_dw = b_dw; a.b_proj = b_proj;
   a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Ce = Ce; a.Cout = Cout; a.residual = residual;
   a.Ho = (H - 1) / stride + 1; a.Wo = (W - 1) / stride + 1;          // k=3, pad=1
   a.kcn = (Cin + 63) / 64;
@@ -582,8 +589,8 @@ extern "C" int b200seg_mbconv_tc(const void* x, const void* w_exp, const float* 
   if (stride == 2 && a.kcn > 1) th = 4;                 // the 15x33 halo tile of a 7-row stride-2 tile x 2 chunks does not fit
   if ((flags >> 16) & 3) th = ((flags >> 16) & 3) == 1 ? 7 : 4;
   cudaStream_t st = (cudaStream_t)s;
-  if (stride == 1) return th == 7 ? launch_mt<1, 7>(a, x, w_exp, w_dwdiag, w_proj, flags, st)
-                                  : launch_mt<1, 4>(a, x, w_exp, w_dwdiag, w_proj, flags, st);
-  return th == 7 ? launch_mt<2, 7>(a, x, w_exp, w_dwdiag, w_proj, flags, st)
-                 : launch_mt<2, 4>(a, x, w_exp, w_dwdiag, w_proj, flags, st);
+  if (stride == 1) return th == 7 ? launch_mt<1, 7>(a, x, w_exp, w_proj, flags, st)
+                                  : launch_mt<1, 4>(a, x, w_exp, w_proj, flags, st);
+  return th == 7 ? launch_mt<2, 7>(a, x, w_exp, w_proj, flags, st)
+                 : launch_mt<2, 4>(a, x, w_exp, w_proj, flags, st);
 }

@@ -49,7 +49,7 @@ def _run(x, we, be, wd, bd, wp, bp, stride, residual, flags=0):
 
 
 def _run_tc(x, we, be, wd, bd, wp, bp, stride, residual, flags=0):
-    return ops.mbconv_tc(x, we, ops.pad_channels(be, 64), ops.pack_dw_diag16(wd), ops.pad_channels(bd, 64), wp,
+    return ops.mbconv_tc(x, we, ops.pad_channels(be, 64), ops.pad_channels(wd, 64), ops.pad_channels(bd, 64), wp,
                          ops.pad_channels(bp, 16), stride, residual, flags=flags)
 
 

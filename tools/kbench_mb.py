@@ -65,13 +65,12 @@ for name, H, W, Cin, Ce, Cout, st in BLOCKS:
     tot_u += us_u
     io_bytes = (x.numel() + y.numel()) * 2
     line = f"{name:4s} {Cin:3d}->{Ce:3d}->{Cout:3d} s{st} @{H}x{W}  unfused {us_u:7.1f} us |"
-    wdd = ops.pack_dw_diag16(wd)
     for f in FLAGS:
         try:
             if os.environ.get("KB_CUDA_DW"):
                 us_f = timeit(lambda: ops.mbconv(x, we, pe, pwd, pbd, wp, pbp, st, res, out=y2, flags=f))
             else:
-                us_f = timeit(lambda: ops.mbconv_tc(x, we, pe, wdd, pbd, wp, pbp, st, res, out=y2, flags=f))
+                us_f = timeit(lambda: ops.mbconv_tc(x, we, pe, pwd, pbd, wp, pbp, st, res, out=y2, flags=f))
         except RuntimeError:
             line += f"  fused[{f:#x}]     n/a (does not fit)          "
             continue
