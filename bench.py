@@ -61,25 +61,30 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line).
+
+    Sampled in-process through NVML (pynvml: two light calls every 20 ms from a background thread).  The nvidia-smi CLI
+    is only the fallback: measured on this pool, each of its queries stalls kernel submission for ~8 ms (and its first
+    start on a fresh box for 25-30 ms), which inflated a 52 ms timed region from 2.62 to 3.0-4.3 ms/step."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index, self.first = [], None, index, 0
-
-    def mark(self):
-        """Start of the timed region: only samples taken from here on are reported.  nvidia-smi is started at process start
-        and we WAIT here until it has delivered its first sample: on a fresh box its first start (binary paged in from the
-        image, NVML initialisation) takes seconds and stalls kernel launches for tens of milliseconds while it lasts --
-        measured: the first bench on a box read 3.7-4.3 ms/step instead of 2.62 when that overlapped the timed region."""
-        if self.proc is not None:
-            t0 = time.time()
-            while not self.rows and time.time() - t0 < 20.0 and self.proc.poll() is None:
-                time.sleep(0.05)
-        self.first = len(self.rows)
+        self.nvml, self.handle, self.stop_flag, self.thread, self.max_mhz = None, None, False, None, None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:                                   # noqa: BLE001 -- no NVML binding: nvidia-smi CLI
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -88,15 +93,42 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll_nvml(self):
+        n = self.nvml
+        names = (("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", n.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksEventReasonSwPowerCap))
+        while not self.stop_flag:
+            try:
+                mhz = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                self.rows.append([str(mhz), str(self.max_mhz)] + [("Active" if mask & bit else "Not Active") for _, bit in names])
+            except Exception:                               # noqa: BLE001
+                pass
+            time.sleep(0.02)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def mark(self):
+        """Start of the timed region: only samples taken from here on are reported.  The sampler is started at process
+        start and we WAIT here until it has delivered its first sample (the nvidia-smi fallback needs seconds on a fresh
+        box)."""
+        if self.nvml is not None or self.proc is not None:
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 20.0 and (self.nvml is not None or self.proc.poll() is None):
+                time.sleep(0.05)
+        self.first = len(self.rows)
+
     def stop(self):
-        if self.proc is None:
+        if self.nvml is None and self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self.nvml is not None:
+            time.sleep(0.03)
+            self.stop_flag = True
+        else:
+            time.sleep(0.15)
+            self.proc.terminate()
         sm, mx, reasons = [], None, set()
         for r in (self.rows[self.first:] or self.rows):
             try:
@@ -107,7 +139,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def cpu_reference_leg(seconds=12.0, warmup=2, fixed_iters=None):
