@@ -105,12 +105,6 @@ int b200seg_mbconv(const void* x, const void* w_exp, const float* b_exp, const f
                    const void* w_proj, const float* b_proj, int residual, void* y, int B, int H, int W, int Cin,
                    int Ce, int Cout, int stride, int flags, b200seg_stream_t s);
 
-/* Same block and the same operands, depthwise stencil on the tensor cores as well (9 taps x diagonal 16x16 weight
- * blocks, written into shared memory by the kernel from w_dw, rounded to bf16; see csrc/mbconv_tc.cu). */
-int b200seg_mbconv_tc(const void* x, const void* w_exp, const float* b_exp, const float* w_dw, const float* b_dw,
-                      const void* w_proj, const float* b_proj, int residual, void* y, int B, int H, int W, int Cin,
-                      int Ce, int Cout, int stride, int flags, b200seg_stream_t s);
-
 /* NHWC [B,H,W,ldc] (first C valid) -> NCHW [B,C,H,W] (UNet returns logits at input resolution). */
 int b200seg_nhwc_to_nchw(const void* x, int dtype, int ldc, void* out, int out_dtype, int B, int H, int W,
                          int C, b200seg_stream_t s);
@@ -119,11 +113,27 @@ int b200seg_nhwc_to_nchw(const void* x, int dtype, int ldc, void* out, int out_d
 int b200seg_maxpool2x2(const void* x, void* y, int dtype, int B, int H, int W, int C, b200seg_stream_t s);
 
 /* nn.CrossEntropyLoss() forward fused with its gradient (main.py:99, train.py:37-38):
- *   logits NCHW f32 [B,C,H,W], target int64 [B,H,W] in [0,C) (or ignore_index = -100)
- *   loss_sum : f32[1], accumulates sum of -log softmax[target] (caller zeroes, divides by count)
- *   dlogits  : NCHW f32 (softmax - onehot) * grad_scale, or NULL for forward only. */
+ *   logits NCHW f32 [B,C,H,W] (any C >= 1), target int64 [B,H,W] in [0,C) or ignore_index
+ *   loss_sum : f32[1], accumulates sum of -log softmax[target] over the non-ignored pixels (caller zeroes)
+ *   dlogits  : NCHW f32 (softmax - onehot) * grad_scale / counts[0], or NULL for forward only
+ *   counts   : device f32[2] from b200seg_ce_count (counts[0] = non-ignored targets: the divisor of the 'mean'
+ *              reduction), or NULL: dlogits is scaled by grad_scale alone. */
 int b200seg_softmax_ce(const float* logits, const int64_t* target, float* loss_sum, float* dlogits,
-                       float grad_scale, int B, int C, int H, int W, b200seg_stream_t s);
+                       float grad_scale, const float* counts, int B, int C, int H, int W, b200seg_stream_t s);
+/* counts[0] += number of targets in [0,C); counts[1] += number of targets that are neither in range nor ignore_index
+ * (torch raises on those; the Python binding turns a non-zero counts[1] into a NaN loss). Caller zeroes counts. */
+int b200seg_ce_count(const int64_t* target, float* counts, long long N, int C, long long ignore_index,
+                     b200seg_stream_t s);
+
+/* Any class count (outconv(in_ch, out_ch), unet.py:108-121, takes any out_ch; the fast kernels above hold <= 16
+ * channels in registers): final_upsample to NCHW logits (mask == NULL) or to the uint8 argmax mask (out == NULL) from
+ * NHWC logits with pixel pitch ldc >= C; its adjoint (dlogits NHWC [B,h,w,ldc], channels >= C zeroed); and the argmax
+ * of NHWC logits at input resolution (plain UNet has no final upsample; inference.py:64). */
+int b200seg_upsample2x_ac_generic(const void* logits, int dtype, int ldc, void* out, int out_dtype, uint8_t* mask, int B,
+                                  int h, int w, int C, b200seg_stream_t s);
+int b200seg_final_bwd_generic(const float* dout, void* dlogits, int dtype, int B, int h, int w, int C, int ldc,
+                              b200seg_stream_t s);
+int b200seg_nhwc_argmax(const void* x, int dtype, int ldc, uint8_t* mask, long long P, int C, b200seg_stream_t s);
 
 /* ---------------------------------------------------------------------------------------------
  * Training path (train.py:35-39: model.train() forward, loss.backward()).  Activations NHWC viewed as
@@ -206,6 +216,15 @@ int b200seg_adam_chunk(void);
 int b200seg_pack_weights_multi(const void* table, const int* chunk_tensor, const int* chunk_index, int n_chunks,
                                b200seg_stream_t s);
 int b200seg_pack_chunk(void);
+/* Gradient finalize (loss.backward() -> p.grad, train.py:38): every parameter gradient of one bucket from the backward
+ * kernels' staging layouts into the parameters' own layout inside the flat gradient arena, one launch, pre-scaled (1/world
+ * for the data-parallel mean).  table: device array of {float* dst; const void* src; long long n; long long slot_stride;
+ * int kind, cout, cin, kk, nslot, pad; float scale; int pad;} (64 bytes).  kind 0: f64 slot sums -> f32 [n]; 1: dense f32
+ * [cout_pad][kk][cin] -> OIHW; 2: stem f32 [kk][cin][cout] -> OIHW; 3: depthwise f64 slot sums [kk][C] -> [C][kk].  Block b
+ * handles elements [chunk_index[b]*CHUNK, +CHUNK) of tensor chunk_tensor[b], CHUNK = b200seg_grad_chunk(). */
+int b200seg_grad_finalize_multi(const void* table, const int* chunk_tensor, const int* chunk_index, int n_chunks,
+                                b200seg_stream_t s);
+int b200seg_grad_chunk(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Frame pre-processing of inference.py:28-46 for a batch: uint8 HWC BGR frames [B,Hs,Ws,3] ->
@@ -215,10 +234,6 @@ int b200seg_pack_chunk(void);
 int b200seg_preprocess_u8(const uint8_t* frames, int B, int Hs, int Ws, void* out, int out_dtype, uint8_t* rgb, int H,
                           int W, float mean0, float mean1, float mean2, float std0, float std1, float std2,
                           b200seg_stream_t s);
-
-/* Diagnostic (not on the product path): cycles for `iters` back-to-back tcgen05.mma kind::f16 of shape M x N x 16 issued
- * by one thread per CTA, `ctas_per_sm` CTAs resident per SM; cycles_out[cta] (device, long long). tools/mma_probe.py. */
-int b200seg_probe_mma(int M, int N, int iters, int ctas_per_sm, long long* cycles_out, b200seg_stream_t s);
 
 #ifdef __cplusplus
 }

@@ -312,3 +312,66 @@ def calibrate_bn(sd: Dict[str, Tensor], x: Tensor, forward=None) -> Dict[str, Te
 
 def bn_stat_keys(sd) -> List[str]:
     return [k for k in sd if k.endswith("running_mean") or k.endswith("running_var")]
+
+
+# --------------------------------------------------------------------------------------
+# Fixture F2: a TRAINED network.  The road-scene generator below is what the live
+# reference is trained on by oracle/make_golden_f2.py; the weights it ends with are committed
+# (int8 per output channel, see f2_state_dict) so that every box evaluates the same network.
+# --------------------------------------------------------------------------------------
+ROAD_PALETTE = [(0.45, 0.65, 0.95), (0.30, 0.30, 0.32), (0.85, 0.15, 0.15), (0.15, 0.75, 0.20), (0.95, 0.85, 0.10),
+                (0.55, 0.25, 0.70), (0.95, 0.55, 0.10), (0.10, 0.80, 0.80), (0.90, 0.90, 0.90), (0.05, 0.05, 0.05)]
+ROAD_MEAN, ROAD_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)       # inference.py:36-37
+
+
+def road_scene_batch(b: int, h: int, w: int, seed: int = 0, noise: float = 0.15) -> Tuple[Tensor, Tensor]:
+    """Synthetic 10-class road scene: class 0 on the top half, class 1 (road) on the bottom half, six
+    random rectangles of classes 2..9 per image; the image is the class palette colour + N(0, noise^2), normalised
+    with the ImageNet statistics the reference uses.  numpy PCG64 streams: identical on every machine."""
+    import numpy as np
+    rng = np.random.default_rng(770000 + seed)
+    t = np.zeros((b, h, w), dtype=np.int64)
+    t[:, h // 2:, :] = 1
+    for i in range(b):
+        for _ in range(6):
+            c = int(rng.integers(2, 10))
+            y0, x0 = int(rng.integers(0, h - 4)), int(rng.integers(0, w - 4))
+            hh, ww = int(rng.integers(4, max(5, h // 3))), int(rng.integers(4, max(5, w // 3)))
+            t[i, y0:y0 + hh, x0:x0 + ww] = c
+    pal = np.asarray(ROAD_PALETTE, dtype=np.float32)
+    img = pal[t] + rng.standard_normal((b, h, w, 3), dtype=np.float32) * np.float32(noise)
+    img = (img - np.asarray(ROAD_MEAN, np.float32)) / np.asarray(ROAD_STD, np.float32)
+    return torch.from_numpy(np.ascontiguousarray(img.transpose(0, 3, 1, 2))), torch.from_numpy(t)
+
+
+def f2_quantize(sd: Dict[str, Tensor]) -> Dict[str, "object"]:
+    """Trained state_dict -> committed form: conv/linear weights as int8 with one f32 scale per output channel,
+    everything else (BN vectors, biases, running stats) as f32.  f2_state_dict() inverts it exactly."""
+    import numpy as np
+    out = {}
+    for k, v in sd.items():
+        if v.dim() == 4 and v.is_floating_point():
+            w = v.detach().float()
+            s = w.abs().amax(dim=(1, 2, 3)).clamp_min(1e-12) / 127.0
+            q = torch.round(w / s[:, None, None, None]).clamp_(-127, 127).to(torch.int8)
+            out["q:" + k] = q.numpy()
+            out["s:" + k] = s.numpy()
+        elif v.is_floating_point():
+            out["f:" + k] = v.detach().float().numpy()
+        else:
+            out["i:" + k] = v.detach().numpy()
+    return out
+
+
+def f2_state_dict(blob) -> Dict[str, Tensor]:
+    """The F2 network every box evaluates: W = scale[o] * int8 (one exact f32 product per element)."""
+    import numpy as np
+    sd: Dict[str, Tensor] = {}
+    for key in blob.files if hasattr(blob, "files") else blob.keys():
+        kind, name = key[:2], key[2:]
+        arr = torch.from_numpy(np.ascontiguousarray(blob[key]))
+        if kind == "q:":
+            sd[name] = arr.float() * torch.from_numpy(np.ascontiguousarray(blob["s:" + name]))[:, None, None, None]
+        elif kind in ("f:", "i:"):
+            sd[name] = arr
+    return sd

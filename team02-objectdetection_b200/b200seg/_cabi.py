@@ -27,14 +27,17 @@ _PROTOS = {
     "b200seg_conv_tc": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "b200seg_dwconv3x3_tc": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "b200seg_mbconv": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
-    "b200seg_mbconv_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "b200seg_conv_simt": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "b200seg_upsample2x_concat": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "b200seg_upsample2x_ac_nchw": [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp],
     "b200seg_upsample2x_ac_argmax": [_vp, _i, _i, _vp, _i, _i, _i, _i, _vp],
     "b200seg_nhwc_to_nchw": [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp],
     "b200seg_maxpool2x2": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
-    "b200seg_softmax_ce": [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _vp],
+    "b200seg_softmax_ce": [_vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _vp],
+    "b200seg_ce_count": [_vp, _vp, _ll, _i, _ll, _vp],
+    "b200seg_upsample2x_ac_generic": [_vp, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp],
+    "b200seg_final_bwd_generic": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "b200seg_nhwc_argmax": [_vp, _i, _i, _vp, _ll, _i, _vp],
     # training path
     "b200seg_bn_stats": [_vp, _i, _ll, _i, _vp, _vp, _i, _ll, _vp],
     "b200seg_bn_finalize": [_vp, _i, _vp, _vp, _i, _ll, _ll, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
@@ -53,11 +56,12 @@ _PROTOS = {
     "b200seg_final_bwd": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "b200seg_nchw_to_nhwc_pad": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "b200seg_preprocess_u8": [_vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _f, _f, _f, _f, _f, _f, _vp],
-    "b200seg_probe_mma": [_i, _i, _i, _i, _vp, _vp],
     "b200seg_adam_multi": [_vp, _vp, _vp, _i, _f, _d, _f, _d, _f, _f, _d, _d, _vp],
     "b200seg_adam_chunk": [],
     "b200seg_pack_weights_multi": [_vp, _vp, _vp, _i, _vp],
     "b200seg_pack_chunk": [],
+    "b200seg_grad_finalize_multi": [_vp, _vp, _vp, _i, _vp],
+    "b200seg_grad_chunk": [],
     "b200seg_maxpool_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
 }
 EXPORTS = sorted(list(_PROTOS) + ["b200seg_last_error"])

@@ -51,8 +51,9 @@ def _double_conv_steps(prefix: str, dc, src: str, dst: str) -> List[Step]:
 
 def _outconv_steps(prefix: str, oc, src: str, dst: str) -> List[Step]:
     seq = oc.conv
+    ncls = seq[3].weight.shape[0]            # logits are stored NHWC with the class axis padded to a multiple of 16
     return [Step("dense", f"{prefix}.conv.0", src, dst + ".a", seq[0], seq[1], ACT_RELU, taps=1),
-            Step("dense", f"{prefix}.conv.3", dst + ".a", dst, seq[3], None, ACT_NONE, taps=1, pad_cout=16)]
+            Step("dense", f"{prefix}.conv.3", dst + ".a", dst, seq[3], None, ACT_NONE, taps=1, pad_cout=(ncls + 15) // 16 * 16)]
 
 
 def build_steps_mbv2unet(model) -> List[Step]:
@@ -128,8 +129,8 @@ class Engine:
         self.graph_after = 2              # eager calls per (shape, weights) before capturing
         self.divisor = 32 if arch == "mbv2unet" else 8
         self.out_ch = model.output_channels
-        if self.out_ch > 16:
-            raise NotImplementedError("b200seg: output_channels > 16 is not supported by the final-upsample kernel")
+        self.dp = None                    # data parallel: set by b200seg.dp.attach() (group, bucket size)
+        self._train_ws = None             # gradient arena + staging (train_path.TrainWorkspace)
 
     # ------------------------------------------------------------------ weights
     def _version_key(self, mode: str):
@@ -139,7 +140,9 @@ class Engine:
         for t in self.model.buffers():
             v += t._version
         p0 = next(self.model.parameters())
-        return (mode, self.dense_impl, v, p0.device, p0.data_ptr())
+        # ops.mutation_epoch: bumped by everything that writes parameters / BN buffers through raw pointers (b200seg.Adam,
+        # the training forward and its CUDA-graph replays) -- those writes do not touch tensor._version
+        return (mode, self.dense_impl, v, ops.mutation_epoch(), p0.device, p0.data_ptr())
 
     def _pack_eval(self, mode: str):
         key = self._version_key(mode)
@@ -286,8 +289,9 @@ class Engine:
                 env[s.dst] = ops.upsample2x_ac_nchw(env[s.src], self.out_ch, out_dtype)
         elif s.op == "to_nchw":
             if want_mask:
-                raise NotImplementedError("predict_mask is implemented for MobileNetV2UNet")
-            env[s.dst] = ops.nhwc_to_nchw(env[s.src], self.out_ch, out_dtype)
+                env[s.dst] = ops.nhwc_argmax(env[s.src], self.out_ch)
+            else:
+                env[s.dst] = ops.nhwc_to_nchw(env[s.src], self.out_ch, out_dtype)
         else:  # pragma: no cover
             raise AssertionError(s.op)
 
@@ -404,9 +408,12 @@ class Engine:
 
     # ------------------------------------------------------------------ dispatch
     def forward(self, x: torch.Tensor, want_mask: bool = False):
-        if self.model.training:
-            if want_mask:
-                raise RuntimeError("predict_mask needs model.eval()")
-            from . import train_path
-            return train_path.forward_train(self, x)
-        return self.forward_eval(x, want_mask)
+        # every kernel is launched on the current stream of the CURRENT device: make the input's device current for the
+        # whole call (model.to("cuda:1") while cuda:0 is current must work like any nn.Module)
+        with torch.cuda.device(x.device):
+            if self.model.training:
+                if want_mask:
+                    raise RuntimeError("predict_mask needs model.eval()")
+                from . import train_path
+                return train_path.forward_train(self, x)
+            return self.forward_eval(x, want_mask)

@@ -36,6 +36,21 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+_MUTATION_EPOCH = 0
+
+
+def mutation_epoch() -> int:
+    return _MUTATION_EPOCH
+
+
+def bump_mutation_epoch() -> None:
+    """Called by every code path that writes parameters or BatchNorm buffers through raw device pointers (fused Adam,
+    the training forward, CUDA-graph replays of it): tensor._version does not see those writes, and the eval-mode
+    packed-weight cache must."""
+    global _MUTATION_EPOCH
+    _MUTATION_EPOCH += 1
+
+
 def conv3x3_smallcin(x_nchw, w, b, stride: int, act: int, out_dtype, out=None):
     """x NCHW [B,Cin<=4,H,W]; w f32 [3,3,Cin,Cout]; -> NHWC [B,Ho,Wo,Cout]."""
     _cuda(x_nchw, w, b)
@@ -151,28 +166,6 @@ def mbconv(x, w_exp, b_exp, w_dw, b_dw, w_proj, b_proj, stride: int, residual: b
     return out
 
 
-def mbconv_tc(x, w_exp, b_exp, w_dw, b_dw, w_proj, b_proj, stride: int, residual: bool, out=None, flags: int = 0):
-    """Fused inverted-residual block with the depthwise stencil on the tensor cores; same operands as mbconv (the
-    depthwise taps are rounded to bf16 inside the kernel)."""
-    _cuda(x, w_exp, b_exp, w_dw, b_dw, w_proj, b_proj)
-    if x.dtype != torch.bfloat16 or w_exp.dtype != torch.bfloat16 or w_proj.dtype != torch.bfloat16:
-        raise TypeError("mbconv_tc is bf16-only")
-    B, H, W, Cin = x.shape
-    Ce, Cout = w_exp.shape[0], w_proj.shape[0]
-    cep, cop = (Ce + 63) // 64 * 64, (Cout + 15) // 16 * 16
-    if (tuple(w_exp.shape) != (Ce, Cin) or tuple(w_proj.shape) != (Cout, Ce) or tuple(w_dw.shape) != (9, cep)
-            or w_dw.dtype != torch.float32 or b_exp.numel() != cep or b_dw.numel() != cep or b_proj.numel() != cop):
-        raise ValueError(f"mbconv_tc: operand shapes w_exp {tuple(w_exp.shape)} w_dw {tuple(w_dw.shape)} "
-                         f"w_proj {tuple(w_proj.shape)} b {b_exp.numel()},{b_dw.numel()},{b_proj.numel()}")
-    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
-    if out is None:
-        out = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=torch.bfloat16)
-    check(lib.b200seg_mbconv_tc(ptr(x), ptr(w_exp), ptr(b_exp), ptr(w_dw), ptr(b_dw), ptr(w_proj), ptr(b_proj),
-                                1 if residual else 0, ptr(out), B, H, W, Cin, Ce, Cout, stride, flags, _stream()),
-          "mbconv_tc")
-    return out
-
-
 def upsample2x_concat(skip, x, out=None):
     """cat([skip, bilinear_x2(x, align_corners=False)], channel) in NHWC."""
     _cuda(skip, x)
@@ -193,6 +186,10 @@ def upsample2x_ac_nchw(logits, C: int, out_dtype, out=None):
     B, h, w, ldc = logits.shape
     if out is None:
         out = torch.empty((B, C, 2 * h, 2 * w), device=logits.device, dtype=out_dtype)
+    if ldc != 16:           # more than 16 classes: generic kernel (csrc/generic_ops.cu)
+        check(lib.b200seg_upsample2x_ac_generic(ptr(logits), _dt(logits), ldc, ptr(out), _dt(out), None, B, h, w, C,
+                                                _stream()), "upsample2x_ac_generic")
+        return out
     check(lib.b200seg_upsample2x_ac_nchw(ptr(logits), _dt(logits), ldc, ptr(out), _dt(out), B, h, w, C, _stream()),
           "upsample2x_ac_nchw")
     return out
@@ -203,6 +200,10 @@ def upsample2x_ac_argmax(logits, C: int, out=None):
     B, h, w, ldc = logits.shape
     if out is None:
         out = torch.empty((B, 2 * h, 2 * w), device=logits.device, dtype=torch.uint8)
+    if ldc != 16:
+        check(lib.b200seg_upsample2x_ac_generic(ptr(logits), _dt(logits), ldc, None, F32, ptr(out), B, h, w, C,
+                                                _stream()), "upsample2x_ac_generic")
+        return out
     check(lib.b200seg_upsample2x_ac_argmax(ptr(logits), _dt(logits), ldc, ptr(out), B, h, w, C, _stream()),
           "upsample2x_ac_argmax")
     return out
@@ -217,6 +218,16 @@ def nhwc_to_nchw(x, C: int, out_dtype, out=None):
     return out
 
 
+def nhwc_argmax(x, C: int, out=None):
+    """uint8 [B,H,W] = argmax over the first C channels of NHWC x (first maximum wins, like torch.max)."""
+    _cuda(x)
+    B, H, W, ldc = x.shape
+    if out is None:
+        out = torch.empty((B, H, W), device=x.device, dtype=torch.uint8)
+    check(lib.b200seg_nhwc_argmax(ptr(x), _dt(x), ldc, ptr(out), B * H * W, C, _stream()), "nhwc_argmax")
+    return out
+
+
 def maxpool2x2(x, out=None):
     _cuda(x)
     B, H, W, Cc = x.shape
@@ -226,20 +237,30 @@ def maxpool2x2(x, out=None):
     return out
 
 
+IGNORE_INDEX = -100      # nn.CrossEntropyLoss default
+
+
 def softmax_ce(logits, target, want_grad: bool = True, grad_scale: Optional[float] = None):
-    """Fused mean cross-entropy over NCHW f32 logits and int64 targets.
-    Returns (loss scalar tensor, dlogits or None); dlogits already carries the 1/(B*H*W) factor."""
+    """Fused mean cross-entropy over NCHW f32 logits and int64 targets (nn.CrossEntropyLoss defaults: 'mean' over the
+    targets that are not ignore_index=-100).  Returns (loss scalar tensor, dlogits or None); dlogits already carries
+    the 1/n_valid factor.  A label outside [0,C) that is not ignore_index makes the loss NaN (torch asserts on the
+    device; neither may silently train on a broken label map).  ``grad_scale`` (tests): plain factor, no counting."""
     _cuda(logits, target)
     if logits.dtype != torch.float32 or target.dtype != torch.int64:
         raise TypeError("softmax_ce expects f32 logits and int64 targets")
     B, Cc, H, W = logits.shape
     n = B * H * W
-    loss_sum = torch.zeros(1, device=logits.device, dtype=torch.float32)
+    acc = torch.zeros(3, device=logits.device, dtype=torch.float32)      # [loss sum, valid targets, bad labels]
     dl = torch.empty_like(logits) if want_grad else None
-    gs = (1.0 / n) if grad_scale is None else grad_scale
-    check(lib.b200seg_softmax_ce(ptr(logits), ptr(target), ptr(loss_sum), ptr(dl), gs, B, Cc, H, W, _stream()),
+    if grad_scale is None:
+        check(lib.b200seg_ce_count(ptr(target), ptr(acc[1:]), n, Cc, IGNORE_INDEX, _stream()), "ce_count")
+        check(lib.b200seg_softmax_ce(ptr(logits), ptr(target), ptr(acc), ptr(dl), 1.0, ptr(acc[1:]), B, Cc, H, W, _stream()),
+              "softmax_ce")
+        loss = acc[0] / acc[1]                                            # 0/0 = NaN for an all-ignored batch, as torch
+        return torch.where(acc[2] > 0, torch.full_like(loss, float("nan")), loss), dl
+    check(lib.b200seg_softmax_ce(ptr(logits), ptr(target), ptr(acc), ptr(dl), grad_scale, None, B, Cc, H, W, _stream()),
           "softmax_ce")
-    return loss_sum[0] / n, dl
+    return acc[0] / n, dl
 
 
 # ------------------------------------------------------------------------------------------------
@@ -296,11 +317,13 @@ def bn_train_forward(z, gamma, beta, running_mean, running_var, eps: float, mome
     return a, sv
 
 
-def bn_train_backward(da, z, sv, act: int):
-    """Returns (dz, dgamma f32[C], dbeta f32[C])."""
+def bn_train_backward(da, z, sv, act: int, red=None):
+    """Returns (dz, dgamma f32[C], dbeta f32[C]).  ``red``: zeroed f64 staging [NSLOT, 2, C] that receives the slot sums
+    (row 0 = d beta, row 1 = d gamma; the gradient-finalize kernel reads them from there)."""
     _cuda(da, z, sv)
     C, P = z.shape[-1], _P(z)
-    red = zero_pool.take((NSLOT, 2, C), z.device)
+    if red is None:
+        red = zero_pool.take((NSLOT, 2, C), z.device)
     check(lib.b200seg_bn_bwd_reduce(ptr(da), ptr(z), ptr(sv[2]), ptr(sv[3]), ptr(sv[0]), ptr(sv[1]), _dt(z), P, C, act,
                                     ptr(red[0, 0]), ptr(red[0, 1]), NSLOT, 2 * C, _stream()), "bn_bwd_reduce")
     g32 = torch.empty(2, C, device=z.device, dtype=torch.float32)
@@ -318,10 +341,14 @@ def act_bwd(da, a_out, act: int):
     return dz
 
 
-def colsum(x):
-    """f32 [C] = sum over pixels of NHWC x."""
+def colsum(x, acc=None):
+    """f32 [C] = sum over pixels of NHWC x.  With ``acc`` (zeroed f64 staging [NSLOT, C]) only the slot sums are
+    produced (returns None)."""
     _cuda(x)
     C = x.shape[-1]
+    if acc is not None:
+        check(lib.b200seg_colsum(ptr(x), _dt(x), _P(x), C, ptr(acc), NSLOT, C, _stream()), "colsum")
+        return None
     acc = zero_pool.take((NSLOT, C), x.device)
     check(lib.b200seg_colsum(ptr(x), _dt(x), _P(x), C, ptr(acc), NSLOT, C, _stream()), "colsum")
     out = torch.empty(C, device=x.device, dtype=torch.float32)
@@ -329,24 +356,26 @@ def colsum(x):
     return out
 
 
-def conv_wgrad(x, dz, taps: int):
-    """f32 [Cout, taps*Cin] = sum_p dz[p] (outer) im2col(x)[p]."""
+def conv_wgrad(x, dz, taps: int, dw=None):
+    """f32 [Cout, taps*Cin] = sum_p dz[p] (outer) im2col(x)[p]  (``dw``: zeroed accumulator to add into)."""
     _cuda(x, dz)
     B, H, W, Cin = x.shape
     Cout = dz.shape[-1]
-    dw = zero_pool32.take((Cout, taps * Cin), x.device)
+    if dw is None:
+        dw = zero_pool32.take((Cout, taps * Cin), x.device)
     check(lib.b200seg_conv_wgrad(ptr(x), ptr(dz), ptr(dw), _dt(x), B, H, W, Cin, Cout, taps, _stream()), "conv_wgrad")
     return dw
 
 
-def conv_wgrad_tc(x, dz, taps: int):
-    """Tensor-core weight gradient: bf16 NHWC x / dz -> f32 [Cout, taps*Cin]."""
+def conv_wgrad_tc(x, dz, taps: int, dw=None):
+    """Tensor-core weight gradient: bf16 NHWC x / dz -> f32 [Cout, taps*Cin]  (``dw``: zeroed accumulator)."""
     _cuda(x, dz)
     if x.dtype != torch.bfloat16 or dz.dtype != torch.bfloat16:
         raise TypeError("conv_wgrad_tc is bf16-only")
     B, H, W, Cin = x.shape
     Cout = dz.shape[-1]
-    dw = zero_pool32.take((Cout, taps * Cin), x.device)
+    if dw is None:
+        dw = zero_pool32.take((Cout, taps * Cin), x.device)
     check(lib.b200seg_conv_wgrad_tc(ptr(x), ptr(dz), ptr(dw), B, H, W, Cin, Cout, taps, _stream()), "conv_wgrad_tc")
     return dw
 
@@ -359,10 +388,13 @@ def dw_dgrad(dz, w9c, in_shape, stride: int, acc=None):
     return dx
 
 
-def dw_wgrad(x, dz, stride: int):
-    """f32 [9, C]."""
+def dw_wgrad(x, dz, stride: int, acc=None):
+    """f32 [9, C].  With ``acc`` (zeroed f64 staging [NSLOT, 9, C]) only the slot sums are produced (returns None)."""
     _cuda(x, dz)
     B, H, W, Cc = x.shape
+    if acc is not None:
+        check(lib.b200seg_dw_wgrad(ptr(x), ptr(dz), ptr(acc), NSLOT, _dt(x), B, H, W, Cc, stride, _stream()), "dw_wgrad")
+        return None
     acc = zero_pool.take((NSLOT, 9, Cc), x.device)
     check(lib.b200seg_dw_wgrad(ptr(x), ptr(dz), ptr(acc), NSLOT, _dt(x), B, H, W, Cc, stride, _stream()), "dw_wgrad")
     out = torch.empty(9, Cc, device=x.device, dtype=torch.float32)
@@ -370,12 +402,13 @@ def dw_wgrad(x, dz, stride: int):
     return out
 
 
-def smallcin_wgrad(x_nchw, dz, stride: int):
-    """f32 [3,3,Cin,Cout]."""
+def smallcin_wgrad(x_nchw, dz, stride: int, dw=None):
+    """f32 [3,3,Cin,Cout]  (``dw``: zeroed accumulator)."""
     _cuda(x_nchw, dz)
     B, Cin, H, W = x_nchw.shape
     Cout = dz.shape[-1]
-    dw = zero_pool32.take((3, 3, Cin, Cout), dz.device)
+    if dw is None:
+        dw = zero_pool32.take((3, 3, Cin, Cout), dz.device)
     check(lib.b200seg_smallcin_wgrad(ptr(x_nchw), _dt(x_nchw), ptr(dz), _dt(dz), ptr(dw), B, Cin, H, W, Cout, stride,
                                      _stream()), "smallcin_wgrad")
     return dw
@@ -393,13 +426,17 @@ def upcat_bwd(dcat, Cs: int, acc_skip=None):
     return dskip, dx
 
 
-def final_bwd(dout_nchw, sdt):
-    """dout NCHW f32 [B,C,2h,2w] -> NHWC [B,h,w,16] of dtype sdt."""
+def final_bwd(dout_nchw, sdt, ldc: int = 16):
+    """dout NCHW f32 [B,C,2h,2w] -> NHWC [B,h,w,ldc] of dtype sdt."""
     _cuda(dout_nchw)
     if dout_nchw.dtype != torch.float32:
         raise TypeError("final_bwd expects f32 upstream gradients")
     B, Cc, H2, W2 = dout_nchw.shape
-    dl = torch.empty(B, H2 // 2, W2 // 2, 16, device=dout_nchw.device, dtype=sdt)
+    dl = torch.empty(B, H2 // 2, W2 // 2, ldc, device=dout_nchw.device, dtype=sdt)
+    if ldc != 16:
+        check(lib.b200seg_final_bwd_generic(ptr(dout_nchw), ptr(dl), _dt(dl), B, H2 // 2, W2 // 2, Cc, ldc, _stream()),
+              "final_bwd_generic")
+        return dl
     check(lib.b200seg_final_bwd(ptr(dout_nchw), ptr(dl), _dt(dl), B, H2 // 2, W2 // 2, Cc, _stream()), "final_bwd")
     return dl
 

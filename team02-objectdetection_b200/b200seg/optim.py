@@ -13,6 +13,7 @@ from typing import Dict, List
 
 import torch
 
+from . import ops
 from ._cabi import check, lib, ptr
 
 
@@ -72,35 +73,42 @@ class Adam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        ops.bump_mutation_epoch()        # parameters change through raw pointers: eval-mode weight caches are stale
         for group in self.param_groups:
             plist = [p for p in group["params"] if p.grad is not None]
             if not plist:
                 continue
-            grads = []
-            for p in plist:
-                g = p.grad
-                if not p.is_cuda or p.dtype != torch.float32 or g.dtype != torch.float32 or g.is_sparse:
-                    raise RuntimeError("b200seg.Adam updates dense CUDA float32 parameters only (no fallback)")
-                grads.append(g if g.is_contiguous() else g.contiguous())
-            plan = self._plan(plist)
-            plan["t"] += 1.0
-            torch._foreach_add_(plan["steps"], 1)
-            t = plan["t"]
-            vals = [x for (pp, mp, vp, n), g in zip(plan["static"], grads) for x in (pp, g.data_ptr(), mp, vp, n)]
-            if vals != plan.get("vals"):             # gradient buffers usually come back at the same addresses
-                r = plan["rot"] = (plan["rot"] + 1) % 4      # rotating pinned staging buffers: the host may run steps ahead
-                if plan["evs"][r] is not None:
-                    plan["evs"][r].synchronize()             # upload from 4 steps ago has left this buffer
-                plan["host"][r].numpy()[:] = vals
-                plan["dev"].copy_(plan["host"][r], non_blocking=True)
-                plan["evs"][r] = torch.cuda.Event()
-                plan["evs"][r].record()
-                plan["vals"] = vals
-            b1, b2 = group["betas"]
-            check(lib.b200seg_adam_multi(ptr(plan["dev"]), ptr(plan["ct"]), ptr(plan["ci"]), plan["n"],
-                                         ctypes.c_float(group["lr"]), ctypes.c_double(1.0 - b1), ctypes.c_float(b2), ctypes.c_double(1.0 - b2),
-                                         ctypes.c_float(group["eps"]), ctypes.c_float(group["weight_decay"]),
-                                         ctypes.c_double(1.0 - b1 ** t), ctypes.c_double(1.0 - b2 ** t),
-                                         torch.cuda.current_stream().cuda_stream), "adam_multi")
-            plan["_keep"] = grads                    # contiguous copies must outlive the asynchronous kernel
+            if not all(p.is_cuda for p in plist):
+                raise RuntimeError("b200seg.Adam updates dense CUDA float32 parameters only (no fallback)")
+            with torch.cuda.device(plist[0].device):
+                self._step_group(group, plist)
         return loss
+
+    def _step_group(self, group, plist):
+        grads = []
+        for p in plist:
+            g = p.grad
+            if not p.is_cuda or p.dtype != torch.float32 or g.dtype != torch.float32 or g.is_sparse:
+                raise RuntimeError("b200seg.Adam updates dense CUDA float32 parameters only (no fallback)")
+            grads.append(g if g.is_contiguous() else g.contiguous())
+        plan = self._plan(plist)
+        plan["t"] += 1.0
+        torch._foreach_add_(plan["steps"], 1)
+        t = plan["t"]
+        vals = [x for (pp, mp, vp, n), g in zip(plan["static"], grads) for x in (pp, g.data_ptr(), mp, vp, n)]
+        if vals != plan.get("vals"):             # gradient buffers usually come back at the same addresses
+            r = plan["rot"] = (plan["rot"] + 1) % 4      # rotating pinned staging buffers: the host may run steps ahead
+            if plan["evs"][r] is not None:
+                plan["evs"][r].synchronize()             # upload from 4 steps ago has left this buffer
+            plan["host"][r].numpy()[:] = vals
+            plan["dev"].copy_(plan["host"][r], non_blocking=True)
+            plan["evs"][r] = torch.cuda.Event()
+            plan["evs"][r].record()
+            plan["vals"] = vals
+        b1, b2 = group["betas"]
+        check(lib.b200seg_adam_multi(ptr(plan["dev"]), ptr(plan["ct"]), ptr(plan["ci"]), plan["n"],
+                                     ctypes.c_float(group["lr"]), ctypes.c_double(1.0 - b1), ctypes.c_float(b2), ctypes.c_double(1.0 - b2),
+                                     ctypes.c_float(group["eps"]), ctypes.c_float(group["weight_decay"]),
+                                     ctypes.c_double(1.0 - b1 ** t), ctypes.c_double(1.0 - b2 ** t),
+                                     torch.cuda.current_stream().cuda_stream), "adam_multi")
+        plan["_keep"] = grads                    # contiguous copies must outlive the asynchronous kernel

@@ -40,7 +40,8 @@ def preprocess_image(image, target_size=(256, 128), device=None, dtype=torch.flo
         out = torch.empty((B, 3, H, W), device=frames.device, dtype=dtype)
     rgb = torch.empty((B, H, W, 3), device=frames.device, dtype=torch.uint8) if want_rgb else None
     f = ctypes.c_float
-    check(lib.b200seg_preprocess_u8(ptr(frames), B, Hs, Ws, ptr(out), BF16 if out.dtype == torch.bfloat16 else F32, ptr(rgb),
-                                    H, W, f(mean[0]), f(mean[1]), f(mean[2]), f(std[0]), f(std[1]), f(std[2]),
-                                    torch.cuda.current_stream().cuda_stream), "preprocess_u8")
+    with torch.cuda.device(frames.device):           # launch on the frames' device, whatever the current one is
+        check(lib.b200seg_preprocess_u8(ptr(frames), B, Hs, Ws, ptr(out), BF16 if out.dtype == torch.bfloat16 else F32, ptr(rgb),
+                                        H, W, f(mean[0]), f(mean[1]), f(mean[2]), f(std[0]), f(std[1]), f(std[2]),
+                                        torch.cuda.current_stream().cuda_stream), "preprocess_u8")
     return out, (None if rgb is None else rgb[0] if single else rgb)

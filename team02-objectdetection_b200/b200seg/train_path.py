@@ -13,9 +13,16 @@ everything else is in csrc/train_ops.cu.  Gradient accumulation for tensors with
 connections, block inputs with a shortcut) rides on the conv kernels' ``+residual`` epilogue or the ``acc``
 argument of the adjoint kernels -- there is no separate add pass.
 
+Gradients: the backward kernels leave raw partial results (f64 slot sums, f32 accumulators in operand layout) in a
+persistent staging buffer; one ``grad_finalize`` launch per bucket writes them, in parameter layout, into the flat
+gradient arena (``dp.GradArena``) whose views ARE ``p.grad`` -- autograd never copies a parameter gradient.  With
+``dp.attach`` each bucket's all-reduce is enqueued behind its finalize launch on a side stream and overlaps the rest
+of backward, eagerly and inside the captured backward graph alike.
+
 Steady state: after ``engine.graph_after`` steps with the same input shape, the forward and the backward are
-each captured into a CUDA graph over static buffers (weight re-packing included, so in-place optimizer updates
-are picked up); a step then costs two graph launches of host time instead of ~1600 kernel launches.
+each captured into a CUDA graph over static buffers (weight re-packing, gradient finalize and the collectives
+included, so in-place optimizer updates are picked up); a step then costs two graph launches of host time instead of
+~1600 kernel launches.
 """
 from __future__ import annotations
 
@@ -118,6 +125,124 @@ def _train_packs(engine, tc: bool):
 
 
 # ----------------------------------------------------------------------------------------------------
+# gradient arena + staging + finalize tables (one per engine)
+# ----------------------------------------------------------------------------------------------------
+class TrainWorkspace:
+    """Where the backward pass puts parameter gradients.
+
+    ``arena``     dp.GradArena: flat fp32 buffer in backward order, bucketed; ``arena.views[id(p)]`` becomes ``p.grad``.
+    ``stage``     {id(param): staging view the backward kernel of that parameter accumulates into}; BatchNorm's two
+                  parameters share one f64 [NSLOT, 2, C] block (``stage[id(bn.weight)]``).
+    ``finalize``  one ``b200seg_grad_finalize_multi`` launch per bucket: staging -> arena (parameter layout, * 1/world).
+    """
+
+    def __init__(self, engine):
+        from . import dp
+        from ._cabi import lib
+        cfg = getattr(engine, "dp", None) or {}
+        params = dp.used_parameters(engine.model)
+        self.arena = dp.GradArena(params, cfg.get("group"), cfg.get("bucket_bytes", 8 << 20))
+        dev = params[0].device
+        NS = ops.NSLOT
+        plan = []                     # (param, kind, which buffer, offset, numel, dims...)
+        n64 = n32 = 0
+        self._shape: Dict[int, tuple] = {}
+        for s in engine.steps:
+            if s.conv is None:
+                continue
+            w = s.conv.weight
+            cout, cin, kk = w.shape[0], w.shape[1], w.shape[2] * w.shape[3]
+            cp = max(cout, s.pad_cout) if s.pad_cout else cout
+            if s.op == "stem":
+                plan.append((w, 2, 32, n32, kk * cin * cout, cout, cin, kk, 0, 0)); self._shape[id(w)] = (w.shape[2], w.shape[3], cin, cout)
+                n32 += (kk * cin * cout + 3) // 4 * 4
+            elif s.op == "dw":
+                plan.append((w, 3, 64, n64, NS * kk * cout, cout, 1, kk, NS, kk * cout)); self._shape[id(w)] = (NS, kk, cout)
+                n64 += NS * kk * cout
+            else:
+                plan.append((w, 1, 32, n32, cp * kk * cin, cout, cin, kk, 0, 0)); self._shape[id(w)] = (cp, kk * cin)
+                n32 += (cp * kk * cin + 3) // 4 * 4
+            if s.conv.bias is not None:
+                b = s.conv.bias
+                plan.append((b, 0, 64, n64, NS * cp, cout, 0, 0, NS, cp)); self._shape[id(b)] = (NS, cp)
+                n64 += NS * cp
+            if s.bn is not None:
+                C = s.bn.weight.shape[0]
+                # [NSLOT][2][C]: row 0 = sum g (d beta), row 1 = sum g*xhat (d gamma)
+                plan.append((s.bn.bias, 0, 64, n64, NS * 2 * C, C, 0, 0, NS, 2 * C)); self._shape[id(s.bn.bias)] = (NS, 2, C)
+                plan.append((s.bn.weight, 0, 64, n64 + C, 0, C, 0, 0, NS, 2 * C))
+                n64 += NS * 2 * C
+        self.s64 = torch.zeros(max(n64, 1), device=dev, dtype=torch.float64)
+        self.s32 = torch.zeros(max(n32, 1), device=dev, dtype=torch.float32)
+        self.stage: Dict[int, torch.Tensor] = {}
+        src_ptr: Dict[int, int] = {}
+        meta: Dict[int, tuple] = {}
+        for (p, kind, buf, off, numel, cout, cin, kk, nslot, sstride) in plan:
+            base = self.s64 if buf == 64 else self.s32
+            if numel:
+                self.stage[id(p)] = base[off:off + numel].view(self._shape[id(p)])
+            src_ptr[id(p)] = base.data_ptr() + off * base.element_size()
+            meta[id(p)] = (kind, cout, cin, kk, nslot, sstride)
+        for s in engine.steps:          # BatchNorm: both parameters are staged in the block registered under bn.bias
+            if s.bn is not None:
+                self.stage[id(s.bn.weight)] = self.stage[id(s.bn.bias)]
+        # finalize table (arena order) + per-bucket chunk lists
+        import struct
+        chunk = int(lib.b200seg_grad_chunk())
+        scale_bits = struct.unpack("<I", struct.pack("<f", 1.0 / self.arena.world))[0]
+        rows = []
+        index = {}
+        for ti, p in enumerate(self.arena.params):
+            kind, cout, cin, kk, nslot, sstride = meta[id(p)]
+            index[id(p)] = ti
+            rows += [self.arena.views[id(p)].data_ptr(), src_ptr[id(p)], p.numel(), sstride,
+                     (cout << 32) | kind, (kk << 32) | cin, nslot, scale_bits]
+        self.table = torch.tensor(rows, dtype=torch.int64, device=dev)
+        self.bucket_chunks = []
+        for b in self.arena.buckets:
+            ct, ci = [], []
+            for p in b["params"]:
+                for c in range((p.numel() + chunk - 1) // chunk):
+                    ct.append(index[id(p)]); ci.append(c)
+            self.bucket_chunks.append((torch.tensor(ct, dtype=torch.int32, device=dev),
+                                       torch.tensor(ci, dtype=torch.int32, device=dev), len(ct)))
+        self.pending: List[int] = []
+
+    def begin_backward(self) -> None:
+        self.s64.zero_()
+        self.s32.zero_()
+        self.pending = [len(b["params"]) for b in self.arena.buckets]
+
+    def done(self, *params) -> None:
+        """The staging of these parameters is complete (their kernels are enqueued).  When a bucket fills: finalize it into
+        the arena and start its all-reduce behind that launch."""
+        from ._cabi import check, lib, ptr
+        for p in params:
+            bi = self.arena.bucket_of[id(p)]
+            self.pending[bi] -= 1
+            if self.pending[bi] == 0:
+                ct, ci, n = self.bucket_chunks[bi]
+                check(lib.b200seg_grad_finalize_multi(ptr(self.table), ptr(ct), ptr(ci), n,
+                                                      torch.cuda.current_stream().cuda_stream), "grad_finalize_multi")
+                self.arena.reduce_bucket(bi)
+
+    def end_backward(self) -> None:
+        if any(self.pending):
+            raise RuntimeError("gradient bucket incomplete: a parameter on the path produced no gradient")
+        self.arena.join()
+
+
+def _workspace(engine) -> TrainWorkspace:
+    ws = getattr(engine, "_train_ws", None)
+    key = tuple(p.data_ptr() for p in _train_params(engine))
+    if ws is None or ws.key != key:
+        ws = TrainWorkspace(engine)
+        ws.key = key
+        engine._train_ws = ws
+    return ws
+
+
+# ----------------------------------------------------------------------------------------------------
 # the two passes as plain functions over tensors (no autograd): used eagerly and under graph capture
 # ----------------------------------------------------------------------------------------------------
 def run_forward(engine, x: torch.Tensor, mode: str):
@@ -156,7 +281,7 @@ def run_forward(engine, x: torch.Tensor, mode: str):
                 res = env[s.res] if (s.op == "dense" and s.res) else None
                 a, sv = ops.bn_train_forward(z, s.bn.weight.detach().float(), s.bn.bias.detach().float(),
                                              s.bn.running_mean, s.bn.running_var, s.bn.eps,
-                                             s.bn.momentum if s.bn.momentum is not None else 0.1, s.act, res)
+                                             s.bn.momentum, s.act, res)
                 counters.append(s.bn.num_batches_tracked)
                 rec["sv"] = sv
                 env[s.dst] = a
@@ -180,19 +305,21 @@ def run_forward(engine, x: torch.Tensor, mode: str):
     return env, saved
 
 
-def run_backward(engine, env, saved, mode: str, dout: torch.Tensor, emit) -> None:
-    """Walk the schedule in reverse; every parameter gradient is handed to ``emit(param, grad)`` as soon as it
-    exists (the data-parallel reducer starts a bucket's all-reduce from there)."""
+def run_backward(engine, env, saved, mode: str, dout: torch.Tensor, ws: TrainWorkspace) -> None:
+    """Walk the schedule in reverse.  Parameter gradients are accumulated in ``ws`` staging; as soon as the last
+    parameter of a gradient bucket is staged the bucket is finalized into the arena and (data parallel) its all-reduce
+    starts on the side stream while the walk continues."""
     sdt = torch.bfloat16 if mode == "bf16" else torch.float32
     tc = mode == "bf16" and (engine.dense_impl or "tc") == "tc"
     g: Dict[str, torch.Tensor] = {"out": dout}
     ops.zero_pool.reset()
     ops.zero_pool32.reset()
+    ws.begin_backward()
     for s in reversed(engine.steps):
         rec = saved[s.name]
         _e0 = _tick()
         if s.op == "final":
-            g[s.src] = ops.final_bwd(g.pop(s.dst), sdt)
+            g[s.src] = ops.final_bwd(g.pop(s.dst), sdt, env[s.src].shape[-1])
         elif s.op == "to_nchw":
             g[s.src] = ops.nchw_to_nhwc_pad(g.pop(s.dst), env[s.src].shape[-1], sdt)
         elif s.op == "upcat":
@@ -211,22 +338,21 @@ def run_backward(engine, env, saved, mode: str, dout: torch.Tensor, emit) -> Non
                 if s.op == "dense" and s.res:           # shortcut: the same gradient flows to the block input
                     assert s.res not in g
                     g[s.res] = da
-                dz, dgamma, dbeta = ops.bn_train_backward(da, z, rec["sv"], s.act)
-                emit(s.bn.weight, dgamma)
-                emit(s.bn.bias, dbeta)
+                dz, _, _ = ops.bn_train_backward(da, z, rec["sv"], s.act, red=ws.stage[id(s.bn.weight)])
+                ws.done(s.bn.weight, s.bn.bias)
             else:
                 dz = da                                   # conv + bias only (the last 1x1 of outconv)
             w = s.conv.weight
-            cout = w.shape[0]
             if s.conv.bias is not None:
-                emit(s.conv.bias, ops.colsum(dz)[:cout].contiguous())
+                ops.colsum(dz, acc=ws.stage[id(s.conv.bias)])
+                ws.done(s.conv.bias)
             src = env[s.src]
             if s.op == "stem":
-                dwp = ops.smallcin_wgrad(src, dz, s.stride)            # [3,3,Cin,Cout]
-                emit(w, dwp.permute(3, 2, 0, 1).contiguous())
+                ops.smallcin_wgrad(src, dz, s.stride, dw=ws.stage[id(w)])             # [3,3,Cin,Cout]
+                ws.done(w)
             elif s.op == "dw":
-                dw9 = ops.dw_wgrad(src, dz, s.stride)                  # [9,C]
-                emit(w, dw9.t().reshape(cout, 1, 3, 3).contiguous())
+                ops.dw_wgrad(src, dz, s.stride, acc=ws.stage[id(w)])                  # f64 slots [NSLOT,9,C]
+                ws.done(w)
                 if s.stride == 1 and g.get(s.src) is None:
                     # stride 1: the data gradient IS the forward depthwise conv of dz with the taps flipped -> the
                     # register-blocked forward kernel (2.5x faster than the generic gather kernel)
@@ -234,10 +360,11 @@ def run_backward(engine, env, saved, mode: str, dout: torch.Tensor, emit) -> Non
                 else:
                     g[s.src] = ops.dw_dgrad(dz, rec["wp"], tuple(src.shape), s.stride, g.get(s.src))
             else:
-                cin = src.shape[-1]
-                k = 3 if s.taps == 9 else 1
-                dwk = ops.conv_wgrad_tc(src, dz, s.taps) if tc else ops.conv_wgrad(src, dz, s.taps)   # [Cout_pad, taps*Cin]
-                emit(w, dwk[:cout].reshape(cout, k, k, cin).permute(0, 3, 1, 2).contiguous())
+                if tc:
+                    ops.conv_wgrad_tc(src, dz, s.taps, dw=ws.stage[id(w)])            # [Cout_pad, taps*Cin]
+                else:
+                    ops.conv_wgrad(src, dz, s.taps, dw=ws.stage[id(w)])
+                ws.done(w)
                 # dgrad = the same conv with W transposed (and the 3x3 taps flipped): packed with the forward operand
                 wt = rec["wt"]                                          # [Cin, taps*Cout_pad]
                 if tc:
@@ -246,6 +373,7 @@ def run_backward(engine, env, saved, mode: str, dout: torch.Tensor, emit) -> Non
                     g[s.src] = ops.conv_simt(dz, wt, None, s.taps, ACT_NONE, g.get(s.src))
         if _e0 is not None:
             TRACE.append(("bwd", s.name, _e0, _tick()))
+    ws.end_backward()
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -259,19 +387,39 @@ class _StepGraph:
         self.x.copy_(x)
         # torch.cuda.graph() does not run the captured work, but BatchNorm's num_batches_tracked bump is captured
         # like any other kernel, so nothing is double counted.
-        # build the persistent repack plan (allocations, table upload) OUTSIDE the capture
+        # build the persistent repack plan and the gradient workspace (allocations, table uploads) OUTSIDE the capture
         _train_packs(engine, mode == "bf16" and (engine.dense_impl or "tc") == "tc")
+        ws = _workspace(engine)
         torch.cuda.synchronize()
         self.fwd = torch.cuda.CUDAGraph()
         with torch.no_grad(), torch.cuda.graph(self.fwd):
             self.env, self.saved = run_forward(engine, self.x, mode)
         self.out = self.env["out"]
         self.dout = torch.zeros_like(self.out)
-        self.grads: Dict[int, torch.Tensor] = {}
         self.bwd = torch.cuda.CUDAGraph()
+        # the per-bucket all-reduces (data parallel) are captured on the arena's side stream: fork/join events become
+        # graph edges, so every replay overlaps them with the rest of backward
         with torch.no_grad(), torch.cuda.graph(self.bwd, pool=self.fwd.pool()):
-            run_backward(engine, self.env, self.saved, mode, self.dout, lambda p, gr: self.grads.__setitem__(id(p), gr))
+            run_backward(engine, self.env, self.saved, mode, self.dout, ws)
         self.pending = False      # a forward has been replayed whose backward has not run yet
+
+
+def _detach_accumulated(params, ws) -> None:
+    """Gradient accumulation: a ``p.grad`` that still aliases the arena (the caller did not zero_grad to None) would be
+    overwritten by this backward; give it storage of its own first."""
+    for p in params:
+        g = p.grad
+        if g is not None and g.data_ptr() == ws.arena.views[id(p)].data_ptr():
+            p.grad = g.clone()
+
+
+def _assign_grads(params, ws) -> None:
+    for p in params:
+        v = ws.arena.views[id(p)]
+        if p.grad is None:
+            p.grad = v if p.dtype == torch.float32 else v.to(p.dtype)
+        else:
+            p.grad.add_(v)
 
 
 class _TrainFn(torch.autograd.Function):
@@ -280,6 +428,7 @@ class _TrainFn(torch.autograd.Function):
         mode = engine._mode(x)
         x = x.contiguous()
         ctx.engine, ctx.mode, ctx.graph = engine, mode, None
+        ops.bump_mutation_epoch()            # BatchNorm running stats / counters change below, also under graph replay
         sg = _graph_for(engine, x, mode) if allow_graph else None
         if sg is not None:
             sg.x.copy_(x)
@@ -296,33 +445,22 @@ class _TrainFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         engine = ctx.engine
-        red = getattr(engine, "reducer", None)      # data parallel: bucketed all-reduce (overlapped with backward when eager)
-        if red is not None:
-            red.reset()
         params = _train_params(engine)
-        sg = ctx.graph
-        if sg is not None:
-            sg.dout.copy_(dout)
-            sg.bwd.replay()
-            sg.pending = False
-            if red is not None:
-                for p in red.params:                 # buckets fill in backward order; all-reduces start as they fill
-                    red.add(p, sg.grads[id(p)])
-                pgrad = red.finish()
-                return (None, None, None, *[pgrad[id(p)].clone().to(p.dtype) for p in params])
-            return (None, None, None, *[sg.grads[id(p)].clone().to(p.dtype) for p in params])
-        pgrad: Dict[int, torch.Tensor] = {}
-
-        def emit(p, gr):
-            pgrad[id(p)] = gr
-            if red is not None:
-                red.add(p, gr)
-        with torch.no_grad():
-            run_backward(engine, ctx.env, ctx.saved, ctx.mode, dout.float().contiguous(), emit)
-        if red is not None:
-            pgrad = red.finish()                     # rank-averaged views into the flat buckets
-        ctx.env = ctx.saved = None
-        return (None, None, None, *[(pgrad[id(p)].to(p.dtype) if id(p) in pgrad else None) for p in params])
+        none = (None, None, None, *[None] * len(params))       # parameter gradients are assigned to p.grad directly
+        with torch.cuda.device(dout.device):
+            ws = _workspace(engine)
+            _detach_accumulated(params, ws)
+            sg = ctx.graph
+            if sg is not None:
+                sg.dout.copy_(dout)
+                sg.bwd.replay()
+                sg.pending = False
+            else:
+                with torch.no_grad():
+                    run_backward(engine, ctx.env, ctx.saved, ctx.mode, dout.float().contiguous(), ws)
+                ctx.env = ctx.saved = None
+            _assign_grads(params, ws)
+        return none
 
 
 def _graph_for(engine, x, mode) -> Optional[_StepGraph]:
@@ -330,7 +468,11 @@ def _graph_for(engine, x, mode) -> Optional[_StepGraph]:
     shape, and no forward still waiting for its backward (two forwards would share the static buffers)."""
     if not engine.use_graphs or TRACE is not None or torch.cuda.is_current_stream_capturing():
         return None
-    key = ("train", tuple(x.shape), x.dtype, mode, engine.dense_impl, engine.tc_flags, x.device)
+    # the captured graphs hold raw pointers of every parameter and BatchNorm buffer: a graph is only valid for them
+    ident = tuple(t.data_ptr() for s in engine.steps for m in (s.conv, s.bn) if m is not None
+                  for t in list(m.parameters()) + list(m.buffers()))
+    key = ("train", tuple(x.shape), x.dtype, mode, engine.dense_impl, engine.tc_flags, x.device, hash(ident),
+           id(getattr(engine, "dp", None)))
     ent = engine._graphs.get(key)
     if ent is None:
         if len(engine._graphs) >= 3:
@@ -345,9 +487,24 @@ def _graph_for(engine, x, mode) -> Optional[_StepGraph]:
     return sg
 
 
+def _check_bn_modes(engine) -> None:
+    """The fused training path implements nn.BatchNorm2d's defaults as the reference uses them; anything else must fail
+    loudly instead of silently training differently."""
+    for s in engine.steps:
+        bn = s.bn
+        if bn is None:
+            continue
+        if not bn.training:
+            raise NotImplementedError(f"{s.name}: per-module bn.eval() inside model.train() is not supported")
+        if bn.momentum is None or not bn.track_running_stats or not bn.affine:
+            raise NotImplementedError(f"{s.name}: BatchNorm2d(momentum=None / track_running_stats=False / affine=False) "
+                                      "is not supported by the fused training path")
+
+
 def forward_train(engine, x: torch.Tensor) -> torch.Tensor:
     params = _train_params(engine)
     engine._check_input(x)
+    _check_bn_modes(engine)
     if params[0].dtype != torch.float32:
         raise TypeError("training keeps fp32 master weights: use model.float() and engine.precision='bf16' "
                         "(or torch.autocast) for bf16 activations")

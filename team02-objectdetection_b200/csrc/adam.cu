@@ -141,3 +141,72 @@ extern "C" int b200seg_pack_weights_multi(const void* table, const int* chunk_te
 }
 
 extern "C" int b200seg_pack_chunk(void) { return b200::PACK_CHUNK; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Gradient finalize (train.py:38 -> p.grad): the backward kernels leave every parameter gradient as a raw partial result
+// in a staging buffer -- f64 per-channel sums in `nslot` copies (BatchNorm gamma/beta, conv biases, depthwise taps) or
+// f32 accumulators in the kernels' operand layout (dense OHWI, stem [kk][cin][cout]).  This kernel turns ALL tensors of
+// one gradient bucket into the parameters' own layout (OIHW / [C]) inside the flat gradient arena, in ONE launch,
+// pre-scaled (1/world for the data-parallel average), replacing ~90 f64->f32 launches, ~60 permute copies and ~400
+// clone/scale copies per step.
+//   kind 0  f64 slots -> f32 [n]                       dst[i] = scale * sum_slot src[slot*stride + i]
+//   kind 1  dense f32 [cout_pad][kk][cin] -> OIHW      dst[(o*cin + i)*kk + t] = scale * src[(o*kk + t)*cin + i]
+//   kind 2  stem f32 [kk][cin][cout] -> OIHW           dst[(o*cin + i)*kk + t] = scale * src[(t*cin + i)*cout + o]
+//   kind 3  depthwise f64 slots [kk][C] -> [C][kk]     dst[c*kk + t] = scale * sum_slot src[slot*stride + t*C + c]
+// ---------------------------------------------------------------------------------------------------------------
+namespace b200 {
+
+struct GradEntry {       // 64 bytes
+  float* dst;
+  const void* src;
+  long long n;
+  long long slot_stride;
+  int kind, cout, cin, kk, nslot, pad_;
+  float scale;
+  int pad2_;
+};
+
+constexpr int GRAD_CHUNK = 2048;
+
+__global__ void __launch_bounds__(256)
+grad_finalize_kernel(const GradEntry* __restrict__ table, const int* __restrict__ chunk_tensor,
+                     const int* __restrict__ chunk_index) {
+  const GradEntry t = table[chunk_tensor[blockIdx.x]];
+  const long long base = (long long)chunk_index[blockIdx.x] * GRAD_CHUNK;
+  const long long end = min(base + GRAD_CHUNK, t.n);
+  for (long long e = base + threadIdx.x; e < end; e += 256) {
+    float v;
+    if (t.kind == 0) {
+      const double* s = reinterpret_cast<const double*>(t.src);
+      double a = 0.0;
+      for (int sl = 0; sl < t.nslot; ++sl) a += s[sl * t.slot_stride + e];
+      v = (float)a;
+    } else if (t.kind == 3) {
+      const double* s = reinterpret_cast<const double*>(t.src);
+      const int c = (int)(e / t.kk), tap = (int)(e - (long long)c * t.kk);
+      double a = 0.0;
+      for (int sl = 0; sl < t.nslot; ++sl) a += s[sl * t.slot_stride + (long long)tap * t.cout + c];
+      v = (float)a;
+    } else {
+      const float* s = reinterpret_cast<const float*>(t.src);
+      const long long per_o = (long long)t.cin * t.kk;
+      const int o = (int)(e / per_o);
+      const int r = (int)(e - (long long)o * per_o);
+      const int i = r / t.kk, tap = r - i * t.kk;
+      v = t.kind == 1 ? s[((long long)o * t.kk + tap) * t.cin + i] : s[((long long)tap * t.cin + i) * t.cout + o];
+    }
+    t.dst[e] = v * t.scale;
+  }
+}
+
+}  // namespace b200
+
+extern "C" int b200seg_grad_finalize_multi(const void* table, const int* chunk_tensor, const int* chunk_index,
+                                           int n_chunks, b200seg_stream_t s) {
+  B200_REQUIRE(table && chunk_tensor && chunk_index && n_chunks > 0, "grad_finalize_multi: bad arguments");
+  b200::grad_finalize_kernel<<<(unsigned)n_chunks, 256, 0, (cudaStream_t)s>>>((const b200::GradEntry*)table, chunk_tensor,
+                                                                               chunk_index);
+  return b200::check_launch("grad_finalize_multi");
+}
+
+extern "C" int b200seg_grad_chunk(void) { return b200::GRAD_CHUNK; }

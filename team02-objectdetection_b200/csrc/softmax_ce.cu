@@ -11,7 +11,8 @@ namespace b200 {
 template <int CMAX>
 __global__ void __launch_bounds__(256)
 softmax_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ target, float* __restrict__ loss_sum,
-                  float* __restrict__ dlogits, float grad_scale, int B, int C, long long HW) {
+                  float* __restrict__ dlogits, float grad_scale, const float* __restrict__ counts, int B, int C,
+                  long long HW) {
   const long long total = (long long)B * HW;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   float loss = 0.f;
@@ -39,10 +40,12 @@ softmax_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ 
     const float inv = 1.f / sum;
     if (valid) loss = logf(sum) - zt;
     if (dlogits) {
+      // 'mean' reduction divides by the number of non-ignored targets (counts[0], from b200seg_ce_count)
+      const float gs = counts ? grad_scale / fmaxf(__ldg(counts), 1.f) : grad_scale;
       float* gp = dlogits + (long long)b * C * HW + pix;
 #pragma unroll
       for (int c = 0; c < CMAX; ++c)
-        if (c < C) gp[(long long)c * HW] = valid ? (v[c] * inv - (c == (int)t ? 1.f : 0.f)) * grad_scale : 0.f;
+        if (c < C) gp[(long long)c * HW] = valid ? (v[c] * inv - (c == (int)t ? 1.f : 0.f)) * gs : 0.f;
     }
   }
   // block reduction of the loss
@@ -59,13 +62,16 @@ softmax_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ 
   }
 }
 
+int launch_softmax_ce_generic(const float* logits, const int64_t* target, float* loss_sum, float* dlogits, float grad_scale,
+                              const float* counts, int B, int C, long long HW, cudaStream_t st);   // generic_ops.cu
+
 }  // namespace b200
 
 using namespace b200;
 
 extern "C" int b200seg_softmax_ce(const float* logits, const int64_t* target, float* loss_sum, float* dlogits,
-                                  float grad_scale, int B, int C, int H, int W, b200seg_stream_t s) {
-  B200_REQUIRE(C >= 1 && C <= 32, "softmax_ce: C=%d must be in 1..32", C);
+                                  float grad_scale, const float* counts, int B, int C, int H, int W, b200seg_stream_t s) {
+  B200_REQUIRE(C >= 1, "softmax_ce: C=%d", C);
   B200_REQUIRE(B > 0 && H > 0 && W > 0, "softmax_ce: empty tensor");
   B200_REQUIRE(logits && target && loss_sum, "softmax_ce: null pointer");
   const long long HW = (long long)H * W;
@@ -73,8 +79,10 @@ extern "C" int b200seg_softmax_ce(const float* logits, const int64_t* target, fl
   const unsigned grid = (unsigned)((total + 255) / 256);
   cudaStream_t st = (cudaStream_t)s;
   if (C <= 16)
-    softmax_ce_kernel<16><<<grid, 256, 0, st>>>(logits, target, loss_sum, dlogits, grad_scale, B, C, HW);
+    softmax_ce_kernel<16><<<grid, 256, 0, st>>>(logits, target, loss_sum, dlogits, grad_scale, counts, B, C, HW);
+  else if (C <= 32)
+    softmax_ce_kernel<32><<<grid, 256, 0, st>>>(logits, target, loss_sum, dlogits, grad_scale, counts, B, C, HW);
   else
-    softmax_ce_kernel<32><<<grid, 256, 0, st>>>(logits, target, loss_sum, dlogits, grad_scale, B, C, HW);
+    return launch_softmax_ce_generic(logits, target, loss_sum, dlogits, grad_scale, counts, B, C, HW, st);
   return check_launch("softmax_ce");
 }

@@ -1,6 +1,6 @@
-"""T4 host logic on CPU: the bucketed gradient reducer and the parameter broadcast,
-world_size 2 over gloo.  (The model itself needs CUDA; here the reducer is driven with synthetic gradients in
-the exact order backward produces them.)"""
+"""T4 host logic on CPU: the flat bucketed gradient arena and the parameter broadcast,
+world_size 2 over gloo.  (The model itself needs CUDA; here the arena is filled with synthetic, 1/world-scaled
+gradients bucket by bucket in the exact order backward finalizes them.)"""
 import os
 import socket
 
@@ -30,14 +30,19 @@ def _worker(rank, world, port, q):
         from b200seg import engine
         m.__dict__["_engine"] = engine.Engine(m, "unet")
         params = dp.used_parameters(m)
-        red = dp.GradBucketReducer(params, bucket_bytes=64 << 10)
-        grads = {id(p): torch.full_like(p, float(rank + 1)) * (i + 1) for i, p in enumerate(params)}
-        red.reset()
-        for p in params:                                    # backward order
-            red.add(p, grads[id(p)])
-        avg = red.finish()
-        ok = all(torch.allclose(avg[id(p)], torch.full_like(p, 1.5 * (i + 1))) for i, p in enumerate(params))
-        q.put((rank, ok, float(w0.sum()), len(red.buckets), len(params)))
+        arena = dp.GradArena(params, bucket_bytes=64 << 10)
+        index = {id(p): i for i, p in enumerate(params)}
+        for bi, b in enumerate(arena.buckets):              # backward order: what grad_finalize does per bucket on the GPU
+            for p in b["params"]:
+                arena.views[id(p)].fill_(float(rank + 1) * (index[id(p)] + 1) / world)
+            arena.reduce_bucket(bi)                         # async: later buckets are filled while this one is in flight
+        arena.join()
+        ok = all(torch.allclose(arena.views[id(p)], torch.full_like(p, 1.5 * (i + 1))) for i, p in enumerate(params))
+        # views tile the flat buffer in order, 16-byte aligned, buckets are contiguous and cover everything
+        ok = ok and all(arena.offsets[id(p)] % 4 == 0 for p in params)
+        ok = ok and arena.buckets[0]["lo"] == 0 and all(a["hi"] == b["lo"] for a, b in zip(arena.buckets, arena.buckets[1:]))
+        ok = ok and arena.buckets[-1]["hi"] == arena.flat.numel()
+        q.put((rank, ok, float(w0.sum()), len(arena.buckets), len(params)))
     finally:
         dist.destroy_process_group()
 
@@ -59,7 +64,7 @@ def test_bucketed_allreduce_and_broadcast_world2():
     assert res[0][4] == 62                                  # 16 convs (weight+bias) + 15 BNs (weight+bias)
 
 
-def test_unused_classifier_is_excluded_from_the_reducer():
+def test_unused_classifier_is_excluded_from_the_arena():
     m = b200seg.MobileNetV2UNet(output_channels=10)
     from b200seg import engine
     m.__dict__["_engine"] = engine.Engine(m, "mbv2unet")
@@ -72,5 +77,6 @@ def test_unused_classifier_is_excluded_from_the_reducer():
     names = {id(p): n for n, p in m.named_parameters()}
     order = [names[id(p)] for p in params]
     assert order[0].startswith("outc.") and order[-1].startswith("backbone.features.0.")
-    red = dp.GradBucketReducer(params, bucket_bytes=8 << 20)
-    assert 2 <= len(red.buckets) <= 6
+    arena = dp.GradArena(params, bucket_bytes=8 << 20)
+    assert 2 <= len(arena.buckets) <= 6
+    assert all(arena.views[id(p)].shape == p.shape for p in params)

@@ -48,11 +48,6 @@ def _run(x, we, be, wd, bd, wp, bp, stride, residual, flags=0):
                       ops.pad_channels(bp, 16), stride, residual, flags=flags)
 
 
-def _run_tc(x, we, be, wd, bd, wp, bp, stride, residual, flags=0):
-    return ops.mbconv_tc(x, we, ops.pad_channels(be, 64), ops.pad_channels(wd, 64), ops.pad_channels(bd, 64), wp,
-                         ops.pad_channels(bp, 16), stride, residual, flags=flags)
-
-
 CASES = [  # B, H, W, Cin, Ce, Cout, stride, residual      (encoder blocks features.2 .. features.17)
     (2, 32, 64, 16, 96, 24, 2, False),
     (2, 16, 32, 24, 144, 24, 1, True),
@@ -108,38 +103,3 @@ def test_mbconv_rejects_bad_arguments():
         _run(x, we, be, wd, bd, wp, bp, 1, True)                  # residual with Cin != Cout
     with pytest.raises((ValueError, RuntimeError)):
         ops.mbconv(x, we, be, wd, bd, wp, bp, 1, False)           # unpadded parameter vectors
-
-
-# ---------------------------------------------------------------------------------------------------------------
-# tensor-core depthwise variant (b200seg_mbconv_tc): the depthwise taps are bf16 there, so the reference rounds them
-# ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("B,H,W,Cin,Ce,Cout,stride,residual", CASES + [(2, 64, 128, 16, 96, 24, 2, False),
-                                                                        (1, 46, 80, 24, 144, 24, 1, True)])
-def test_mbconv_tc_matches_unfused_reference(B, H, W, Cin, Ce, Cout, stride, residual):
-    x, we, be, wd, bd, wp, bp = _case(B, H, W, Cin, Ce, Cout, stride, residual)
-    wd = wd.bfloat16().float()
-    ref = _reference(x, we, be, wd, bd, wp, bp, stride, residual)
-    got = _run_tc(x, we, be, wd, bd, wp, bp, stride, residual)
-    assert got.shape == ref.shape
-    err = float((got.double() - ref).abs().max() / ref.abs().max())
-    assert err < 1e-2, err
-
-
-@pytest.mark.parametrize("stride", [1, 2])
-@pytest.mark.parametrize("flags", [1 | (1 << 2) | (1 << 4), 2 | (2 << 2) | (2 << 4) | (1 << 6), (1 << 8), 1 << 16, 2 << 16,
-                                   (1 << 6) | (2 << 16), (1 << 6) | (1 << 16)])
-def test_mbconv_tc_variants_agree(flags, stride):
-    """Buffer counts, CTAs per SM, tile height and grid size do not change the result (bit-identical)."""
-    args = _case(4, 32, 64, 32, 192, 32 if stride == 1 else 64, stride, stride == 1, seed=10)
-    base = _run_tc(*args, stride, stride == 1)
-    assert torch.equal(_run_tc(*args, stride, stride == 1, flags=flags), base)
-
-
-def test_mbconv_tc_agrees_with_cuda_core_variant():
-    """Same block through both fused kernels (bf16-representable depthwise taps): identical rounding points."""
-    x, we, be, wd, bd, wp, bp = _case(3, 32, 48, 64, 384, 64, 1, True, seed=30)
-    wd = wd.bfloat16().float()
-    a = _run(x, we, be, wd, bd, wp, bp, 1, True)
-    b = _run_tc(x, we, be, wd, bd, wp, bp, 1, True)
-    err = float((a.float() - b.float()).abs().max() / a.float().abs().max())
-    assert err < 8e-3, err

@@ -37,3 +37,14 @@ def rel_err(a, b):
     """max |a-b| / max |b|  -- the 'relative' of BASELINE's tolerances."""
     a, b = a.double(), b.double()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def f2_sd():
+    """Fixture F2: the network the LIVE reference trained for 600 Adam steps on the road-scene generator
+    (oracle/make_golden_f2.py), reconstructed exactly from tests/golden/f2_weights.npz."""
+    return O.f2_state_dict(gold("f2_weights.npz"))
+
+
+def f2_meta():
+    import json
+    return json.loads(str(gold("f2_eval.npz")["meta"]))

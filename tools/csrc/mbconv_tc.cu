@@ -26,6 +26,11 @@
 // for a single weight stage and serialised expand(c+1) behind project(c)).
 #include "common.cuh"
 
+// experiment, built only into tools/_build/libb200seg_tools.so (tools/build_tools.py); not part of the product ABI
+extern "C" int b200seg_mbconv_tc(const void* x, const void* w_exp, const float* b_exp, const float* w_dw, const float* b_dw,
+                                 const void* w_proj, const float* b_proj, int residual, void* y, int B, int H, int W, int Cin,
+                                 int Ce, int Cout, int stride, int flags, b200seg_stream_t s);
+
 namespace b200 {
 
 namespace {

@@ -4,6 +4,8 @@
 // Used for DESIGN.md finding 8 (cost per MMA as a function of M and N, with one or two CTAs per SM).
 #include "common.cuh"
 
+extern "C" int b200seg_probe_mma(int M, int N, int iters, int ctas_per_sm, long long* cycles_out, b200seg_stream_t s);
+
 namespace b200 {
 
 __global__ void __launch_bounds__(128)

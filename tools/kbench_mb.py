@@ -67,10 +67,7 @@ for name, H, W, Cin, Ce, Cout, st in BLOCKS:
     line = f"{name:4s} {Cin:3d}->{Ce:3d}->{Cout:3d} s{st} @{H}x{W}  unfused {us_u:7.1f} us |"
     for f in FLAGS:
         try:
-            if os.environ.get("KB_CUDA_DW"):
-                us_f = timeit(lambda: ops.mbconv(x, we, pe, pwd, pbd, wp, pbp, st, res, out=y2, flags=f))
-            else:
-                us_f = timeit(lambda: ops.mbconv_tc(x, we, pe, pwd, pbd, wp, pbp, st, res, out=y2, flags=f))
+            us_f = timeit(lambda: ops.mbconv(x, we, pe, pwd, pbd, wp, pbp, st, res, out=y2, flags=f))
         except RuntimeError:
             line += f"  fused[{f:#x}]     n/a (does not fit)          "
             continue

@@ -3,12 +3,14 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "team02-objectdetection_b200"))
 import torch
-from b200seg._cabi import check, lib, ptr
+from b200seg._cabi import ptr
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from _toolslib import check, lib
 ITERS = 4096
 sms = torch.cuda.get_device_properties(0).multi_processor_count
 print(f"{'M':>4s} {'N':>4s} {'CTAs/SM':>8s} {'cycles/MMA per CTA':>20s} {'cycles/MMA per SM':>18s} {'MAC/clk/SM':>11s}")
 for M in (128, 64):
-    for N in (16, 32, 64, 128, 256):
+    for N in (16, 32, 48, 64, 96, 128, 192, 240, 256):
         for ctas in (1, 2):
             out = torch.zeros(sms * ctas, dtype=torch.int64, device="cuda")
             for _ in range(2):
