@@ -8,6 +8,10 @@ Default workload (N=1): BASELINE config[1] -- MobileNetV2UNet bf16 inference, ba
 3x256x512, 10 classes, random-init weights, synthetic frames; frames are sharded across ranks with no
 collective (weak scaling).  One "step" = one forward pass over one batch.
 
+Every default run also times BASELINE config[2] -- the data-parallel training step (batch 32/GPU, bf16 activations, fused
+Adam, bucketed all-reduce inside the backward graph when N > 1) -- for the same --steps/--warmup and reports it as numeric
+`train_*` keys inside `config`, next to the torch-eager (cuDNN) incumbent on the same GPU (`eager_*` keys, N=1 only).
+
 One JSON line on rank 0:
   value     images/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
   e2e       same metric through the public API with HOST (pinned) frames: H2D copy + forward +
@@ -15,8 +19,8 @@ One JSON line on rank 0:
   roofline  the dominant kernel's achieved HBM GB/s (or TFLOP/s) vs MEASURED_PEAKS.json, measured
             live with CUDA events on the launch stream
   cpu_baseline  the oracle port of the reference path (fp32, PyTorch CPU) on this box's host cores
---impl reference: times that CPU path alone (the reference is Python and is not present on the GPU
-box; the oracle port is its restatement, see oracle/unet_oracle.py).
+--impl reference: times that CPU path alone: the real reference (/root/reference via the Appendix-D shim) when that
+tree is present, else its restatement oracle/unet_oracle.py (the GPU box has no /root/reference); `kind` says which ran.
 """
 import argparse
 import json
@@ -48,6 +52,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default 64 infer / 32 train)")
     ap.add_argument("--breakdown", action="store_true", help="print the per-kernel table to stderr")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-leg", action="store_true", help="skip the config[2] training leg of the default run")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the torch-eager incumbent legs (N=1)")
+    ap.add_argument("--sustain-seconds", type=float, default=2.0, help="length of the extra sustained-throughput loop")
     return ap.parse_args()
 
 
@@ -143,25 +150,9 @@ class ClockSampler:
 
 
 def cpu_reference_leg(seconds=12.0, warmup=2, fixed_iters=None):
-    """The reference's CPU path (oracle port, fp32, batch 1 at 3x256x512, eval) on the host cores."""
-    from oracle import unet_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
-    sd = O.synth_state_dict(O.mbv2unet_param_shapes(NCLS), seed=0)
-    x = O.synth_input(1, H, W, seed=0)
-    times = []
-    with torch.no_grad():
-        for _ in range(warmup):
-            O.mobilenetv2_unet_forward(sd, x)
-        t_end = time.perf_counter() + seconds
-        while (fixed_iters is None and time.perf_counter() < t_end) or (fixed_iters is not None and len(times) < fixed_iters):
-            t0 = time.perf_counter()
-            O.mobilenetv2_unet_forward(sd, x)
-            times.append(time.perf_counter() - t0)
-    tot = sum(times)
-    return dict(value=len(times) / tot, unit="images/s", cores=torch.get_num_threads(), kind="port",
-                sample=f"{len(times)} x (batch 1, 3x{H}x{W}, fp32 eval forward) oracle port of src/unet.py on PyTorch-CPU; "
-                       f"best {min(times) * 1e3:.1f} ms median {statistics.median(times) * 1e3:.1f} ms",
-                ms_per_image=tot / len(times) * 1e3)
+    """The reference's CPU path (fp32, batch 1 at 3x256x512, eval) on the host cores: see bench_baselines.cpu_leg."""
+    from bench_baselines import cpu_leg
+    return cpu_leg(seconds, warmup, fixed_iters)
 
 
 _REAL_STDOUT = None
@@ -269,6 +260,15 @@ def main():
         barrier()
         ms = e0.elapsed_time(e1)
         clk = clocks.stop() if rank == 0 else None
+        # sustained figure: the same loop for >= --sustain-seconds (power/thermals settled), reported beside `value`
+        n_sus = max(args.steps, int(args.sustain_seconds * 1e3 / max(ms / args.steps, 1e-3)))
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(n_sus):
+            y = model(xs[i % nrot])
+        s1.record()
+        torch.cuda.synchronize()
+        ms_sus = s0.elapsed_time(s1) / n_sus
 
     # ---------------- e2e leg: host frames in, class mask out ----------------
     # the reference's per-frame flow (inference.py:28-46,162-164): uint8 BGR camera frame -> preprocess_image -> model ->
@@ -305,7 +305,7 @@ def main():
         torch.cuda.synchronize()
 
     with torch.no_grad():
-        e2e_steps(max(6, args.warmup))          # untimed: first touches of the pinned buffers / copy engines on a fresh box
+        e2e_steps(max(12, args.warmup))         # untimed: first touches of the pinned buffers / copy engines on a fresh box
         barrier()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
@@ -384,13 +384,26 @@ def main():
 
     # ---------------- max over ranks ----------------
     if dist is not None:
-        t = torch.tensor([ms, ms_e2e], device=dev)
+        t = torch.tensor([ms, ms_e2e, ms_sus], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+        ms, ms_e2e, ms_sus = float(t[0]), float(t[1]), float(t[2])
+
+    # ---------------- config[2]: the training step (every rank; data parallel when N > 1) ----------------
+    train = None
+    if args.workload == "infer" and not args.no_train_leg:
+        del xs, xd, xn, y
+        eng._graphs.clear()
+        torch.cuda.empty_cache()
+        from bench_train import train_leg
+        train = train_leg(args, dev, dist, world, rank)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
+    eager = {}
+    if world == 1 and args.workload == "infer" and not args.no_eager_baseline:
+        from bench_baselines import gpu_eager_leg
+        eager = gpu_eager_leg(dev)
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -405,7 +418,7 @@ def main():
                                    + ("(BASELINE config[4]: 720x1280 frames padded to 736 rows; " if args.workload == "infer720" else "(BASELINE config[1]; ")
                                    + "frames sharded by rank, no collective)",
                        "global_batch": B * world, "l2": "4 rotating input batches; ~7 GB of activations per step >> 126 MB L2",
-                       "sm_count": sms, "cc": cc},
+                       "sm_count": sms, "cc": cc, "sustained_img_s": B * world / (ms_sus * 1e-3), "sustained_steps": n_sus},
             "e2e": {"value": B * world * args.steps / (ms_e2e * 1e-3), "unit": "images/s",
                     "h2d_bytes_per_step": B * 3 * H * W, "d2h_bytes_per_step": B * H * W,
                     "api": "b200seg.preprocess_image(uint8 BGR HWC frames, pinned) -> model.predict_mask(...) -> uint8 class mask "
@@ -415,6 +428,15 @@ def main():
             "roofline": roofline, "step_roofline": step_roofline, "clocks": clk}
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if train is not None:
+        # BASELINE config[2], numeric keys only (train.py:31-42 loop body; see bench_train.py): whole-job images/s
+        line["config"].update({
+            "train_img_s": train["img_s"], "train_ms_per_step": train["ms_per_step"], "train_e2e_img_s": train["e2e_img_s"],
+            "train_roofline_frac": train["achieved_gbs"] / pk["hbm"], "train_batch_per_gpu": train["B"],
+            "train_host_issue_ms": train["host_issue_ms_per_step"], "allreduce_exposed_ms": train["allreduce_exposed_ms"],
+            "train_launches_per_step": train["launches_per_step"], "train_last_loss": train["last_loss"]})
+    for k, v in eager.items():
+        line["config"][k] = v
     emit(line)
     if dist is not None:
         dist.destroy_process_group()

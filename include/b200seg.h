@@ -216,6 +216,16 @@ int b200seg_adam_chunk(void);
 int b200seg_pack_weights_multi(const void* table, const int* chunk_tensor, const int* chunk_index, int n_chunks,
                                b200seg_stream_t s);
 int b200seg_pack_chunk(void);
+/* Eval-mode weight preparation (model.eval(), inference.py:25) for all layers in one launch: BatchNorm folded into the
+ * convolution in fp32 (w' = w*g/sqrt(rv+eps), b' = beta + (b - rm)*g/sqrt(rv+eps)) and written in the operand layout of
+ * the forward kernels.  table: device array of {const float* w (OIHW), cbias, gamma, beta, rmean, rvar (NULL gamma = no
+ * BN); void* out_w; float* out_b (or NULL); int cout, cin, kk, ldw, kind; float eps; long long pad;} (96 bytes), one row
+ * per output operand.  kind 0/1: dense bf16/f32 [cout_pad][kk][cin]; 2: stem f32 [kk][cin][cout]; 3: depthwise f32
+ * [kk][ldw]; 4: depthwise block-diagonal bf16 [C][kk][64]; 5: depthwise bf16 [kk][ldw].  Outputs are caller-zeroed (padding
+ * is never written).  Chunking as above, CHUNK = b200seg_fold_chunk() over cout*cin*kk (+ cout shift elements). */
+int b200seg_fold_pack_eval_multi(const void* table, const int* chunk_tensor, const int* chunk_index, int n_chunks,
+                                 b200seg_stream_t s);
+int b200seg_fold_chunk(void);
 /* Gradient finalize (loss.backward() -> p.grad, train.py:38): every parameter gradient of one bucket from the backward
  * kernels' staging layouts into the parameters' own layout inside the flat gradient arena, one launch, pre-scaled (1/world
  * for the data-parallel mean).  table: device array of {float* dst; const void* src; long long n; long long slot_stride;

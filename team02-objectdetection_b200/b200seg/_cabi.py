@@ -60,6 +60,8 @@ _PROTOS = {
     "b200seg_adam_chunk": [],
     "b200seg_pack_weights_multi": [_vp, _vp, _vp, _i, _vp],
     "b200seg_pack_chunk": [],
+    "b200seg_fold_pack_eval_multi": [_vp, _vp, _vp, _i, _vp],
+    "b200seg_fold_chunk": [],
     "b200seg_grad_finalize_multi": [_vp, _vp, _vp, _i, _vp],
     "b200seg_grad_chunk": [],
     "b200seg_maxpool_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
@@ -85,7 +87,11 @@ def _load():
 lib = _load()
 
 
+LAUNCHES = [0]      # C-ABI calls that returned success (each is one kernel launch; two for a few wrappers' helpers)
+
+
 def check(rc: int, what: str = "") -> None:
+    LAUNCHES[0] += 1
     if rc != 0:
         msg = lib.b200seg_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"libb200seg {what} failed (rc={rc}): {msg}")

@@ -98,18 +98,6 @@ def build_steps_unet(model) -> List[Step]:
     return st
 
 
-def fold_conv_bn(conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d]):
-    """Eval-mode BatchNorm folded into the convolution, in fp32:
-    w' = w * g/sqrt(rv+eps);  b' = beta + (b - rm) * g/sqrt(rv+eps)."""
-    w = conv.weight.detach().float()
-    b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(w.shape[0], device=w.device)
-    if bn is not None:
-        scale = bn.weight.detach().float() * torch.rsqrt(bn.running_var.detach().float() + bn.eps)
-        w = w * scale[:, None, None, None]
-        b = bn.bias.detach().float() + (b - bn.running_mean.detach().float()) * scale
-    return w, b
-
-
 class Engine:
     def __init__(self, model, arch: str):
         self.model = model
@@ -144,42 +132,107 @@ class Engine:
         # the training forward and its CUDA-graph replays) -- those writes do not touch tensor._version
         return (mode, self.dense_impl, v, ops.mutation_epoch(), p0.device, p0.data_ptr())
 
-    def _pack_eval(self, mode: str):
-        key = self._version_key(mode)
-        if key == self._packed_key:
-            return self._packed
-        dense_impl = self.dense_impl or ("tc" if mode == "bf16" else "simt")
+    def _eval_plan(self, mode: str, dense_impl: str):
+        """Persistent eval operand buffers + the device table of the one-launch fold/pack kernel
+        (b200seg_fold_pack_eval_multi).  Rebuilt only when the parameter tensors themselves are replaced."""
+        from ._cabi import lib
+        convs = [s for s in self.steps if s.conv is not None]
+        ident = tuple(t.data_ptr() for s in convs for m in (s.conv, s.bn) if m is not None
+                      for t in list(m.parameters()) + [b for b in m.buffers() if b.is_floating_point()])
+        key = (mode, dense_impl, ident)
+        plan = getattr(self, "_eval_plan_cache", None)
+        if plan is not None and plan["key"] == key:
+            return plan
+        dev = convs[0].conv.weight.device
+        chunk = int(lib.b200seg_fold_chunk())
+        tc = dense_impl == "tc"
         packed: Dict[str, dict] = {}
-        with torch.no_grad():
-            for s in self.steps:
-                if s.conv is None:
-                    continue
-                w, b = fold_conv_bn(s.conv, s.bn)
-                cout = w.shape[0]
-                if s.op == "stem":
-                    packed[s.name] = dict(w=w.permute(2, 3, 1, 0).contiguous(), b=b.contiguous())
-                elif s.op == "dw":
-                    w9c = w.reshape(cout, 9).t().contiguous()
-                    packed[s.name] = dict(w=w9c, b=b.contiguous())
-                    if mode == "bf16":          # block-diagonal packing for the tensor-core depthwise kernel
-                        packed[s.name]["wdiag"] = ops.pack_dw_diag(w9c)
-                else:
-                    wk = w.permute(0, 2, 3, 1).reshape(cout, -1)        # [Cout][taps*Cin], K-major
-                    if s.pad_cout and cout < s.pad_cout:
-                        wk = torch.cat([wk, wk.new_zeros(s.pad_cout - cout, wk.shape[1])], 0)
-                        b = torch.cat([b, b.new_zeros(s.pad_cout - cout)], 0)
-                    wk = wk.to(torch.bfloat16) if dense_impl == "tc" else wk
-                    packed[s.name] = dict(w=wk.contiguous(), b=b.contiguous())
-            if mode == "bf16" and dense_impl == "tc":
-                # operands of the fused inverted-residual kernel: the three layers' packs, parameter vectors zero
-                # padded to the 64-channel chunks the kernel processes
-                for e, d, pj in self._mb_triples():
-                    packed[pj.name + "#mb"] = dict(
-                        w_exp=packed[e.name]["w"], b_exp=ops.pad_channels(packed[e.name]["b"], 64),
-                        w_dw=ops.pad_channels(packed[d.name]["w"], 64), b_dw=ops.pad_channels(packed[d.name]["b"], 64),
-                        w_proj=packed[pj.name]["w"], b_proj=ops.pad_channels(packed[pj.name]["b"], 16))
-        self._packed, self._packed_key = packed, key
-        return packed
+        rows, ct, ci = [], [], []
+        mirror_src, mirror_dst, mirrors = [], [], {}
+        import struct
+
+        def f32ptr(t):
+            """fp32 source of a parameter/buffer: the tensor itself, or (model.bfloat16()) a persistent fp32 mirror that
+            is refreshed with one multi-tensor copy before every repack."""
+            if t is None:
+                return 0
+            if t.dtype == torch.float32 and t.is_contiguous():
+                return t.data_ptr()
+            if id(t) not in mirrors:
+                mirrors[id(t)] = torch.empty(t.shape, device=dev, dtype=torch.float32)
+                mirror_src.append(t); mirror_dst.append(mirrors[id(t)])
+            return mirrors[id(t)].data_ptr()
+
+        def add_row(s, out_w, out_b, kind, ldw):
+            w, bn = s.conv.weight, s.bn
+            cout, cin, kk = w.shape[0], w.shape[1], w.shape[2] * w.shape[3]
+            eps = struct.unpack("<I", struct.pack("<f", float(bn.eps) if bn is not None else 0.0))[0]
+            ti = len(rows) // 12
+            rows.extend([f32ptr(w), f32ptr(s.conv.bias), f32ptr(bn.weight) if bn is not None else 0,
+                         f32ptr(bn.bias) if bn is not None else 0, f32ptr(bn.running_mean) if bn is not None else 0,
+                         f32ptr(bn.running_var) if bn is not None else 0,
+                         out_w.data_ptr(), 0 if out_b is None else out_b.data_ptr(),
+                         (cin << 32) | cout, (ldw << 32) | kk, (eps << 32) | kind, 0])
+            n = cout * cin * kk + (cout if out_b is not None else 0)
+            for c in range((n + chunk - 1) // chunk):
+                ct.append(ti); ci.append(c)
+
+        for s in convs:
+            w = s.conv.weight
+            cout, cin, kk = w.shape[0], w.shape[1], w.shape[2] * w.shape[3]
+            bfull = torch.zeros((cout + 63) // 64 * 64, device=dev, dtype=torch.float32)
+            if s.op == "stem":
+                ow = torch.zeros(w.shape[2], w.shape[3], cin, cout, device=dev, dtype=torch.float32)
+                add_row(s, ow, bfull, 2, 0)
+                packed[s.name] = dict(w=ow, b=bfull[:cout])
+            elif s.op == "dw":
+                ow = torch.zeros(kk, cout, device=dev, dtype=torch.float32)
+                add_row(s, ow, bfull, 3, cout)
+                packed[s.name] = dict(w=ow, b=bfull[:cout], b64=bfull)
+                cep = bfull.numel()
+                if mode == "bf16":
+                    wdiag = torch.zeros(cout, kk, 64, device=dev, dtype=torch.bfloat16)
+                    add_row(s, wdiag, None, 4, 0)
+                    packed[s.name]["wdiag"] = wdiag
+                    w64 = ow
+                    if cep != cout:
+                        w64 = torch.zeros(kk, cep, device=dev, dtype=torch.float32)
+                        add_row(s, w64, None, 3, cep)
+                    packed[s.name]["w64"] = w64
+            else:
+                cp = max(cout, s.pad_cout) if s.pad_cout else cout
+                ow = torch.zeros(cp, kk * cin, device=dev, dtype=torch.bfloat16 if tc else torch.float32)
+                add_row(s, ow, bfull, 0 if tc else 1, 0)
+                packed[s.name] = dict(w=ow, b=bfull[:cp], b64=bfull)
+        if mode == "bf16" and tc:
+            # operands of the fused inverted-residual kernel: views of the three layers' packs (parameter vectors are
+            # zero padded to the 64-channel chunks the kernel processes)
+            for e, d, pj in self._mb_triples():
+                cop = (pj.conv.weight.shape[0] + 15) // 16 * 16
+                packed[pj.name + "#mb"] = dict(
+                    w_exp=packed[e.name]["w"], b_exp=packed[e.name]["b64"], w_dw=packed[d.name]["w64"],
+                    b_dw=packed[d.name]["b64"], w_proj=packed[pj.name]["w"], b_proj=packed[pj.name]["b64"][:cop])
+        plan = dict(key=key, packed=packed, n=len(ct), mirror_src=mirror_src, mirror_dst=mirror_dst,
+                    table=torch.tensor(rows, dtype=torch.int64, device=dev),
+                    ct=torch.tensor(ct, dtype=torch.int32, device=dev), ci=torch.tensor(ci, dtype=torch.int32, device=dev))
+        self._eval_plan_cache = plan
+        self._packed_key = None
+        return plan
+
+    def _pack_eval(self, mode: str):
+        """Folded + packed eval weights for the current parameter values: ONE kernel launch when anything changed."""
+        from ._cabi import check, lib, ptr
+        dense_impl = self.dense_impl or ("tc" if mode == "bf16" else "simt")
+        plan = self._eval_plan(mode, dense_impl)
+        key = self._version_key(mode)
+        if key != self._packed_key:
+            if plan["mirror_src"]:
+                with torch.no_grad():
+                    torch._foreach_copy_(plan["mirror_dst"], plan["mirror_src"])
+            check(lib.b200seg_fold_pack_eval_multi(ptr(plan["table"]), ptr(plan["ct"]), ptr(plan["ci"]), plan["n"],
+                                                   torch.cuda.current_stream().cuda_stream), "fold_pack_eval_multi")
+            self._packed, self._packed_key = plan["packed"], key
+        return self._packed
 
     # ------------------------------------------------------------------ fused inverted-residual blocks
     def _mb_triples(self):

@@ -391,6 +391,8 @@ class _StepGraph:
         _train_packs(engine, mode == "bf16" and (engine.dense_impl or "tc") == "tc")
         ws = _workspace(engine)
         torch.cuda.synchronize()
+        from ._cabi import LAUNCHES
+        n0 = LAUNCHES[0]
         self.fwd = torch.cuda.CUDAGraph()
         with torch.no_grad(), torch.cuda.graph(self.fwd):
             self.env, self.saved = run_forward(engine, self.x, mode)
@@ -401,6 +403,7 @@ class _StepGraph:
         # graph edges, so every replay overlaps them with the rest of backward
         with torch.no_grad(), torch.cuda.graph(self.bwd, pool=self.fwd.pool()):
             run_backward(engine, self.env, self.saved, mode, self.dout, ws)
+        self.n_launches = LAUNCHES[0] - n0     # hand-written kernels inside the two graphs (ATen fills/copies not counted)
         self.pending = False      # a forward has been replayed whose backward has not run yet
 
 

@@ -210,3 +210,77 @@ extern "C" int b200seg_grad_finalize_multi(const void* table, const int* chunk_t
 }
 
 extern "C" int b200seg_grad_chunk(void) { return b200::GRAD_CHUNK; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Eval-mode weight preparation (model.eval(), inference.py:25): fold every BatchNorm into its convolution in fp32
+// (w' = w * g / sqrt(rv + eps); b' = beta + (b - rm) * g / sqrt(rv + eps)) and write the operand
+// layout the forward kernels read -- ALL layers in one launch (before: ~20 ATen kernels per layer, ~1300 per model).
+// One table row per OUTPUT operand (a layer may have several: depthwise taps are needed as [9][C] f32, zero padded to
+// 64-channel chunks for the fused block, and block-diagonal bf16 for the tensor-core depthwise):
+//   kind 0  dense bf16 [cout_pad][kk][cin]        kind 1  dense f32 [cout_pad][kk][cin]
+//   kind 2  stem f32 [kk][cin][cout]              kind 3  depthwise f32 [kk][ldw]  (ldw >= C, padding stays zero)
+//   kind 4  depthwise block-diagonal bf16 [C][kk][64]: out[c][t][c % 64] = w'[c][t]      (b200seg_dwconv3x3_tc)
+//   kind 5  depthwise bf16 [kk][ldw]
+// Every row may also write the folded shift to out_b (f32, caller-zeroed beyond cout).  Buffers are zero-initialised by the
+// caller; only real elements are written.
+// ---------------------------------------------------------------------------------------------------------------
+namespace b200 {
+
+struct FoldEntry {       // 96 bytes
+  const float* w;        // OIHW master weights
+  const float* cbias;    // conv bias or NULL
+  const float* gamma;    // BatchNorm weight or NULL (no BN: plain copy)
+  const float* beta;
+  const float* rmean;
+  const float* rvar;
+  void* out_w;
+  float* out_b;          // or NULL
+  int cout, cin, kk, ldw, kind;
+  float eps;
+  long long pad_;
+};
+
+constexpr int FOLD_CHUNK = 2048;
+
+__global__ void __launch_bounds__(256)
+fold_pack_eval_kernel(const FoldEntry* __restrict__ table, const int* __restrict__ chunk_tensor,
+                      const int* __restrict__ chunk_index) {
+  const FoldEntry t = table[chunk_tensor[blockIdx.x]];
+  const long long per_o = (long long)t.cin * t.kk;
+  const long long n = (long long)t.cout * per_o;
+  const long long base = (long long)chunk_index[blockIdx.x] * FOLD_CHUNK;
+  const long long end = min(base + FOLD_CHUNK, n + (t.out_b ? t.cout : 0));
+  for (long long e = base + threadIdx.x; e < end; e += 256) {
+    const int o = e < n ? (int)(e / per_o) : (int)(e - n);
+    float scale = 1.f;
+    if (t.gamma) scale = __ldg(t.gamma + o) * rsqrtf(__ldg(t.rvar + o) + t.eps);
+    if (e >= n) {                                   // folded shift
+      const float b = t.cbias ? __ldg(t.cbias + o) : 0.f;
+      t.out_b[o] = t.gamma ? __ldg(t.beta + o) + (b - __ldg(t.rmean + o)) * scale : b;
+      continue;
+    }
+    const int r = (int)(e - (long long)o * per_o);
+    const int i = r / t.kk, tap = r - i * t.kk;
+    const float v = __ldg(t.w + e) * scale;
+    switch (t.kind) {
+      case 0: reinterpret_cast<__nv_bfloat16*>(t.out_w)[((long long)o * t.kk + tap) * t.cin + i] = __float2bfloat16_rn(v); break;
+      case 1: reinterpret_cast<float*>(t.out_w)[((long long)o * t.kk + tap) * t.cin + i] = v; break;
+      case 2: reinterpret_cast<float*>(t.out_w)[((long long)tap * t.cin + i) * t.cout + o] = v; break;
+      case 3: reinterpret_cast<float*>(t.out_w)[(long long)tap * t.ldw + o] = v; break;
+      case 4: reinterpret_cast<__nv_bfloat16*>(t.out_w)[((long long)o * t.kk + tap) * 64 + (o & 63)] = __float2bfloat16_rn(v); break;
+      default: reinterpret_cast<__nv_bfloat16*>(t.out_w)[(long long)tap * t.ldw + o] = __float2bfloat16_rn(v); break;
+    }
+  }
+}
+
+}  // namespace b200
+
+extern "C" int b200seg_fold_pack_eval_multi(const void* table, const int* chunk_tensor, const int* chunk_index,
+                                            int n_chunks, b200seg_stream_t s) {
+  B200_REQUIRE(table && chunk_tensor && chunk_index && n_chunks > 0, "fold_pack_eval_multi: bad arguments");
+  b200::fold_pack_eval_kernel<<<(unsigned)n_chunks, 256, 0, (cudaStream_t)s>>>((const b200::FoldEntry*)table, chunk_tensor,
+                                                                                chunk_index);
+  return b200::check_launch("fold_pack_eval_multi");
+}
+
+extern "C" int b200seg_fold_chunk(void) { return b200::FOLD_CHUNK; }
