@@ -18,16 +18,29 @@ import torch.multiprocessing as mp
 LR, STEPS = 1.5e-4, 5
 
 
-def make_model(dev, load):
+def make_model(dev, load, f2=False):
+    """Fixture F1 (random init, BN calibrated) for the single-step identity; fixture F2 (the trained network) for the
+    multi-step trajectory -- F1 is chaotic: Adam turns fp32 summation-order noise into +-lr steps there."""
     import b200seg
-    from util import expand_aliases, fixture_sd
+    from util import expand_aliases, f2_sd, fixture_sd
     m = b200seg.MobileNetV2UNet(output_channels=10)
     if load:
-        m.load_state_dict(expand_aliases(fixture_sd()), strict=True)
+        full = dict(m.state_dict())
+        full.update(expand_aliases(f2_sd() if f2 else fixture_sd()))
+        m.load_state_dict(full, strict=True)
     return m.to(dev)
 
 
 def worker(rank, world, port, q):
+    try:
+        _worker(rank, world, port, q)
+    except BaseException:                                   # noqa: BLE001 -- report instead of leaving main waiting
+        import traceback
+        q.put({"rank": rank, "error": traceback.format_exc()})
+        os._exit(1)
+
+
+def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
@@ -49,9 +62,11 @@ def worker(rank, world, port, q):
     grads = {n: p.grad.detach().cpu() for n, p in m.named_parameters() if p.grad is not None}
     out = {"rank": rank, "loss1": float(loss), "grads1": grads}
 
-    # ---- 2. five steps, graphs on / off
+    # ---- 2. five steps on the trained fixture, graphs on / off
+    x2, t2 = O.road_scene_batch(8, 64, 128, seed=31)
+    xs, ts = x2[rank * 4:(rank + 1) * 4].to(dev), t2[rank * 4:(rank + 1) * 4].to(dev)
     for tag, use_graphs in (("graph", True), ("eager", False)):
-        m = make_model(dev, load=rank == 0)
+        m = make_model(dev, load=rank == 0, f2=True)
         dp.broadcast_model(m)
         dp.attach(m, bucket_bytes=2 << 20)
         eng = m._get_engine()
@@ -70,9 +85,19 @@ def worker(rank, world, port, q):
                         params={n: p.detach().cpu() for n, p in m.named_parameters()},
                         grads={n: p.grad.detach().cpu() for n, p in m.named_parameters() if p.grad is not None},
                         bufs={n: b.detach().cpu() for n, b in m.named_buffers()})
+    # plain numpy through the pipe (torch tensors travel as shared-memory handles that need this process alive)
+    def np_(d):
+        return {k: v.numpy() for k, v in d.items()}
+    out["grads1"] = np_(out["grads1"])
+    for tag in ("graph", "eager"):
+        for k in ("params", "grads", "bufs"):
+            out[tag][k] = np_(out[tag][k])
     q.put(out)
+    q.close()
+    q.join_thread()                       # the result is in the pipe before this process goes away
     dist.barrier()
-    dist.destroy_process_group()
+    torch.cuda.synchronize()
+    os._exit(0)                           # skip interpreter teardown (NCCL communicators + captured graphs): nothing left to check
 
 
 def main():
@@ -81,9 +106,24 @@ def main():
     procs = [ctx.Process(target=worker, args=(r, 2, 29577, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted([q.get(timeout=600) for _ in procs], key=lambda r: r["rank"])
+    res = []
+    for _ in procs:
+        r = q.get(timeout=240)
+        if "error" in r:
+            print(f"rank {r['rank']} failed:\n{r['error']}")
+            for p in procs:
+                p.kill()
+            sys.exit(1)
+        r["grads1"] = {k: torch.from_numpy(v) for k, v in r["grads1"].items()}
+        for tag in ("graph", "eager"):
+            for k in ("params", "grads", "bufs"):
+                r[tag][k] = {n: torch.from_numpy(v) for n, v in r[tag][k].items()}
+        res.append(r)
+    res.sort(key=lambda r: r["rank"])
     for p in procs:
-        p.join(timeout=120)
+        p.join(timeout=20)
+        if p.is_alive():
+            p.kill()
     # single-process expectation of step 1: each shard separately on GPU 0 (per-replica BN), gradients averaged
     import b200seg
     from oracle import unet_oracle as O
@@ -110,13 +150,16 @@ def main():
     same_g = all(torch.equal(a["grads"][k], b["grads"][k]) for k in a["grads"])
     same_b = all(torch.equal(a["bufs"][k], b["bufs"][k]) for k in a["bufs"] if "running" not in k)   # BN stats are per replica
     e = res[0]["eager"]
-    dmax = max(float((a["params"][k] - e["params"][k]).abs().max()) for k in a["params"])
-    dmean = sum(float((a["params"][k] - e["params"][k]).abs().sum()) for k in a["params"]) / sum(v.numel() for v in a["params"].values())
+    used = [k for k in a["params"] if not k.startswith("backbone.classifier")]      # never on the path: random per construction
+    dmax = max(float((a["params"][k] - e["params"][k]).abs().max()) for k in used)
+    dmean = sum(float((a["params"][k] - e["params"][k]).abs().sum()) for k in used) / sum(a["params"][k].numel() for k in used)
     dloss = max(abs(u - v) for u, v in zip(a["losses"], e["losses"]))
     print(f"{STEPS} steps (3..{STEPS} replayed, all-reduce inside the backward graph): replicas bit-identical params {same_p} grads {same_g} "
           f"counters {same_b}; graph vs eager trajectory: max |dp| {dmax / LR:.2f} lr, mean {dmean / LR:.4f} lr, max |dloss| {dloss:.2e}; "
           f"losses {['%.5f' % v for v in a['losses']]}")
     assert same_p and same_g and same_b
+    # Adam normalises every element's step to ~lr whatever |g| is: elements whose gradient is at the fp32 summation-noise
+    # floor may move by up to +-lr per step in either run; the bulk must agree far below one step and the losses closely
     assert dmax <= 2.05 * LR * STEPS and dmean < 0.1 * LR and dloss < 2e-3
     print("DP CHECK OK")
 
