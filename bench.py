@@ -168,6 +168,21 @@ def protect_stdout():
         os.dup2(2, 1)
 
 
+def shutdown(dist) -> None:
+    """Leave the process group without ever hanging the launcher: NCCL's communicator teardown blocks while anything that
+    captured its collectives is still alive, so it runs under a watchdog that ends the process (the JSON line is out)."""
+    if dist is None:
+        return
+    t = threading.Timer(20.0, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
+    try:
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+    finally:
+        t.cancel()
+
+
 def emit(line: dict) -> None:
     data = (json.dumps(line) + "\n").encode()
     if _REAL_STDOUT is None:
@@ -228,7 +243,7 @@ def main():
         clocks.start()
     if args.workload in ("train", "unet_train"):
         from bench_train import run_train          # training step benchmark lives in its own file
-        return run_train(args, dev, dist, world, rank, peaks(), clocks, emit)
+        return run_train(args, dev, dist, world, rank, peaks(), clocks, emit, shutdown)
 
     global H, W
     if args.workload == "infer720":
@@ -397,8 +412,7 @@ def main():
         from bench_train import train_leg
         train = train_leg(args, dev, dist, world, rank)
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        shutdown(dist)
         return
     eager = {}
     if world == 1 and args.workload == "infer" and not args.no_eager_baseline:
@@ -438,8 +452,7 @@ def main():
     for k, v in eager.items():
         line["config"][k] = v
     emit(line)
-    if dist is not None:
-        dist.destroy_process_group()
+    shutdown(dist)
 
 
 if __name__ == "__main__":

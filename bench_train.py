@@ -123,9 +123,8 @@ def train_leg(args, dev, dist, world, rank, unet=False, batch=0, want_breakdown=
     # which no longer matters -- this is the last thing the leg does with the model)
     ms_nocomm = None
     if dist is not None:
-        eng.dp = None
-        eng._train_ws = None
-        eng._graphs.clear()
+        del loss
+        dp.detach(model)                     # also releases the graphs that captured NCCL collectives
         for i in range(eng.graph_after + 3):
             step(xs[i % nrot], ys[i % nrot])
         ms_nocomm, _, _ = timed(args.steps)
@@ -158,12 +157,16 @@ def train_leg(args, dev, dist, world, rank, unet=False, batch=0, want_breakdown=
                allreduce_exposed_ms=(ms - ms_nocomm) / args.steps if ms_nocomm is not None else 0.0,
                h2d_bytes_per_step=B * 3 * H * W * 4 + B * H * W * 8, rows=rows, rows_total=tot, clocks=clk,
                launches_per_step=launches_per_step)
-    del model, optimizer, xs, ys, xd, yd
+    eng._graphs.clear()
+    eng._train_ws = None
+    del model, optimizer, xs, ys, xd, yd, eng
+    import gc
+    gc.collect()
     torch.cuda.empty_cache()
     return res
 
 
-def run_train(args, dev, dist, world, rank, pk, clocks, emit):
+def run_train(args, dev, dist, world, rank, pk, clocks, emit, shutdown):
     unet = args.workload == "unet_train"
     r = train_leg(args, dev, dist, world, rank, unet=unet, batch=args.batch, want_breakdown=True, clocks=clocks)
     rows, tot = r["rows"], r["rows_total"]
@@ -174,8 +177,7 @@ def run_train(args, dev, dist, world, rank, pk, clocks, emit):
         print(f"sum fwd {sum(v for (p, _), v in rows if p == 'fwd'):.2f} ms, bwd {sum(v for (p, _), v in rows if p == 'bwd'):.2f} ms "
               f"(one warm eager step); graphed step {r['ms_per_step']:.2f} ms", file=sys.stderr)
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        shutdown(dist)
         return
     (top_phase, top_name), top_ms = rows[0]
     B, H, W = r["B"], r["H"], r["W"]
@@ -200,5 +202,4 @@ def run_train(args, dev, dist, world, rank, pk, clocks, emit):
                          "share_of_step": top_ms / tot},
             "gpu_launches": int(r["launches_per_step"] * args.steps), "launches_per_step": r["launches_per_step"], "clocks": r["clocks"]}
     emit(line)                # bench.py's emitter: the ONE stdout line (bench.py runs as __main__, do not re-import it)
-    if dist is not None:
-        dist.destroy_process_group()
+    shutdown(dist)

@@ -119,3 +119,17 @@ def attach(model, group=None, bucket_bytes: int = 8 << 20) -> None:
     eng.dp = dict(group=group, bucket_bytes=bucket_bytes)
     eng._train_ws = None                  # the gradient arena is rebuilt with the new bucket plan
     eng._graphs.clear()
+
+
+def detach(model) -> None:
+    """Back to single-replica gradients; releases every captured step graph.  NCCL refuses to tear a communicator down
+    while CUDA graphs that captured its collectives are alive, so call this (or drop the model) BEFORE
+    ``dist.destroy_process_group()``."""
+    import gc
+    eng = model._get_engine()
+    eng.dp = None
+    eng._train_ws = None
+    eng._graphs.clear()
+    gc.collect()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()

@@ -458,6 +458,7 @@ class _TrainFn(torch.autograd.Function):
                 sg.dout.copy_(dout)
                 sg.bwd.replay()
                 sg.pending = False
+                ctx.graph = None             # the loss tensor's autograd node must not keep the captured graphs alive
             else:
                 with torch.no_grad():
                     run_backward(engine, ctx.env, ctx.saved, ctx.mode, dout.float().contiguous(), ws)
