@@ -105,6 +105,13 @@ int b200seg_mbconv(const void* x, const void* w_exp, const float* b_exp, const f
                    const void* w_proj, const float* b_proj, int residual, void* y, int B, int H, int W, int Cin,
                    int Ce, int Cout, int stride, int flags, b200seg_stream_t s);
 
+/* The output tail of MobileNetV2UNet.forward in one kernel, eval mode, bf16 (unet.py:47-49, :108-121, :30):
+ * outconv(32, C) = 1x1 32->16 (+folded BN) + ReLU -> 1x1 16->C + bias, then final_upsample (bilinear x2,
+ * align_corners=True) to NCHW logits (mask == NULL) or to the uint8 argmax mask of inference.py:64 (out == NULL).
+ *   x [B,h,w,32] bf16;  w0 bf16 [16][32], b0 f32 [16];  w3 bf16 [16][16] (rows >= C zero), b3 f32 [16];  C <= 16. */
+int b200seg_tail_fused(const void* x, const void* w0, const float* b0, const void* w3, const float* b3, void* out,
+                       int out_dtype, uint8_t* mask, int B, int h, int w, int C, b200seg_stream_t s);
+
 /* NHWC [B,H,W,ldc] (first C valid) -> NCHW [B,C,H,W] (UNet returns logits at input resolution). */
 int b200seg_nhwc_to_nchw(const void* x, int dtype, int ldc, void* out, int out_dtype, int B, int H, int W,
                          int C, b200seg_stream_t s);

@@ -107,6 +107,7 @@ class Engine:
         self.dense_impl: Optional[str] = None       # None = "tc" for bf16, "simt" for fp32 (tests may force)
         self.dw_impl: Optional[str] = None          # None = per-layer choice; "tc" / "simt" force one kernel
         self.mbconv_impl: Optional[str] = None      # None = per-block choice; "fused" / "unfused" force (eval bf16 only)
+        self.tail_impl: Optional[str] = None        # None = fused outconv + final upsample (+argmax) when it applies; "unfused"
         self.mbconv_flags = 0
         self._eval_sched: Dict[tuple, List[Step]] = {}
         self.tc_flags = 0
@@ -252,9 +253,9 @@ class Engine:
         fused step where the fused kernel is the faster one (measured, tools/kbench_mb.py: every block except the
         stride-2 block at half resolution, whose 4x-larger expanded tile makes the CUDA-core phases dominate)."""
         impl = self.mbconv_impl or "auto"
-        if mode != "bf16" or dense_impl != "tc" or impl == "unfused":
+        if mode != "bf16" or dense_impl != "tc":
             return self.steps
-        key = (impl, H, W)
+        key = (impl, self.tail_impl, H, W)
         if key not in self._eval_sched:
             first = {id(e): (e, d, pj) for e, d, pj in self._mb_triples()}
             out, skip = [], set()
@@ -266,7 +267,7 @@ class Engine:
             for st in self.steps:
                 if id(st) in skip:
                     continue
-                if id(st) in first:
+                if id(st) in first and impl != "unfused":
                     e, d, pj = first[id(st)]
                     in_w = W // max(scale.get(e.src, 1), 1)
                     if impl == "fused" or not (d.stride == 2 and in_w >= 256):
@@ -275,6 +276,12 @@ class Engine:
                         skip.update((id(d), id(pj)))
                         continue
                 out.append(st)
+            # output tail of MobileNetV2UNet: outc.conv.0 -> outc.conv.3 -> final_upsample (+ argmax) as one kernel
+            if (self.tail_impl != "unfused" and len(out) >= 3 and out[-1].op == "final" and self.out_ch <= 16
+                    and out[-2].op == "dense" and out[-3].op == "dense" and out[-2].taps == 1 and out[-3].taps == 1
+                    and tuple(out[-3].conv.weight.shape[:2]) == (16, 32) and out[-2].conv.weight.shape[1] == 16):
+                c0, c3, fin = out[-3], out[-2], out[-1]
+                out = out[:-3] + [Step("tail", "outc+final_upsample", c0.src, fin.dst, parts=(c0, c3, fin))]
             self._eval_sched[key] = out
         return self._eval_sched[key]
 
@@ -331,6 +338,9 @@ class Engine:
             p = pk[s.parts[2].name + "#mb"]
             env[s.dst] = ops.mbconv(env[s.src], p["w_exp"], p["b_exp"], p["w_dw"], p["b_dw"], p["w_proj"], p["b_proj"],
                                     s.stride, s.res is not None, flags=self.mbconv_flags)
+        elif s.op == "tail":
+            p0, p3 = pk[s.parts[0].name], pk[s.parts[1].name]
+            env[s.dst] = ops.tail_fused(env[s.src], p0["w"], p0["b64"], p3["w"], p3["b64"], self.out_ch, out_dtype, want_mask)
         elif s.op == "upcat":
             env[s.dst] = ops.upsample2x_concat(env[s.res], env[s.src])
         elif s.op == "pool":
@@ -373,7 +383,7 @@ class Engine:
         steps = self._schedule(mode, dense_impl, x.shape[2], x.shape[3])
 
         if keep is None and profile is None and self.use_graphs and not torch.cuda.is_current_stream_capturing():
-            key = (tuple(x.shape), x.dtype, mode, dense_impl, self.dw_impl, self.mbconv_impl, self.tc_flags,
+            key = (tuple(x.shape), x.dtype, mode, dense_impl, self.dw_impl, self.mbconv_impl, self.tail_impl, self.tc_flags,
                    self.mbconv_flags, self._packed_key, x.device)
             ent = self._graphs.get(key)
             if ent is None:
@@ -409,7 +419,7 @@ class Engine:
         graph's private pool and stay valid for every replay."""
         pk, mode, sdt, dense_impl, out_dtype, want_mask = args
         head, body, tail = steps[0], steps[1:-1], steps[-1]
-        assert head.op == "stem" and tail.op in ("final", "to_nchw")
+        assert head.op == "stem" and tail.op in ("final", "to_nchw", "tail")
         p = pk[head.name]
         ent["head_args"] = (p["w"], p["b"], head.stride, head.act, sdt)
         ent["head_dst"] = head.dst
@@ -432,6 +442,11 @@ class Engine:
         out = env[s.dst]
         nbytes = out.numel() * out.element_size() + env[s.src].numel() * env[s.src].element_size()
         flops = 0
+        if s.op == "tail":
+            c0, c3, _ = s.parts
+            npix = env[s.src].numel() // env[s.src].shape[-1]
+            nbytes += (c0.conv.weight.numel() + c3.conv.weight.numel()) * 2 + 2 * 16 * 4
+            return nbytes, 2 * npix * (c0.conv.weight.numel() + c3.conv.weight.numel())
         if s.op == "mbconv":
             # algorithmic bytes of the FUSED block: input, output, residual and the three weight sets once
             e, d, pj = s.parts

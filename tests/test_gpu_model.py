@@ -272,3 +272,26 @@ def test_padded_720p_frame_fp32_matches_oracle():
     agree = (y.argmax(1) == ref.argmax(1)).float().mean().item()
     _note("fp32_eval_736x1280", err=e, argmax_agree=agree)
     assert y.shape == (1, 10, 736, 1280) and e < 1e-4 and agree >= 0.999
+
+
+def test_fused_tail_agrees_with_the_three_kernel_tail(model_and_sd):
+    """outc.conv.0 -> outc.conv.3 -> final_upsample as one kernel (default in bf16 eval) against the same three steps
+    launched separately: identical up to the bf16 rounding of the half-resolution logits the unfused path stores."""
+    m, sd = model_and_sd
+    eng = m._get_engine()
+    x = O.synth_input(2, 64, 96, seed=3).to(DEV)
+    eng.precision = "bf16"
+    try:
+        with torch.no_grad():
+            assert eng._schedule("bf16", "tc", 64, 96)[-1].op == "tail"
+            y = eng.forward_eval(x).float()
+            mk = eng.forward_eval(x, want_mask=True)
+            eng.tail_impl = "unfused"
+            assert eng._schedule("bf16", "tc", 64, 96)[-1].op == "final"
+            y_ref = eng.forward_eval(x).float()
+            mk_ref = eng.forward_eval(x, want_mask=True)
+    finally:
+        eng.precision, eng.tail_impl = None, None
+    rng = float(y_ref.max() - y_ref.min())
+    assert float((y - y_ref).abs().max()) / rng < 8e-3
+    assert (mk == mk_ref).float().mean().item() > 0.995

@@ -219,3 +219,38 @@ def test_softmax_ce_fused_forward_and_gradient(B, C, H, W):
     l2 = b200seg.CrossEntropyLoss()(lg, tg)
     l2.backward()
     assert _err(lg.grad, gref) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# fused output tail: outconv(32, C) + final_upsample (+ argmax)  (unet.py:47-49, :108-121; inference.py:64)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,h,w,C", [(2, 16, 32, 10), (1, 24, 40, 1), (3, 48, 80, 16), (1, 368, 640, 10), (2, 16, 16, 7)])
+def test_tail_fused_matches_the_three_ops_it_replaces(B, h, w, C):
+    g = torch.Generator().manual_seed(h * 131 + C)
+    x = torch.randn(B, h, w, 32, generator=g).bfloat16().cuda()
+    w0 = (torch.randn(16, 32, generator=g) * 0.25).bfloat16().cuda()
+    b0 = torch.zeros(64); b0[:16] = torch.randn(16, generator=g) * 0.3
+    w3 = torch.zeros(16, 16); w3[:C] = torch.randn(C, 16, generator=g) * 0.35
+    w3 = w3.bfloat16().cuda()
+    b3 = torch.zeros(64); b3[:C] = torch.randn(C, generator=g) * 0.3
+    b0, b3 = b0.cuda(), b3.cuda()
+    hid = torch.relu(x.double() @ w0.double().t() + b0[:16].double()).bfloat16().double()      # bf16 where the unfused path stored it
+    lg = (hid @ w3.double().t() + b3[:16].double())[..., :C].permute(0, 3, 1, 2)
+    ref = F.interpolate(lg, scale_factor=2, mode="bilinear", align_corners=True)
+    rng = float(ref.max() - ref.min()) + 1e-6
+    y32 = ops.tail_fused(x, w0, b0, w3, b3, C, torch.float32)
+    assert y32.shape == (B, C, 2 * h, 2 * w)
+    # the hidden activation is rounded to bf16 from an fp32 accumulator here and from float64 in the reference: on large
+    # tensors a few values sit on a rounding boundary and flip by one bf16 ulp (-> ~1e-3 of a logit); everything else agrees
+    # to fp32 rounding
+    d = (y32.double() - ref).abs().flatten() / rng
+    assert float(d.max()) < 2e-3
+    assert float(torch.quantile(d[:: max(1, d.numel() // 1000000)], 0.999)) < 2e-5
+    y16 = ops.tail_fused(x, w0, b0, w3, b3, C, torch.bfloat16)
+    assert float((y16.double() - ref).abs().max()) / rng < 5e-3
+    mask = ops.tail_fused(x, w0, b0, w3, b3, C, want_mask=True)
+    assert mask.dtype == torch.uint8 and mask.shape == (B, 2 * h, 2 * w)
+    am = ref.argmax(1)
+    top2 = ref.topk(min(2, C), dim=1).values
+    tie = (top2[:, 0] - top2[:, -1]).abs() < 1e-4 * rng if C > 1 else torch.zeros_like(am, dtype=torch.bool)
+    assert bool(((mask.long() == am) | tie).all())
