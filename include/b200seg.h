@@ -52,6 +52,12 @@ int b200seg_conv3x3_smallcin(const void* x, int x_dtype, const float* w, const f
 int b200seg_dwconv3x3(const void* x, const float* w, const float* b, void* y, int dtype, int B, int H,
                       int W, int C, int stride, int act, b200seg_stream_t s);
 
+/* Same operator for bf16 activations with bf16 taps w [9][C]: the stencil runs on the sm_100a mixed-precision FMA
+ * (f32 += bf16 * bf16 read from either half of a packed register), so no unpack instructions are issued; results equal
+ * b200seg_dwconv3x3 for bf16-representable taps.  variant: register-blocking choice (0 = default). */
+int b200seg_dwconv3x3_bf16w(const void* x, const void* w, const float* b, void* y, int B, int H, int W, int C, int stride,
+                            int act, int variant, b200seg_stream_t s);
+
 /* Dense convolution on the 5th-gen tensor cores: TMA -> smem ring -> tcgen05.mma -> TMEM ->
  * epilogue(bias, act, +residual) -> TMA store.  bf16 in / fp32 accumulate / bf16 out.
  * taps = 1 (pointwise, mobilenetv2.py:38,53; unet.py:113,116) or 9 (3x3 pad 1 stride 1, unet.py:58,61).
@@ -99,9 +105,10 @@ int b200seg_upsample2x_ac_argmax(const void* logits, int dtype, int ldc, uint8_t
  * project, + x when stride 1 and Cin == Cout; reached through unet.py:15-19,34-42).  The expanded activation
  * stays in shared memory / TMEM.
  *   x [B,H,W,Cin] bf16;  w_exp [Ce][Cin] bf16;  w_proj [Cout][Ce] bf16;  y [B,Ho,Wo,Cout] bf16
- *   b_exp, b_dw: f32 [ceil64(Ce)] zero padded;  w_dw: f32 [9][ceil64(Ce)] zero padded;  b_proj: f32 [ceil16(Cout)]
+ *   b_exp, b_dw: f32 [ceil64(Ce)] zero padded;  w_dw: bf16 [9][ceil64(Ce)] zero padded (the stencil runs on the
+ *   mixed-precision FMA, f32 += bf16 * bf16);  b_proj: f32 [ceil16(Cout)]
  *   flags: tuning only (0 = heuristics). */
-int b200seg_mbconv(const void* x, const void* w_exp, const float* b_exp, const float* w_dw, const float* b_dw,
+int b200seg_mbconv(const void* x, const void* w_exp, const float* b_exp, const void* w_dw, const float* b_dw,
                    const void* w_proj, const float* b_proj, int residual, void* y, int B, int H, int W, int Cin,
                    int Ce, int Cout, int stride, int flags, b200seg_stream_t s);
 

@@ -195,10 +195,13 @@ class Engine:
                     wdiag = torch.zeros(cout, kk, 64, device=dev, dtype=torch.bfloat16)
                     add_row(s, wdiag, None, 4, 0)
                     packed[s.name]["wdiag"] = wdiag
-                    w64 = ow
+                    wb = torch.zeros(kk, cout, device=dev, dtype=torch.bfloat16)      # bf16 taps (mixed-precision FMA kernels)
+                    add_row(s, wb, None, 5, cout)
+                    packed[s.name]["wb"] = wb
+                    w64 = wb                                                          # ... zero padded to 64-channel chunks
                     if cep != cout:
-                        w64 = torch.zeros(kk, cep, device=dev, dtype=torch.float32)
-                        add_row(s, w64, None, 3, cep)
+                        w64 = torch.zeros(kk, cep, device=dev, dtype=torch.bfloat16)
+                        add_row(s, w64, None, 5, cep)
                     packed[s.name]["w64"] = w64
             else:
                 cp = max(cout, s.pad_cout) if s.pad_cout else cout
@@ -250,8 +253,7 @@ class Engine:
 
     def _schedule(self, mode: str, dense_impl: str, H: int, W: int) -> List[Step]:
         """Eval schedule for an input of H x W: self.steps with the inverted-residual triples replaced by one
-        fused step where the fused kernel is the faster one (measured, tools/kbench_mb.py: every block except the
-        stride-2 block at half resolution, whose 4x-larger expanded tile makes the CUDA-core phases dominate)."""
+        fused step (measured faster for every block, tools/kbench_mb.py), and the output tail by its fused kernel."""
         impl = self.mbconv_impl or "auto"
         if mode != "bf16" or dense_impl != "tc":
             return self.steps
@@ -270,7 +272,9 @@ class Engine:
                 if id(st) in first and impl != "unfused":
                     e, d, pj = first[id(st)]
                     in_w = W // max(scale.get(e.src, 1), 1)
-                    if impl == "fused" or not (d.stride == 2 and in_w >= 256):
+                    # every expand-ratio-6 block is faster fused since the depthwise stencil runs on the mixed-precision FMA
+                    # (tools/kbench_mb.py; before, the stride-2 block at half resolution was 5 % slower fused)
+                    if impl in ("fused", "auto") or in_w < 0:
                         out.append(Step("mbconv", pj.name.rsplit(".conv.", 1)[0], e.src, pj.dst, stride=d.stride,
                                         res=pj.res, parts=(e, d, pj)))
                         skip.update((id(d), id(pj)))
@@ -320,11 +324,12 @@ class Engine:
             env[s.dst] = ops.conv3x3_smallcin(env[s.src], p["w"], p["b"], s.stride, s.act, sdt)
         elif s.op == "dw":
             p = pk[s.name]
-            # tensor-core depthwise wins only where HALO addressing applies (stride 1, rows >= 96 px);
-            # elsewhere the register-blocked SIMT kernel is faster (tools/kbench.py)
-            use_tc = self.dw_impl == "tc" or (self.dw_impl is None and s.stride == 1 and env[s.src].shape[2] >= 96)
-            if mode == "bf16" and use_tc:
+            if mode == "bf16" and self.dw_impl == "tc":
                 env[s.dst] = ops.dwconv3x3_tc(env[s.src], p["wdiag"], p["b"], s.stride, s.act, flags=self.tc_flags)
+            elif mode == "bf16" and self.dw_impl != "simt":
+                # bf16 taps + mixed-precision FMA (FHFMA.BF16): 15-25 % faster than the f32-tap kernel on stride 1 and faster
+                # than the block-diagonal tensor-core variant on every layer of this net (tools/kbench_dw.py)
+                env[s.dst] = ops.dwconv3x3_bf16w(env[s.src], p["wb"], p["b"], s.stride, s.act)
             else:
                 env[s.dst] = ops.dwconv3x3(env[s.src], p["w"], p["b"], s.stride, s.act)
         elif s.op == "dense":

@@ -76,6 +76,22 @@ def dwconv3x3(x, w9c, b, stride: int, act: int, out=None):
     return out
 
 
+def dwconv3x3_bf16w(x, w9c_bf16, b, stride: int, act: int, out=None, variant: int = 0):
+    """Depthwise 3x3 on bf16 activations with bf16 taps [9,C] (mixed-precision FMA, no unpack instructions)."""
+    _cuda(x, w9c_bf16, b)
+    if x.dtype != torch.bfloat16 or w9c_bf16.dtype != torch.bfloat16:
+        raise TypeError("dwconv3x3_bf16w is bf16-only")
+    B, H, W, Cc = x.shape
+    if tuple(w9c_bf16.shape) != (9, Cc):
+        raise ValueError(f"dwconv3x3_bf16w: taps {tuple(w9c_bf16.shape)} != (9, {Cc})")
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    if out is None:
+        out = torch.empty((B, Ho, Wo, Cc), device=x.device, dtype=torch.bfloat16)
+    check(lib.b200seg_dwconv3x3_bf16w(ptr(x), ptr(w9c_bf16), ptr(b), ptr(out), B, H, W, Cc, stride, act, variant, _stream()),
+          "dwconv3x3_bf16w")
+    return out
+
+
 def pack_dw_diag(w9c: torch.Tensor) -> torch.Tensor:
     """f32 [9, C] depthwise taps -> block-diagonal bf16 [C, 9, 64] for dwconv3x3_tc."""
     C = w9c.shape[1]
@@ -146,11 +162,11 @@ def pad_channels(t: torch.Tensor, mult: int) -> torch.Tensor:
 
 def mbconv(x, w_exp, b_exp, w_dw, b_dw, w_proj, b_proj, stride: int, residual: bool, out=None, flags: int = 0):
     """Fused inverted-residual block (expand 1x1 + ReLU6 -> depthwise 3x3 + ReLU6 -> project 1x1 [+ x]), bf16 NHWC.
-    w_exp [Ce, Cin] bf16, w_proj [Cout, Ce] bf16; b_exp/b_dw f32 [ceil64(Ce)], w_dw f32 [9, ceil64(Ce)],
+    w_exp [Ce, Cin] bf16, w_proj [Cout, Ce] bf16; b_exp/b_dw f32 [ceil64(Ce)], w_dw bf16 [9, ceil64(Ce)],
     b_proj f32 [ceil16(Cout)] (see pad_channels)."""
     _cuda(x, w_exp, b_exp, w_dw, b_dw, w_proj, b_proj)
-    if x.dtype != torch.bfloat16 or w_exp.dtype != torch.bfloat16 or w_proj.dtype != torch.bfloat16:
-        raise TypeError("mbconv is bf16-only")
+    if x.dtype != torch.bfloat16 or w_exp.dtype != torch.bfloat16 or w_proj.dtype != torch.bfloat16 or w_dw.dtype != torch.bfloat16:
+        raise TypeError("mbconv is bf16-only (activations, 1x1 weights and depthwise taps)")
     B, H, W, Cin = x.shape
     Ce, Cout = w_exp.shape[0], w_proj.shape[0]
     cep, cop = (Ce + 63) // 64 * 64, (Cout + 15) // 16 * 16

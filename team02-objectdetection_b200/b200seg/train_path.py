@@ -74,6 +74,7 @@ def _train_packs(engine, tc: bool):
         rows, views, ct, ci = [], {}, [], []
         n16 = n32 = 0
         metas = []
+        dw16 = [s for s in convs if s.op == "dw"] if tc else []      # bf16 taps for the mixed-precision-FMA depthwise kernel
         for s in convs:
             w = s.conv.weight
             if not w.is_contiguous() or w.dtype != torch.float32:
@@ -89,6 +90,9 @@ def _train_packs(engine, tc: bool):
                 cp = max(cout, s.pad_cout) if s.pad_cout else cout
                 nf = nd = cp * kk * cin
             metas.append((s, kind, cout, cin, kk, cp, nf, nd))
+            if s in dw16:
+                metas.append((s, 4, cout, cin, kk, cp, nf, nd))
+                n16 += 2 * ((nf + 7) // 8 * 8)
             if kind == 0:
                 n16 += (nf + 7) // 8 * 8 + (nd + 7) // 8 * 8
             else:
@@ -97,7 +101,7 @@ def _train_packs(engine, tc: bool):
         buf32 = torch.zeros(max(n32, 4), device=dev, dtype=torch.float32)
         o16 = o32 = 0
         for ti, (s, kind, cout, cin, kk, cp, nf, nd) in enumerate(metas):
-            if kind == 0:
+            if kind in (0, 4):
                 fwd = buf16[o16:o16 + nf]; o16 += (nf + 7) // 8 * 8
                 dg = buf16[o16:o16 + nd]; o16 += (nd + 7) // 8 * 8
             else:
@@ -105,6 +109,8 @@ def _train_packs(engine, tc: bool):
                 dg = buf32[o32:o32 + nd] if nd else None; o32 += (nd + 3) // 4 * 4
             if s.op == "stem":
                 views[s.name] = dict(wp=fwd.view(s.conv.weight.shape[2], s.conv.weight.shape[3], cin, cout))
+            elif s.op == "dw" and kind == 4:
+                views[s.name].update(wb=fwd.view(kk, cout), wbf=dg.view(kk, cout))
             elif s.op == "dw":
                 views[s.name] = dict(wp=fwd.view(kk, cout), wpf=dg.view(kk, cout))
             else:
@@ -267,7 +273,11 @@ def run_forward(engine, x: torch.Tensor, mode: str):
                 z = ops.conv3x3_smallcin(src, rec["wp"], bias, s.stride, ACT_NONE, sdt)
             elif s.op == "dw":
                 rec["wp"], rec["wpf"] = pk["wp"], pk["wpf"]
-                z = ops.dwconv3x3(src, rec["wp"], bias, s.stride, ACT_NONE)
+                if "wb" in pk:          # bf16 activations: mixed-precision-FMA kernel with bf16 taps
+                    rec["wbf"] = pk["wbf"]
+                    z = ops.dwconv3x3_bf16w(src, pk["wb"], bias, s.stride, ACT_NONE)
+                else:
+                    z = ops.dwconv3x3(src, rec["wp"], bias, s.stride, ACT_NONE)
             else:
                 if s.pad_cout and cout < s.pad_cout and bias is not None:
                     bias = torch.cat([bias, bias.new_zeros(s.pad_cout - cout)], 0)
@@ -356,7 +366,10 @@ def run_backward(engine, env, saved, mode: str, dout: torch.Tensor, ws: TrainWor
                 if s.stride == 1 and g.get(s.src) is None:
                     # stride 1: the data gradient IS the forward depthwise conv of dz with the taps flipped -> the
                     # register-blocked forward kernel (2.5x faster than the generic gather kernel)
-                    g[s.src] = ops.dwconv3x3(dz, rec["wpf"], None, 1, ACT_NONE)
+                    if "wbf" in rec:
+                        g[s.src] = ops.dwconv3x3_bf16w(dz, rec["wbf"], None, 1, ACT_NONE)
+                    else:
+                        g[s.src] = ops.dwconv3x3(dz, rec["wpf"], None, 1, ACT_NONE)
                 else:
                     g[s.src] = ops.dw_dgrad(dz, rec["wp"], tuple(src.shape), s.stride, g.get(s.src))
             else:

@@ -89,6 +89,7 @@ extern "C" int b200seg_adam_chunk(void) { return ADAM_CHUNK; }
 //           (the transposed, tap-flipped weights of the data gradient)
 //   kind 1  dense, fp32 path: the same two layouts in f32
 //   kind 2  stem: f32 [kh][kw][Cin][Cout]          kind 3  depthwise: f32 [9][C] (+ the tap-flipped [9][C] for the data gradient)
+//   kind 4  depthwise: bf16 [9][C] + tap-flipped bf16 [9][C]
 // One thread per element of the padded OIHW tensor (coalesced reads; rows >= Cout are written as zeros).
 // ---------------------------------------------------------------------------------------------------------------
 namespace b200 {
@@ -122,10 +123,13 @@ pack_weights_kernel(const PackEntry* __restrict__ table, const int* __restrict__
       reinterpret_cast<float*>(t.dgrad)[((long long)i * t.kk + (t.kk - 1 - tap)) * t.cout_pad + o] = v;
     } else if (t.kind == 2) {
       reinterpret_cast<float*>(t.fwd)[((long long)tap * t.cin + i) * t.cout + o] = v;
-    } else {
+    } else if (t.kind == 3) {
       reinterpret_cast<float*>(t.fwd)[(long long)tap * t.cout + o] = v;
       // tap-flipped twin: the stride-1 data gradient of a depthwise conv is the same depthwise conv with flipped taps
       if (t.dgrad) reinterpret_cast<float*>(t.dgrad)[(long long)(t.kk - 1 - tap) * t.cout + o] = v;
+    } else {   // kind 4: the same two depthwise layouts in bf16 (taps of the mixed-precision-FMA kernel)
+      reinterpret_cast<__nv_bfloat16*>(t.fwd)[(long long)tap * t.cout + o] = __float2bfloat16_rn(v);
+      if (t.dgrad) reinterpret_cast<__nv_bfloat16*>(t.dgrad)[(long long)(t.kk - 1 - tap) * t.cout + o] = __float2bfloat16_rn(v);
     }
   }
 }

@@ -244,6 +244,21 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
+// sm_100a mixed-precision FMA (SASS FHFMA.BF16, full FP32-pipe rate, measured in tools/fhfma_probe.cu): c + a.half * b.half
+// with both bf16 operands taken straight from either half of a packed register -- no bf16 -> f32 unpack instructions.
+__device__ __forceinline__ float fma_bf16_lo(uint32_t a, uint32_t b, float c) {
+  float d;
+  asm("{.reg .b16 al, ah, bl, bh; mov.b32 {al, ah}, %1; mov.b32 {bl, bh}, %2; fma.rn.f32.bf16 %0, al, bl, %3;}"
+      : "=f"(d) : "r"(a), "r"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float fma_bf16_hi(uint32_t a, uint32_t b, float c) {
+  float d;
+  asm("{.reg .b16 al, ah, bl, bh; mov.b32 {al, ah}, %1; mov.b32 {bl, bh}, %2; fma.rn.f32.bf16 %0, ah, bh, %3;}"
+      : "=f"(d) : "r"(a), "r"(b), "f"(c));
+  return d;
+}
+
 // A 16-byte vector of activations in storage type T, viewed as floats.
 template <typename T>
 struct Vec16;

@@ -413,6 +413,96 @@ dwconv3x3_bf16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restri
   }
 }
 
+// Same blocking with bf16 taps and the mixed-precision FMA (FHFMA.BF16: f32 += bf16 * bf16 from either register half):
+// no unpack of the activations, the nine tap vectors of the thread's 8 channels stay in 36 registers for the whole tile.
+// Arithmetic is identical to the f32-tap kernel for bf16-representable taps (products of two bf16 are exact in f32).
+template <int S, int TW, int TH>
+__global__ void __launch_bounds__(256, 2)
+dwconv3x3_bf16w_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
+                       __nv_bfloat16* __restrict__ y, int B, int H, int W, int C, int Ho, int Wo, int act) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int NCOL = (TW - 1) * S + 3, NROW = (TH - 1) * S + 3;
+  const int cv = C >> 3;
+  const int sw_ = (Wo + TW - 1) / TW, sh_ = (Ho + TH - 1) / TH;
+  const long long total = (long long)B * sh_ * sw_ * cv;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c0 = (int)(idx % cv) << 3;
+  long long p = idx / cv;
+  const int tw = (int)(p % sw_); p /= sw_;
+  const int th = (int)(p % sh_);
+  const int b = (int)(p / sh_);
+  const int wo0 = tw * TW, ho0 = th * TH;
+  const int wi0 = wo0 * S - 1, hi0 = ho0 * S - 1;
+  const float lo = act != B200SEG_ACT_NONE ? 0.f : -INFINITY, hi_ = act == B200SEG_ACT_RELU6 ? 6.f : INFINITY;
+
+  uint4 wt[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) wt[k] = __ldg(reinterpret_cast<const uint4*>(w + (long long)k * C + c0));
+  float acc[TH][TW][8];
+  {
+    const float4 b0 = bias ? __ldg(reinterpret_cast<const float4*>(bias + c0)) : make_float4(0, 0, 0, 0);
+    const float4 b1 = bias ? __ldg(reinterpret_cast<const float4*>(bias + c0 + 4)) : make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int o = 0; o < TH; ++o)
+#pragma unroll
+      for (int t = 0; t < TW; ++t) {
+        acc[o][t][0] = b0.x; acc[o][t][1] = b0.y; acc[o][t][2] = b0.z; acc[o][t][3] = b0.w;
+        acc[o][t][4] = b1.x; acc[o][t][5] = b1.y; acc[o][t][6] = b1.z; acc[o][t][7] = b1.w;
+      }
+  }
+  const __nv_bfloat16* xb = x + (long long)b * H * W * C + c0;
+#pragma unroll
+  for (int r = 0; r < NROW; ++r) {
+    const int hi = hi0 + r;
+    if (hi < 0 || hi >= H) continue;            // zero padding row: contributes nothing
+    const __nv_bfloat16* row = xb + (long long)hi * W * C;
+    uint4 raw[NCOL];
+#pragma unroll
+    for (int i = 0; i < NCOL; ++i) {
+      const int wi = wi0 + i;
+      raw[i] = (wi >= 0 && wi < W) ? __ldg(reinterpret_cast<const uint4*>(row + (long long)wi * C)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int o = 0; o < TH; ++o) {
+      const int kh = r - o * S;                 // compile-time after unrolling
+      if (kh < 0 || kh > 2) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const uint4 wv = wt[kh * 3 + kw];
+#pragma unroll
+        for (int t = 0; t < TW; ++t) {
+          const uint4 xv = raw[t * S + kw];
+          float* a = acc[o][t];
+          a[0] = fma_bf16_lo(xv.x, wv.x, a[0]); a[1] = fma_bf16_hi(xv.x, wv.x, a[1]);
+          a[2] = fma_bf16_lo(xv.y, wv.y, a[2]); a[3] = fma_bf16_hi(xv.y, wv.y, a[3]);
+          a[4] = fma_bf16_lo(xv.z, wv.z, a[4]); a[5] = fma_bf16_hi(xv.z, wv.z, a[5]);
+          a[6] = fma_bf16_lo(xv.w, wv.w, a[6]); a[7] = fma_bf16_hi(xv.w, wv.w, a[7]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < TH; ++o) {
+    const int ho = ho0 + o;
+    if (ho >= Ho) continue;
+    __nv_bfloat16* yrow = y + (((long long)b * Ho + ho) * Wo) * C + c0;
+#pragma unroll
+    for (int t = 0; t < TW; ++t) {
+      const int wo = wo0 + t;
+      if (wo >= Wo) continue;
+      float* a = acc[o][t];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = fminf(fmaxf(a[j], lo), hi_);
+      uint4 v;
+      v.x = pack_bf16x2(a[0], a[1]); v.y = pack_bf16x2(a[2], a[3]);
+      v.z = pack_bf16x2(a[4], a[5]); v.w = pack_bf16x2(a[6], a[7]);
+      *reinterpret_cast<uint4*>(yrow + (long long)wo * C) = v;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // y[b,ho,wo,0:Cs] = skip ; y[b,ho,wo,Cs:] = bilinear x2 (align_corners=False) of x.
 // One thread = one 16-byte channel vector of a 2x2 block of output pixels: the 3x3 source
@@ -719,6 +809,29 @@ int b200seg_dwconv3x3(const void* x, const float* w, const float* b, void* y, in
   }
 #undef LAUNCH
   return check_launch("dwconv3x3");
+}
+
+int b200seg_dwconv3x3_bf16w(const void* x, const void* w, const float* b, void* y, int B, int H, int W, int C, int stride,
+                            int act, int variant, b200seg_stream_t s) {
+  B200_REQUIRE(C > 0 && C % 8 == 0, "dwconv3x3_bf16w: C=%d must be a positive multiple of 8", C);
+  B200_REQUIRE(stride == 1 || stride == 2, "dwconv3x3_bf16w: stride=%d", stride);
+  B200_REQUIRE(B > 0 && H > 0 && W > 0 && x && w && y, "dwconv3x3_bf16w: bad arguments");
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  cudaStream_t st = (cudaStream_t)s;
+  const int threads = 256;
+#define LAUNCHW(S, TW, TH)                                                                                        \
+  {                                                                                                               \
+    const long long total = (long long)B * ((Ho + TH - 1) / TH) * ((Wo + TW - 1) / TW) * (C / 8);                 \
+    launch_pdl(dwconv3x3_bf16w_kernel<S, TW, TH>, dim3((unsigned)grid_for(total, threads)), dim3((unsigned)threads), (size_t)0, st, (const bf16*)x, (const bf16*)w, b, (bf16*)y, \
+               B, H, W, C, Ho, Wo, act);                                                                          \
+  }
+  if (stride == 1) {
+    if (variant == 1) LAUNCHW(1, 4, 1) else if (variant == 2) LAUNCHW(1, 2, 2) else if (variant == 3) LAUNCHW(1, 4, 4) else LAUNCHW(1, 4, 2)
+  } else {
+    if (variant == 1) LAUNCHW(2, 2, 1) else if (variant == 2) LAUNCHW(2, 2, 2) else if (variant == 3) LAUNCHW(2, 4, 2) else LAUNCHW(2, 4, 1)
+  }
+#undef LAUNCHW
+  return check_launch("dwconv3x3_bf16w");
 }
 
 int b200seg_upsample2x_concat(const void* skip, const void* x, void* y, int dtype, int B, int h, int w, int Cs,

@@ -33,7 +33,7 @@ struct MbArgs {
   const __nv_bfloat16* x;    // [B][H][W][Cin]
   __nv_bfloat16* y;          // [B][Ho][Wo][Cout]
   const float* b_exp;        // [ce_chunks*64]
-  const float* w_dw;         // [9][ce_chunks*64]
+  const __nv_bfloat16* w_dw; // [9][ce_chunks*64] bf16 taps (mixed-precision FMA: f32 += bf16 * bf16, no unpack)
   const float* b_dw;         // [ce_chunks*64]
   const float* b_proj;       // [cout_pad]
   int B, H, W, Ho, Wo, Cin, Ce, Cout;
@@ -127,28 +127,24 @@ __device__ __forceinline__ void dw_chunk(const uint8_t* __restrict__ sE, uint8_t
   }
 #pragma unroll
   for (int dh = 0; dh < 3; ++dh) {
-    float wt[3][8];
+    uint4 wt[3];
 #pragma unroll
-    for (int dw = 0; dw < 3; ++dw) {
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.w_dw + (dh * 3 + dw) * cstride + cbase));
-      const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.w_dw + (dh * 3 + dw) * cstride + cbase + 4));
-      wt[dw][0] = w0.x; wt[dw][1] = w0.y; wt[dw][2] = w0.z; wt[dw][3] = w0.w;
-      wt[dw][4] = w1.x; wt[dw][5] = w1.y; wt[dw][6] = w1.z; wt[dw][7] = w1.w;
-    }
+    for (int dw = 0; dw < 3; ++dw) wt[dw] = __ldg(reinterpret_cast<const uint4*>(a.w_dw + (dh * 3 + dw) * cstride + cbase));
     const int prow0 = (orow * S + dh) * IW + ocol0 * S;
 #pragma unroll
     for (int j = 0; j < NCOL; ++j) {
       const int pr = prow0 + j;
       const uint4 t = *reinterpret_cast<const uint4*>(sE + pr * 128 + ((g ^ (pr & 7)) << 4));
-      float v[8];
-      v[0] = bf16lo(t.x); v[1] = bf16hi(t.x); v[2] = bf16lo(t.y); v[3] = bf16hi(t.y);
-      v[4] = bf16lo(t.z); v[5] = bf16hi(t.z); v[6] = bf16lo(t.w); v[7] = bf16hi(t.w);
 #pragma unroll
       for (int o = 0; o < PXT; ++o) {
         const int dw = j - o * S;                 // compile-time after unrolling
         if (dw >= 0 && dw < 3) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[o][i] = fmaf(v[i], wt[dw][i], acc[o][i]);
+          const uint4 wv = wt[dw];
+          float* ac = acc[o];
+          ac[0] = fma_bf16_lo(t.x, wv.x, ac[0]); ac[1] = fma_bf16_hi(t.x, wv.x, ac[1]);
+          ac[2] = fma_bf16_lo(t.y, wv.y, ac[2]); ac[3] = fma_bf16_hi(t.y, wv.y, ac[3]);
+          ac[4] = fma_bf16_lo(t.z, wv.z, ac[4]); ac[5] = fma_bf16_hi(t.z, wv.z, ac[5]);
+          ac[6] = fma_bf16_lo(t.w, wv.w, ac[6]); ac[7] = fma_bf16_hi(t.w, wv.w, ac[7]);
         }
       }
     }
@@ -458,7 +454,7 @@ using namespace b200;
 
 // flags: bits 0-1 expand accumulator buffers (0 = auto), bits 2-3 D buffers, bits 4-5 weight stages,
 //        bits 6-7 CTAs per SM (1 = force one), bits 8-15 grid/4, bits 16-17 stride-1 tile rows (1 = 8, 2 = 4)
-extern "C" int b200seg_mbconv(const void* x, const void* w_exp, const float* b_exp, const float* w_dw,
+extern "C" int b200seg_mbconv(const void* x, const void* w_exp, const float* b_exp, const void* w_dw,
                               const float* b_dw, const void* w_proj, const float* b_proj, int residual, void* y,
                               int B, int H, int W, int Cin, int Ce, int Cout, int stride, int flags,
                               b200seg_stream_t s) {
@@ -471,7 +467,7 @@ extern "C" int b200seg_mbconv(const void* x, const void* w_exp, const float* b_e
   B200_REQUIRE(!residual || (stride == 1 && Cin == Cout), "mbconv: residual needs stride 1 and Cin == Cout");
   MbArgs a;
   a.x = (const __nv_bfloat16*)x; a.y = (__nv_bfloat16*)y;
-  a.b_exp = b_exp; a.w_dw = w_dw; a.b_dw = b_dw; a.b_proj = b_proj;
+  a.b_exp = b_exp; a.w_dw = reinterpret_cast<const __nv_bfloat16*>(w_dw); a.b_dw = b_dw; a.b_proj = b_proj;
   a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Ce = Ce; a.Cout = Cout; a.stride = stride; a.residual = residual;
   a.Ho = (H - 1) / stride + 1; a.Wo = (W - 1) / stride + 1;          // k=3, pad=1
   a.TW = 16; a.TH = stride == 1 ? 8 : 4;

@@ -24,7 +24,7 @@ def _case(B, H, W, Cin, Ce, Cout, stride, residual, seed=0):
     x = _rand(B, H, W, Cin, seed=seed + 1).bfloat16()
     we = _rand(Ce, Cin, seed=seed + 2, scale=(2.0 / Cin) ** 0.5).bfloat16()
     be = _rand(Ce, seed=seed + 3, scale=0.3)
-    wd = _rand(9, Ce, seed=seed + 4, scale=0.4)
+    wd = _rand(9, Ce, seed=seed + 4, scale=0.4).bfloat16().float()      # bf16-representable taps (the kernel reads bf16)
     bd = _rand(Ce, seed=seed + 5, scale=0.3)
     wp = _rand(Cout, Ce, seed=seed + 6, scale=(1.0 / Ce) ** 0.5).bfloat16()
     bp = _rand(Cout, seed=seed + 7, scale=0.2)
@@ -44,7 +44,7 @@ def _reference(x, we, be, wd, bd, wp, bp, stride, residual):
 
 
 def _run(x, we, be, wd, bd, wp, bp, stride, residual, flags=0):
-    return ops.mbconv(x, we, ops.pad_channels(be, 64), ops.pad_channels(wd, 64), ops.pad_channels(bd, 64), wp,
+    return ops.mbconv(x, we, ops.pad_channels(be, 64), ops.pad_channels(wd.bfloat16(), 64), ops.pad_channels(bd, 64), wp,
                       ops.pad_channels(bp, 16), stride, residual, flags=flags)
 
 
@@ -102,4 +102,6 @@ def test_mbconv_rejects_bad_arguments():
     with pytest.raises(RuntimeError):
         _run(x, we, be, wd, bd, wp, bp, 1, True)                  # residual with Cin != Cout
     with pytest.raises((ValueError, RuntimeError)):
-        ops.mbconv(x, we, be, wd, bd, wp, bp, 1, False)           # unpadded parameter vectors
+        ops.mbconv(x, we, be, wd.bfloat16(), bd, wp, bp, 1, False)   # unpadded parameter vectors
+    with pytest.raises(TypeError):
+        _run(x, we, be, wd, bd, wp.float(), bp, 1, False)         # f32 weights

@@ -67,6 +67,23 @@ def test_dwconv3x3(dt, B, H, W, C, stride):
     assert _err(_nchw(got), ref) < TOL[dt]
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("B,H,W,C,stride", [(2, 128, 256, 32, 1), (2, 128, 256, 96, 2), (1, 64, 128, 144, 1),
+                                            (2, 16, 32, 576, 2), (3, 8, 16, 960, 1), (1, 7, 9, 24, 1), (1, 9, 7, 8, 2),
+                                            (1, 1, 1, 16, 1), (1, 23, 40, 192, 2)])
+def test_dwconv3x3_bf16_taps_mixed_precision_fma(variant, B, H, W, C, stride):
+    """bf16 activations x bf16 taps on the mixed-precision FMA: equals the float64 convolution of the same bf16 operands up
+    to fp32 accumulation + the output rounding, and equals the f32-tap kernel BIT FOR BIT (bf16 products are exact in f32)."""
+    x = _rand(B, C, H, W, seed=4).bfloat16()
+    w = _rand(C, 1, 3, 3, seed=5, scale=0.4).bfloat16()
+    b = _rand(C, seed=6, scale=0.1)
+    ref = torch.clamp(F.conv2d(x.double(), w.double(), b.double(), stride, 1, 1, C), 0, 6)
+    w9c = w.reshape(C, 9).t().contiguous()
+    got = ops.dwconv3x3_bf16w(_nhwc(x), w9c, b, stride, 2, variant=variant)
+    assert _err(_nchw(got), ref) < TOL[torch.bfloat16]
+    assert torch.equal(got, ops.dwconv3x3(_nhwc(x), w9c.float(), b, stride, 2))
+
+
 @pytest.mark.parametrize("flags", [0, 2], ids=["auto", "tap_mode"])
 @pytest.mark.parametrize("B,H,W,C,stride", [(2, 128, 256, 32, 1), (1, 128, 256, 96, 2), (1, 64, 128, 144, 1),
                                             (2, 16, 32, 576, 2), (3, 8, 16, 960, 1), (1, 7, 9, 24, 1), (1, 9, 7, 8, 2),

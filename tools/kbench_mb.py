@@ -59,7 +59,7 @@ for name, H, W, Cin, Ce, Cout, st in BLOCKS:
             ops.dwconv3x3(e, wd, bd, st, 2, out=d)
         ops.conv_tc(d, wp, bp, 1, 0, x if res else None, out=y)
 
-    pe, pwd, pbd, pbp = ops.pad_channels(be, 64), ops.pad_channels(wd, 64), ops.pad_channels(bd, 64), ops.pad_channels(bp, 16)
+    pe, pwd, pbd, pbp = ops.pad_channels(be, 64), ops.pad_channels(wd.bfloat16(), 64), ops.pad_channels(bd, 64), ops.pad_channels(bp, 16)
     y2 = torch.empty_like(y)
     us_u = timeit(unfused)
     tot_u += us_u
