@@ -154,6 +154,10 @@ __global__ void bn_finalize_kernel(const T* __restrict__ z0, const double* __res
   }
 }
 
+// "Last block done" epilogue of a cross-CTA reduction: every block fences its atomics and takes a ticket; the block that
+// draws the last ticket sees all partial sums (read through L2) and finishes the reduction in the same launch -- the tiny
+// finalize / f64->f32 kernels that used to follow each of the 61 BatchNorm reductions (5-6 us of launch + dependency latency
+// each, twice per layer per step) disappear.  `counter` is a zeroed 32-bit word per reduction.
 // a = act(z * scale + shift) (+ residual).  Thread = one channel vector x several pixels (same (tx, ty) layout as the
 // reductions): the per-channel constants are loaded once per thread instead of once per element.
 template <typename T>
@@ -515,6 +519,87 @@ dw_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dz, int B, int H,
       double* dst = dw + ((long long)(blockIdx.x % nslot) * 9 + o) * C + c0;      // one of nslot copies (see channel_reduce)
 #pragma unroll
       for (int j = 0; j < VN; ++j) atomicAdd(dst + j, (double)red[threadIdx.x][j]);
+    }
+  }
+}
+
+// bf16 specialisation: a thread owns PW consecutive output pixels of one row x 8 channels.  The 3 x ((PW-1)S+3) input
+// vectors they touch are loaded once (instead of 9 per pixel) and both operands stay packed bf16: every product goes through
+// the mixed-precision FMA (f32 += bf16 * bf16, exact product), so the loop has no unpack instructions at all.
+template <int S, int PW>
+__global__ void __launch_bounds__(256, 2)
+dw_wgrad_bf16_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dz, int B, int H, int W, int C,
+                     int Ho, int Wo, int gpb /* pixel groups per block */, double* dw /* [nslot][9][C] */, int nslot) {
+  constexpr int NCOL = (PW - 1) * S + 3;
+  const int TX = blockDim.x, TY = blockDim.y;
+  const int c0 = (blockIdx.y * TX + threadIdx.x) * 8;
+  const bool active = c0 < C;
+  const int gw = (Wo + PW - 1) / PW;                       // pixel groups per output row
+  const long long G = (long long)B * Ho * gw;
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+  const long long g0 = (long long)blockIdx.x * gpb, g1 = min(g0 + gpb, G);
+  if (active) {
+    const long long rowC = (long long)W * C;
+    for (long long gi = g0 + threadIdx.y; gi < g1; gi += TY) {
+      const int gx = (int)(gi % gw);
+      const long long t_ = gi / gw;
+      const int ho = (int)(t_ % Ho), b = (int)(t_ / Ho);
+      const int wo0 = gx * PW;
+      uint4 d[PW];
+      const __nv_bfloat16* dp = dz + (((long long)b * Ho + ho) * Wo + wo0) * C + c0;
+#pragma unroll
+      for (int o = 0; o < PW; ++o)
+        d[o] = (wo0 + o < Wo) ? __ldg(reinterpret_cast<const uint4*>(dp + (long long)o * C)) : make_uint4(0, 0, 0, 0);
+      const int hi0 = ho * S - 1, wi0 = wo0 * S - 1;
+      const __nv_bfloat16* xb = x + (((long long)b * H + hi0) * W + wi0) * C + c0;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const bool hok = (unsigned)(hi0 + kh) < (unsigned)H;
+        uint4 xr[NCOL];
+#pragma unroll
+        for (int i = 0; i < NCOL; ++i)
+          xr[i] = (hok && (unsigned)(wi0 + i) < (unsigned)W) ? __ldg(reinterpret_cast<const uint4*>(xb + kh * rowC + (long long)i * C))
+                                                             : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          float* a = acc[kh * 3 + kw];
+#pragma unroll
+          for (int o = 0; o < PW; ++o) {
+            const uint4 xv = xr[o * S + kw], dv = d[o];
+            a[0] = fma_bf16_lo(xv.x, dv.x, a[0]); a[1] = fma_bf16_hi(xv.x, dv.x, a[1]);
+            a[2] = fma_bf16_lo(xv.y, dv.y, a[2]); a[3] = fma_bf16_hi(xv.y, dv.y, a[3]);
+            a[4] = fma_bf16_lo(xv.z, dv.z, a[4]); a[5] = fma_bf16_hi(xv.z, dv.z, a[5]);
+            a[6] = fma_bf16_lo(xv.w, dv.w, a[6]); a[7] = fma_bf16_hi(xv.w, dv.w, a[7]);
+          }
+        }
+      }
+    }
+  }
+  __shared__ float red[256][8 + 1];
+  const int tid = threadIdx.y * TX + threadIdx.x;
+#pragma unroll
+  for (int o = 0; o < 9; ++o) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[tid][j] = acc[o][j];
+    __syncthreads();
+    int top = 1;
+    while (top < TY) top <<= 1;
+    for (int stride = top >> 1; stride >= 1; stride >>= 1) {
+      if (threadIdx.y < stride && threadIdx.y + stride < TY) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[tid][j] += red[tid + stride * TX][j];
+      }
+      __syncthreads();
+    }
+    if (threadIdx.y == 0 && active) {
+      double* dst = dw + ((long long)(blockIdx.x % nslot) * 9 + o) * C + c0;      // one of nslot copies (see channel_reduce)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(dst + j, (double)red[threadIdx.x][j]);
     }
   }
 }
@@ -1020,6 +1105,19 @@ int b200seg_dw_wgrad(const void* x, const void* dz, double* dw, int nslot, int d
   const int ppb = red_ppb(P, block, C / vn);
   dim3 grid(cdiv(P, ppb), cdiv(C / vn, block.x));
   cudaStream_t st = (cudaStream_t)s;
+  static int variant = -1;      // B200SEG_DW_WGRAD: 0 = generic kernel, 2 / 4 = pixels per thread of the bf16 kernel (default 2)
+  if (variant < 0) { const char* e = getenv("B200SEG_DW_WGRAD"); variant = e ? atoi(e) : 2; }
+  if (dtype == B200SEG_BF16 && variant > 0) {
+    const int pw = variant == 4 ? 4 : 2;
+    const long long G = (long long)B * Ho * ((Wo + pw - 1) / pw);
+    const int gpb = max(1, (ppb + pw - 1) / pw);
+    dim3 g2(cdiv(G, gpb), cdiv(C / vn, block.x));
+#define DWW(S, PW) dw_wgrad_bf16_kernel<S, PW><<<g2, block, 0, st>>>((const bf16*)x, (const bf16*)dz, B, H, W, C, Ho, Wo, gpb, dw, nslot)
+    if (stride == 1) { if (pw == 4) DWW(1, 4); else DWW(1, 2); }
+    else { if (pw == 4) DWW(2, 4); else DWW(2, 2); }
+#undef DWW
+    return check_launch("dw_wgrad");
+  }
   DISPATCH_T(dtype, (dw_wgrad_kernel<float><<<grid, block, 0, st>>>((const float*)x, (const float*)dz, B, H, W, C, Ho, Wo, stride, ppb, dw, nslot)),
              (dw_wgrad_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)x, (const bf16*)dz, B, H, W, C, Ho, Wo, stride, ppb, dw, nslot)), "dw_wgrad")
   return check_launch("dw_wgrad");

@@ -124,22 +124,24 @@ def test_optimizer_and_preprocess_have_no_cpu_fallback_either():
 
 
 def test_fused_schedule_replaces_the_inverted_residual_triples():
-    """Eval bf16 schedule: the 16 expand-ratio-6 blocks are one step each where the policy fuses them (everything but the
-    stride-2 block at half resolution for a 256x512 input), 62 convs stay covered exactly once."""
+    """Eval bf16 schedule: the 16 expand-ratio-6 blocks are one step each, outconv + final upsample are one step, the 62
+    convs stay covered exactly once."""
     from b200seg import engine
     m = b200seg.MobileNetV2UNet(output_channels=10)
     eng = m._get_engine()
     assert len(eng._mb_triples()) == 16
     sched = eng._schedule("bf16", "tc", 256, 512)
     fused = [s for s in sched if s.op == "mbconv"]
-    assert len(fused) == 15 and len(sched) == 37
+    assert len(fused) == 16 and len(sched) == 33
     assert all(s.parts[1].stride in (1, 2) and s.parts[0].src == s.src and s.parts[2].dst == s.dst for s in fused)
-    assert "backbone.features.2" not in {s.name for s in fused}               # 16->96->24 stride 2 at 128x256 stays unfused
-    n_convs = sum(3 if s.op == "mbconv" else 1 for s in sched if s.op in ("stem", "dw", "dense", "mbconv"))
+    assert sched[-1].op == "tail" and [p.name for p in sched[-1].parts] == ["outc.conv.0", "outc.conv.3", "final_upsample"]
+    n_convs = sum(3 if s.op == "mbconv" else 2 if s.op == "tail" else 1 for s in sched if s.op in ("stem", "dw", "dense", "mbconv", "tail"))
     assert n_convs == 62
     assert eng._schedule("fp32", "simt", 256, 512) is eng.steps               # the exact path is never fused
-    eng.mbconv_impl = "fused"
-    assert sum(s.op == "mbconv" for s in eng._schedule("bf16", "tc", 256, 512)) == 16
+    eng.mbconv_impl, eng.tail_impl = "unfused", "unfused"
+    assert [s.name for s in eng._schedule("bf16", "tc", 256, 512)] == [s.name for s in eng.steps]
+    m17 = b200seg.MobileNetV2UNet(output_channels=17)                          # > 16 classes: the generic tail kernels
+    assert m17._get_engine()._schedule("bf16", "tc", 256, 512)[-1].op == "final"
 
 
 def test_schedule_covers_every_used_parameter():
