@@ -117,6 +117,25 @@ def dwconv3x3_tc(x, wdiag, b, stride: int, act: int, out=None, flags: int = 0):
     return out
 
 
+USE_CONV_RS = True       # 3x3 convs with <= 32 output channels on wide maps go through the row-stacked kernel (conv_rs.cu)
+CONV_RS_FLAGS = 0        # tuning flags of b200seg_conv_rs (tools only)
+
+
+def conv_rs(x, w, b, act: int, res=None, out=None, flags: int = 0):
+    """Row-stacked 3x3 tensor-core conv for few output channels: same operands/results as conv_tc(taps=9)."""
+    _cuda(x, w, b, res)
+    if x.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
+        raise TypeError("conv_rs is bf16-only")
+    B, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    if w.shape[1] != 9 * Cin:
+        raise ValueError(f"conv_rs: weight {tuple(w.shape)} does not match Cin={Cin}")
+    if out is None:
+        out = torch.empty((B, H, W, Cout), device=x.device, dtype=torch.bfloat16)
+    check(lib.b200seg_conv_rs(ptr(x), ptr(w), ptr(b), ptr(res), ptr(out), B, H, W, Cin, Cout, act, flags, _stream()), "conv_rs")
+    return out
+
+
 def conv_tc(x, w, b, taps: int, act: int, res=None, out=None, flags: int = 0):
     """Tensor-core conv. x NHWC bf16 [B,H,W,Cin]; w bf16 [Cout, taps*Cin]; b f32 [Cout]."""
     _cuda(x, w, b, res)
@@ -126,6 +145,8 @@ def conv_tc(x, w, b, taps: int, act: int, res=None, out=None, flags: int = 0):
     Cout = w.shape[0]
     if w.shape[1] != taps * Cin:
         raise ValueError(f"conv_tc: weight {tuple(w.shape)} does not match taps={taps} Cin={Cin}")
+    if taps == 9 and USE_CONV_RS and flags == 0 and lib.b200seg_conv_rs_supported(H, W, Cin, Cout):
+        return conv_rs(x, w, b, act, res, out, CONV_RS_FLAGS)
     if out is None:
         out = torch.empty((B, H, W, Cout), device=x.device, dtype=torch.bfloat16)
     check(lib.b200seg_conv_tc(ptr(x), ptr(w), ptr(b), ptr(res), ptr(out), B, H, W, Cin, Cout, taps, act, flags,

@@ -271,3 +271,44 @@ def test_tail_fused_matches_the_three_ops_it_replaces(B, h, w, C):
     top2 = ref.topk(min(2, C), dim=1).values
     tie = (top2[:, 0] - top2[:, -1]).abs() < 1e-4 * rng if C > 1 else torch.zeros_like(am, dtype=torch.bool)
     assert bool(((mask.long() == am) | tie).all())
+
+
+# ------------------------------------------------------------------------------------------------
+# row-stacked 3x3 conv for few output channels (conv_rs.cu): same contract as conv_tc(taps=9)
+# ------------------------------------------------------------------------------------------------
+RS_CASES = [  # B, H, W, Cin, Cout, act, res
+    (2, 128, 256, 80, 32, 1, False),     # up4.conv.0: two column tiles per row, 2 K chunks (64 + 16)
+    (2, 128, 256, 32, 32, 1, False),     # up4.conv.3
+    (3, 40, 96, 32, 32, 0, True),        # narrow map (one 96-pixel tile), accumulate into res (the data-gradient use)
+    (1, 3, 200, 8, 24, 2, False),        # minimal height, ragged second column tile, Cout 24 -> 32 columns, K = 8
+    (5, 7, 130, 24, 16, 1, True),        # 16-column variant, many short strips (ranges span images)
+    (1, 128, 256, 32, 8, 0, False),      # Cout = 8
+    (2, 33, 257, 136, 32, 1, False),     # odd sizes, 3 K chunks
+]
+
+
+@pytest.mark.parametrize("flags", [0, 1 << 20, (2 << 16) | (1 << 20), (7 << 8)], ids=["auto", "1cta", "1cta_2stages", "grid28"])
+@pytest.mark.parametrize("B,H,W,Cin,Cout,act,res", RS_CASES)
+def test_conv_rs(flags, B, H, W, Cin, Cout, act, res):
+    x = _rand(B, Cin, H, W, seed=21).bfloat16()
+    w = _rand(Cout, Cin, 3, 3, seed=22, scale=(2.0 / (Cin * 9)) ** 0.5).bfloat16()
+    b = _rand(Cout, seed=23, scale=0.1)
+    r = _rand(B, Cout, H, W, seed=24).bfloat16() if res else None
+    ref = _act(F.conv2d(x.double(), w.double(), b.double(), 1, 1), act)
+    if res:
+        ref = ref + r.double()
+    wk = w.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous()
+    got = ops.conv_rs(_nhwc(x), wk, b, act, _nhwc(r) if res else None, flags=flags)
+    torch.cuda.synchronize()
+    assert _err(_nchw(got), ref) < TOL[torch.bfloat16]
+    # and against the tap-by-tap tensor-core kernel (flags=2: TAP addressing, never dispatched to conv_rs)
+    old = ops.conv_tc(_nhwc(x), wk, b, 9, act, _nhwc(r) if res else None, flags=2)
+    assert _err(got.float(), old.double()) < 8e-3          # one bf16 ulp of the largest output
+
+
+def test_conv_tc_dispatches_small_cout_3x3_to_conv_rs():
+    from b200seg._cabi import lib
+    assert lib.b200seg_conv_rs_supported(128, 256, 80, 32) == 1 and lib.b200seg_conv_rs_supported(128, 256, 32, 32) == 1
+    assert lib.b200seg_conv_rs_supported(64, 128, 152, 64) == 0          # 64 output channels: 3 accumulators exceed TMEM
+    assert lib.b200seg_conv_rs_supported(32, 64, 32, 32) == 0            # narrow map: conv_tc's 2-D tiles
+    assert lib.b200seg_conv_rs_supported(128, 256, 1344, 32) == 0        # weights would not stay resident
