@@ -206,6 +206,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+// 8 columns into the first 8 registers of r
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor: K-major operand tile, 128-byte swizzle, rows of 64 bf16 (128 B),
@@ -218,6 +225,16 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
   d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset = 1024 B       [32,46)
   d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)    [46,48)
   d |= (uint64_t)2 << 61;                        // SWIZZLE_128B                      [61,64)
+  return d;
+}
+// UMMA shared-memory descriptor of a K-major operand WITHOUT swizzle: 8-row x 16-byte core matrices (128 contiguous bytes
+// each); LBO = byte distance between core matrices adjacent along K, SBO = between 8-row groups along M/N.
+__device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell); layout type 0 = SWIZZLE_NONE
   return d;
 }
 // Instruction descriptor for kind::f16, A=B=bf16 K-major, D=f32, shape M x N (cute InstrDescriptor)

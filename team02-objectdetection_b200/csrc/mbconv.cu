@@ -44,6 +44,7 @@ struct MbArgs {
   int ce_chunks;             // 64-channel chunks of Ce
   int cout_pad, n_proj, proj_n;   // project N: n_proj MMAs of proj_n columns
   int nbuf_e, nbuf_d, nws;
+  int last_nv;               // valid channels of the last Ce chunk handled exactly: 16 | 32, else 64 (= full-width path)
   int x_chunk_stride, x_bytes, e_bytes, we_bytes, wp_bytes;
   int tiles_w, tiles_h;
   long long total_tiles;
@@ -104,15 +105,21 @@ struct Geo {
   static constexpr int MX = (NHALO + 127) / 128;
 };
 
-template <int S, int TH>
+// GSH = log2(valid 8-channel groups of the chunk): a narrow last chunk (Ce % 64 = 32 | 16) spreads its pixels over 2x | 4x
+// as many threads instead of computing 64 - nv dead channels (Ce = 96 and 144 -- the three most expensive blocks -- would
+// otherwise pay for 128 and 192 channels).
+template <int S, int TH, int GSH>
 __device__ __forceinline__ void dw_chunk(const uint8_t* __restrict__ sE, uint8_t* __restrict__ sD, const MbArgs& a,
                                          const int chunk, const int ct) {
-  constexpr int PXT = TH / 2;                     // adjacent outputs per thread: 256 threads x 8 channels x PXT = tile
+  constexpr int NPT = 256 >> GSH;                 // threads along the pixel axis
+  constexpr int PXT = (TH * 16) / NPT > 0 ? (TH * 16) / NPT : 1;   // adjacent outputs per thread
+  constexpr int TPR = 16 / PXT;                   // threads per output row
   constexpr int NCOL = (PXT - 1) * S + 3;         // input columns they touch
   constexpr int IW = Geo<S, TH>::IW, TW = Geo<S, TH>::TW;
-  const int g = ct & 7, pt = ct >> 3;
-  const int orow = PXT == 4 ? (pt >> 2) : (pt >> 3);
-  const int ocol0 = PXT == 4 ? (pt & 3) * 4 : (pt & 7) * 2;
+  const int g = ct & ((1 << GSH) - 1), pt = ct >> GSH;
+  if (pt * PXT >= TH * 16) return;                // more threads than outputs (4-row tile, 16-channel chunk)
+  const int orow = pt / TPR;
+  const int ocol0 = (pt % TPR) * PXT;
   const int cbase = chunk * 64 + g * 8;
   const int cstride = a.ce_chunks * 64;
   float acc[PXT][8];
@@ -158,6 +165,50 @@ __device__ __forceinline__ void dw_chunk(const uint8_t* __restrict__ sE, uint8_t
   }
 }
 
+// E_acc (TMEM) -> ReLU6 -> bf16 -> smem E for one chunk.  Warp (q, half) converts lane quarter q of every M tile, columns
+// [half * NV/2, +NV/2) of the chunk's NV valid channels.  The expand bias is already in the accumulator (it enters the
+// MMA as an extra k-step against an all-ones A tile), so a value costs half a cvt.relu + half a packed min.  The loads
+// are software-pipelined: the tcgen05.ld of stage i+1 is in flight while stage i is converted.
+template <int S, int TH, int NV>
+__device__ __forceinline__ void e_chunk(uint8_t* __restrict__ sE, const uint32_t tcol, const int q, const int half,
+                                        const int lane, const int gh0, const int gw0, const int H, const int W) {
+  using G = Geo<S, TH>;
+  constexpr int CW = NV / 2;                      // columns per warp
+  constexpr int LW = CW >= 16 ? 16 : 8;           // columns per tcgen05.ld
+  constexpr int NL = CW / LW;
+  constexpr int NST = G::MX * NL;
+  uint32_t v[2][16];
+  auto load = [&](const int st, uint32_t (&r)[16]) {
+    const uint32_t ad = tcol + (uint32_t)((st / NL) * 64 + half * CW + (st % NL) * LW);
+    if (LW == 16) tmem_ld16(ad, r); else tmem_ld8(ad, r);
+  };
+  load(0, v[0]);
+#pragma unroll
+  for (int st = 0; st < NST; ++st) {
+    tmem_ld_wait();
+    if (st + 1 < NST) load(st + 1, v[(st + 1) & 1]);
+    const uint32_t(&r)[16] = v[st & 1];
+    const int p = (st / NL) * 128 + q * 32 + lane;
+    if (p < G::NHALO) {
+      const int ih = p / G::IW, iw = p - ih * G::IW;
+      const int gh = gh0 + ih, gw = gw0 + iw;
+      const bool inside = gh >= 0 && gh < H && gw >= 0 && gw < W;      // the depthwise conv pads E with zeros
+      uint32_t pk[LW / 2];
+#pragma unroll
+      for (int i = 0; i < LW / 2; ++i)
+        pk[i] = inside ? relu6_pack(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])) : 0u;
+      uint8_t* erow = sE + p * 128;
+      const int j = (half * CW + (st % NL) * LW) >> 3;
+      *reinterpret_cast<uint4*>(erow + ((j ^ (p & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      if (LW == 16)
+        *reinterpret_cast<uint4*>(erow + (((j + 1) ^ (p & 7)) << 4)) = make_uint4(pk[LW / 2 - 4], pk[LW / 2 - 3], pk[LW / 2 - 2], pk[LW / 2 - 1]);
+    }
+  }
+}
+
+constexpr int MB_BIAS_TILE = 2048;    // [64 expanded channels][16 k] bf16, no swizzle: 8 row groups x (2 core matrices of 128 B)
+constexpr int MB_ONES_BYTES = 256;    // all-ones A operand of the bias k-step: every core matrix aliases these bytes (SBO = 0)
+
 template <int MINB, int S, int TH>
 __global__ void __launch_bounds__(MB_THREADS, MINB)
 mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWe,
@@ -175,11 +226,12 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   uint8_t* sE = sX + a.kcn * a.x_chunk_stride;                               // expanded tile, 64 channels
   uint8_t* sD = sE + a.e_bytes;                                              // nbuf_d x [128][64] bf16
   uint8_t* sW = sD + a.nbuf_d * 16384;                                       // nws x (We chunk | Wp chunk)
-  const int w_stage = a.we_bytes + a.wp_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + a.nws * w_stage);
+  const int w_stage = a.we_bytes + a.wp_bytes + MB_BIAS_TILE;                // + the chunk's expand-bias tile (built in place)
+  uint8_t* sOnes = sW + a.nws * w_stage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + MB_ONES_BYTES);
   uint64_t* x_full = bars;          // [1]
   uint64_t* x_empty = bars + 1;     // [1]
-  uint64_t* w_full = bars + 2;      // [2]
+  uint64_t* w_full = bars + 2;      // [2]  expand side of a weight stage: We chunk + bias tile
   uint64_t* w_empty = bars + 4;     // [2]
   uint64_t* e_full = bars + 6;      // [2]
   uint64_t* e_empty = bars + 8;     // [2]
@@ -187,7 +239,9 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   uint64_t* d_empty = bars + 12;    // [2]
   uint64_t* p_full = bars + 14;     // [1]
   uint64_t* p_empty = bars + 15;    // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* wp_full = bars + 16;    // [2]  project side of a weight stage (Wp chunk): its own barriers, so that the next
+  uint64_t* wp_empty = bars + 18;   // [2]  chunk's We never waits for this chunk's project MMA (single-stage configurations)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
@@ -198,6 +252,8 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     for (int i = 0; i < 2; ++i) {
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
+      mbar_init(&wp_full[i], 1);
+      mbar_init(&wp_empty[i], 1);
       mbar_init(&e_full[i], 1);
       mbar_init(&e_empty[i], MB_CWARPS);
       mbar_init(&d_full[i], MB_CWARPS);
@@ -210,6 +266,14 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   if (warp == 1) {
     tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
     tmem_relinquish();
+  }
+  if (warp == 2) {                     // all-ones A tile (bf16 1.0) and the zero half (k = 8..15) of every bias tile
+    for (int i = lane; i < MB_ONES_BYTES / 4; i += 32) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
+    for (int st = 0; st < a.nws; ++st) {
+      uint32_t* bt = reinterpret_cast<uint32_t*>(sW + st * w_stage + a.we_bytes + a.wp_bytes);
+      for (int i = lane; i < MB_BIAS_TILE / 4; i += 32) bt[i] = 0u;
+    }
+    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -237,12 +301,33 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       __syncwarp();
       for (int c = 0; c < nc; ++c) {
         mb_wait(&w_empty[wr.i], wr.ph ^ 1u, 11);
+        {
+          // bias tile of the chunk: row n (expanded channel) holds {hi, lo, 0...} with hi + lo = b_exp[n] to 16 mantissa
+          // bits; as B operand against the all-ones A tile it adds the bias inside the expand MMA
+          uint8_t* bt = sW + wr.i * w_stage + a.we_bytes + a.wp_bytes;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int n = lane + 32 * h;
+            const float b = __ldg(a.b_exp + c * 64 + n);
+            const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+            *reinterpret_cast<uint32_t*>(bt + (n >> 3) * 256 + (n & 7) * 16) =
+                (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+        }
         if (lane == 0) {
           uint8_t* st = sW + wr.i * w_stage;
-          mbar_arrive_expect_tx(&w_full[wr.i], (uint32_t)w_stage);
+          mbar_arrive_expect_tx(&w_full[wr.i], (uint32_t)a.we_bytes);
           for (int kc = 0; kc < a.kcn; ++kc) tma_load_3d(st + kc * 8192, &tmWe, &w_full[wr.i], kc * 64, 0, c * 64);
+        }
+        mb_wait(&wp_empty[wr.i], wr.ph ^ 1u, 12);
+        if (lane == 0) {
+          uint8_t* st = sW + wr.i * w_stage;
+          mbar_arrive_expect_tx(&wp_full[wr.i], (uint32_t)a.wp_bytes);
           for (int j = 0; j < a.n_proj; ++j)
-            tma_load_3d(st + a.we_bytes + j * a.proj_n * 128, &tmWp, &w_full[wr.i], c * 64, 0, j * a.proj_n);
+            tma_load_3d(st + a.we_bytes + j * a.proj_n * 128, &tmWp, &wp_full[wr.i], c * 64, 0, j * a.proj_n);
         }
         __syncwarp();
         wr.next(a.nws);
@@ -251,6 +336,8 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   } else if (warp == 1) {
     // ================= tcgen05 issuer =================
     const uint32_t idesc_e = umma_idesc_bf16(128, 64);
+    const uint32_t idesc_el = umma_idesc_bf16(128, a.last_nv);        // last chunk: only its valid channels
+    const uint64_t ones_desc = umma_desc_nosw(smem_u32(sOnes), 128, 0);
     const uint32_t idesc_p = umma_idesc_bf16(128, a.proj_n);
     const uint32_t desc_hi = (uint32_t)(umma_desc_k128(0) >> 32);
     const uint32_t x_lo0 = (uint32_t)umma_desc_k128(smem_u32(sX));
@@ -263,6 +350,7 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     Ring wp_r = {0, 0u}, d_r = {0, 0u};       // project side (runs one chunk behind): weight stage, D buffer
 
     auto project = [&](const int c) {
+      mb_wait(&wp_full[wp_r.i], wp_r.ph, 25);
       mb_wait(&d_full[d_r.i], d_r.ph, 20);
       if (c == 0) mb_wait(p_empty, tph ^ 1u, 21);     // previous tile's output has been read
       tc_fence_after();
@@ -275,7 +363,7 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             umma_bf16_lohi(tmem_base + pcol0 + (uint32_t)(j * a.proj_n), al + 2u * k,
                            bl + (uint32_t)(j * a.proj_n * 8) + 2u * k, desc_hi, idesc_p, (c > 0 || k > 0) ? 1u : 0u);
         umma_commit(&d_empty[d_r.i]);
-        umma_commit(&w_empty[wp_r.i]);
+        umma_commit(&wp_empty[wp_r.i]);
         if (c == nc - 1) umma_commit(p_full);
       }
       __syncwarp();
@@ -286,32 +374,31 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tph ^= 1u) {
       mb_wait(x_full, tph, 22);
       for (int c = 0; c < nc; ++c) {
-        if (c >= 1 && a.nws == 1) project(c - 1);             // single stage: free it first
         mb_wait(&w_full[we_r.i], we_r.ph, 23);
         mb_wait(&e_empty[e_r.i], e_r.ph ^ 1u, 24);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t bl0 = w_lo0 + (uint32_t)we_r.i * w_stage16;
+          const uint32_t id_e = c == nc - 1 ? idesc_el : idesc_e;
+          const uint64_t bias_desc = umma_desc_nosw(smem_u32(sW) + (uint32_t)(we_r.i * w_stage + a.we_bytes + a.wp_bytes), 128, 256);
           for (int m = 0; m < MX; ++m) {
             const uint32_t tacc = tmem_base + (uint32_t)((e_r.i * MX + m) * 64);
-            uint32_t first = 0u;
+            umma_bf16(tacc, ones_desc, bias_desc, id_e, 0u);           // E_acc = 1 . bias^T
             for (int kc = 0; kc < a.kcn; ++kc) {
               const int ks = (min(64, a.Cin - kc * 64) + 15) >> 4;
               const uint32_t al = x_lo0 + (uint32_t)kc * x_chunk16 + (uint32_t)m * (16384u >> 4);
               const uint32_t bl = bl0 + (uint32_t)kc * (8192u >> 4);
-              for (int k = 0; k < ks; ++k) {
-                umma_bf16_lohi(tacc, al + 2u * k, bl + 2u * k, desc_hi, idesc_e, first);
-                first = 1u;
-              }
+              for (int k = 0; k < ks; ++k) umma_bf16_lohi(tacc, al + 2u * k, bl + 2u * k, desc_hi, id_e, 1u);
             }
           }
           umma_commit(&e_full[e_r.i]);
+          umma_commit(&w_empty[we_r.i]);
           if (c == nc - 1) umma_commit(x_empty);
         }
         __syncwarp();
         e_r.next(a.nbuf_e);
         we_r.next(a.nws);
-        if (c >= 1 && a.nws > 1) project(c - 1);
+        if (c >= 1) project(c - 1);
       }
       project(nc - 1);
     }
@@ -328,47 +415,15 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       const int h0 = (t % a.tiles_h) * G::TH;
       const int bb = t / a.tiles_h;
       for (int c = 0; c < nc; ++c) {
-        // ---- E_acc -> smem E ----  warp (q, half): lane quarter q of every M tile, columns [32*half, +32)
-        float be[32];
-        {
-          const float4* bp = reinterpret_cast<const float4*>(a.b_exp + c * 64 + half * 32);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 b4 = __ldg(bp + i);
-            be[4 * i] = b4.x; be[4 * i + 1] = b4.y; be[4 * i + 2] = b4.z; be[4 * i + 3] = b4.w;
-          }
-        }
+        // ---- E_acc -> smem E ----
+        const bool narrow = c == nc - 1 && a.last_nv != 64;
         mb_wait(&e_full[e_r.i], e_r.ph, 30);
         tc_fence_after();
-#pragma unroll
-        for (int m = 0; m < MX; ++m) {
-          const int p = m * 128 + q * 32 + lane;
-          const int ih = p / G::IW, iw = p - ih * G::IW;
-          const int gh = h0 * S - 1 + ih, gw = w0 * S - 1 + iw;
-          const bool inside = gh >= 0 && gh < a.H && gw >= 0 && gw < a.W;
-          const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((e_r.i * MX + m) * 64 + half * 32);
-          uint32_t v[2][16];
-          tmem_ld16(trow, v[0]);
-          tmem_ld16(trow + 16u, v[1]);
-          tmem_ld_wait();
-          if (p < G::NHALO) {
-            uint8_t* erow = sE + p * 128;
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-              uint32_t pk[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                pk[i] = relu6_pack(__uint_as_float(v[cc][2 * i]) + be[cc * 16 + 2 * i],
-                                   __uint_as_float(v[cc][2 * i + 1]) + be[cc * 16 + 2 * i + 1]);
-              if (!inside) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) pk[i] = 0u;
-              }
-              const int j = half * 4 + cc * 2;
-              *reinterpret_cast<uint4*>(erow + ((j ^ (p & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              *reinterpret_cast<uint4*>(erow + (((j + 1) ^ (p & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            }
-          }
+        {
+          const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(e_r.i * MX * 64);
+          if (!narrow) e_chunk<S, TH, 64>(sE, tcol, q, half, lane, h0 * S - 1, w0 * S - 1, a.H, a.W);
+          else if (a.last_nv == 32) e_chunk<S, TH, 32>(sE, tcol, q, half, lane, h0 * S - 1, w0 * S - 1, a.H, a.W);
+          else e_chunk<S, TH, 16>(sE, tcol, q, half, lane, h0 * S - 1, w0 * S - 1, a.H, a.W);
         }
         tc_fence_before();
         __syncwarp();
@@ -377,7 +432,9 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         named_bar_sync(1, MB_CWARPS * 32);                 // E complete
         // ---- depthwise 3x3: smem E -> smem D ----
         mb_wait(&d_empty[d_r.i], d_r.ph ^ 1u, 31);
-        dw_chunk<S, TH>(sE, sD + d_r.i * 16384, a, c, ct);
+        if (!narrow) dw_chunk<S, TH, 3>(sE, sD + d_r.i * 16384, a, c, ct);
+        else if (a.last_nv == 32) dw_chunk<S, TH, 2>(sE, sD + d_r.i * 16384, a, c, ct);
+        else dw_chunk<S, TH, 1>(sE, sD + d_r.i * 16384, a, c, ct);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&d_full[d_r.i]);
@@ -485,15 +542,16 @@ extern "C" int b200seg_mbconv(const void* x, const void* w_exp, const float* b_e
   a.x_bytes = a.IH * a.IW * 128;
   a.x_chunk_stride = round_up(a.x_bytes, 1024);
   a.e_bytes = round_up(a.x_bytes, 1024);
+  a.last_nv = (Ce % 64 == 16 || Ce % 64 == 32) ? Ce % 64 : 64;
   a.we_bytes = a.kcn * 8192;
   a.wp_bytes = a.cout_pad * 128;
   a.tiles_w = (a.Wo + a.TW - 1) / a.TW;
   a.tiles_h = (a.Ho + a.TH - 1) / a.TH;
   a.total_tiles = (long long)B * a.tiles_h * a.tiles_w;
 
-  const int cap = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
+  const int cap = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - MB_ONES_BYTES;
   const int x_region = a.kcn * a.x_chunk_stride;      // the over-read of the last M tile lands in E (see kernel)
-  auto smem_for = [&](int nd, int nw) { return x_region + a.e_bytes + nd * 16384 + nw * (a.we_bytes + a.wp_bytes); };
+  auto smem_for = [&](int nd, int nw) { return x_region + a.e_bytes + nd * 16384 + nw * (a.we_bytes + a.wp_bytes + MB_BIAS_TILE); };
   // Two CTAs per SM (each single-buffered, <= 256 TMEM columns, <= half the shared memory) hide one CTA's phase
   // barriers and TMEM/LDS latency behind the other; otherwise one CTA per SM with double-buffered rings.
   const int half_cap = cap / 2 - 1024;
@@ -520,7 +578,7 @@ extern "C" int b200seg_mbconv(const void* x, const void* w_exp, const float* b_e
   B200_REQUIRE(tmem_need <= 512, "mbconv: %d TMEM columns needed", tmem_need);
   a.tmem_cols = 32;
   while (a.tmem_cols < tmem_need) a.tmem_cols <<= 1;
-  int smem = smem_used + 1024 + 256;
+  int smem = smem_used + 1024 + 256 + MB_ONES_BYTES;
   if (a.tmem_cols > 256 || smem > cap / 2) per_sm = 1;
   // a CTA that owns more than half of the SM's 512 TMEM columns must not share the SM (the second CTA's
   // tcgen05.alloc would block until the first exits)
