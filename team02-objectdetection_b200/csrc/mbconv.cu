@@ -27,6 +27,11 @@ namespace b200 {
 namespace {
 
 constexpr int MB_THREADS = 320;
+// Row pitch of the expanded tile in shared memory.  Only CUDA cores touch it (E-phase stores: lane = pixel row; stencil
+// loads: 8 lanes = the 8 16-byte channel groups of one pixel), so instead of the 128-byte XOR swizzle the rows are padded by
+// 16 bytes: consecutive rows start in different bank groups (conflict-free stores) and every stencil load is base + immediate
+// (the 18 swizzled addresses per thread were hoisted out of the chunk loop and spilled under the 96-register cap).
+constexpr int MB_E_PITCH = 144;
 constexpr int MB_CWARPS = 8;
 
 struct MbArgs {
@@ -141,7 +146,7 @@ __device__ __forceinline__ void dw_chunk(const uint8_t* __restrict__ sE, uint8_t
 #pragma unroll
     for (int j = 0; j < NCOL; ++j) {
       const int pr = prow0 + j;
-      const uint4 t = *reinterpret_cast<const uint4*>(sE + pr * 128 + ((g ^ (pr & 7)) << 4));
+      const uint4 t = *reinterpret_cast<const uint4*>(sE + pr * MB_E_PITCH + (g << 4));
 #pragma unroll
       for (int o = 0; o < PXT; ++o) {
         const int dw = j - o * S;                 // compile-time after unrolling
@@ -197,11 +202,11 @@ __device__ __forceinline__ void e_chunk(uint8_t* __restrict__ sE, const uint32_t
 #pragma unroll
       for (int i = 0; i < LW / 2; ++i)
         pk[i] = inside ? relu6_pack(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])) : 0u;
-      uint8_t* erow = sE + p * 128;
+      uint8_t* erow = sE + p * MB_E_PITCH;
       const int j = (half * CW + (st % NL) * LW) >> 3;
-      *reinterpret_cast<uint4*>(erow + ((j ^ (p & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(erow + (j << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       if (LW == 16)
-        *reinterpret_cast<uint4*>(erow + (((j + 1) ^ (p & 7)) << 4)) = make_uint4(pk[LW / 2 - 4], pk[LW / 2 - 3], pk[LW / 2 - 2], pk[LW / 2 - 1]);
+        *reinterpret_cast<uint4*>(erow + ((j + 1) << 4)) = make_uint4(pk[LW / 2 - 4], pk[LW / 2 - 3], pk[LW / 2 - 2], pk[LW / 2 - 1]);
     }
   }
 }
@@ -541,7 +546,7 @@ extern "C" int b200seg_mbconv(const void* x, const void* w_exp, const float* b_e
   B200_REQUIRE(a.proj_n % 16 == 0, "mbconv: Cout=%d cannot be split into UMMA N tiles", Cout);
   a.x_bytes = a.IH * a.IW * 128;
   a.x_chunk_stride = round_up(a.x_bytes, 1024);
-  a.e_bytes = round_up(a.x_bytes, 1024);
+  a.e_bytes = round_up(a.IH * a.IW * MB_E_PITCH, 1024);
   a.last_nv = (Ce % 64 == 16 || Ce % 64 == 32) ? Ce % 64 : 64;
   a.we_bytes = a.kcn * 8192;
   a.wp_bytes = a.cout_pad * 128;
