@@ -350,14 +350,15 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     const uint32_t w_lo0 = (uint32_t)umma_desc_k128(smem_u32(sW));
     const uint32_t x_chunk16 = (uint32_t)a.x_chunk_stride >> 4;
     const uint32_t w_stage16 = (uint32_t)w_stage >> 4, we16 = (uint32_t)a.we_bytes >> 4;
-    uint32_t tph = 0;
+    uint32_t tph = 0, pe_ph = 0;
+    int pend = -1;                            // chunk whose project MMA is still to be issued (may belong to the previous tile)
     Ring we_r = {0, 0u}, e_r = {0, 0u};       // expand side: weight stage, accumulator buffer
     Ring wp_r = {0, 0u}, d_r = {0, 0u};       // project side (runs one chunk behind): weight stage, D buffer
 
     auto project = [&](const int c) {
       mb_wait(&wp_full[wp_r.i], wp_r.ph, 25);
       mb_wait(&d_full[d_r.i], d_r.ph, 20);
-      if (c == 0) mb_wait(p_empty, tph ^ 1u, 21);     // previous tile's output has been read
+      if (c == 0) { mb_wait(p_empty, pe_ph ^ 1u, 21); pe_ph ^= 1u; }     // previous tile's output has been read
       tc_fence_after();
       if (elect_one()) {
         const int ks = (min(64, a.Ce - c * 64) + 15) >> 4;
@@ -403,53 +404,23 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         __syncwarp();
         e_r.next(a.nbuf_e);
         we_r.next(a.nws);
-        if (c >= 1) project(c - 1);
+        // the expand of the NEXT chunk -- also across a tile boundary -- is always in flight before the project of this one
+        // is issued, so the E hand-off of the next chunk/tile never waits for project -> commit -> expand in series
+        if (pend >= 0) project(pend);
+        pend = c;
       }
-      project(nc - 1);
     }
+    if (pend >= 0) project(pend);
   } else {
     // ================= compute warps =================
     const int ct = threadIdx.x - 64;
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;       // which 32 of the chunk's 64 columns this warp converts
-    uint32_t tph = 0;
-    Ring e_r = {0, 0u}, d_r = {0, 0u};
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tph ^= 1u) {
-      int t = tile;
-      const int w0 = (t % a.tiles_w) * G::TW; t /= a.tiles_w;
-      const int h0 = (t % a.tiles_h) * G::TH;
-      const int bb = t / a.tiles_h;
-      for (int c = 0; c < nc; ++c) {
-        // ---- E_acc -> smem E ----
-        const bool narrow = c == nc - 1 && a.last_nv != 64;
-        mb_wait(&e_full[e_r.i], e_r.ph, 30);
-        tc_fence_after();
-        {
-          const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(e_r.i * MX * 64);
-          if (!narrow) e_chunk<S, TH, 64>(sE, tcol, q, half, lane, h0 * S - 1, w0 * S - 1, a.H, a.W);
-          else if (a.last_nv == 32) e_chunk<S, TH, 32>(sE, tcol, q, half, lane, h0 * S - 1, w0 * S - 1, a.H, a.W);
-          else e_chunk<S, TH, 16>(sE, tcol, q, half, lane, h0 * S - 1, w0 * S - 1, a.H, a.W);
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&e_empty[e_r.i]);
-        e_r.next(a.nbuf_e);
-        named_bar_sync(1, MB_CWARPS * 32);                 // E complete
-        // ---- depthwise 3x3: smem E -> smem D ----
-        mb_wait(&d_empty[d_r.i], d_r.ph ^ 1u, 31);
-        if (!narrow) dw_chunk<S, TH, 3>(sE, sD + d_r.i * 16384, a, c, ct);
-        else if (a.last_nv == 32) dw_chunk<S, TH, 2>(sE, sD + d_r.i * 16384, a, c, ct);
-        else dw_chunk<S, TH, 1>(sE, sD + d_r.i * 16384, a, c, ct);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&d_full[d_r.i]);
-        d_r.next(a.nbuf_d);
-        named_bar_sync(2, MB_CWARPS * 32);                 // every read of E done before the next chunk overwrites it
-      }
-      // ---- P_acc -> global ----
-      mb_wait(p_full, tph, 32);
+    // ---- P_acc -> global (+bias, +residual) for the tile (bb, h0, w0) ----
+    auto p_epilogue = [&](const int bb, const int h0, const int w0, const uint32_t parity) {
+      mb_wait(p_full, parity, 32);
       tc_fence_after();
-      {
+
         const int r = q * 32 + lane;
         const int oh = r / G::TW, ow = r - oh * G::TW;
         const int gh = h0 + oh, gw = w0 + ow;
@@ -492,11 +463,51 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             *reinterpret_cast<uint4*>(yp + c0 + 8) = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
                                                                 pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
         }
-      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_empty);
+    };
+    uint32_t tph = 0;
+    int pbb = 0, ph0 = 0, pw0 = 0;
+    bool have_prev = false;
+    Ring e_r = {0, 0u}, d_r = {0, 0u};
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tph ^= 1u) {
+      int t = tile;
+      const int w0 = (t % a.tiles_w) * G::TW; t /= a.tiles_w;
+      const int h0 = (t % a.tiles_h) * G::TH;
+      const int bb = t / a.tiles_h;
+      for (int c = 0; c < nc; ++c) {
+        // ---- E_acc -> smem E ----
+        const bool narrow = c == nc - 1 && a.last_nv != 64;
+        mb_wait(&e_full[e_r.i], e_r.ph, 30);
+        tc_fence_after();
+        {
+          const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(e_r.i * MX * 64);
+          if (!narrow) e_chunk<S, TH, 64>(sE, tcol, q, half, lane, h0 * S - 1, w0 * S - 1, a.H, a.W);
+          else if (a.last_nv == 32) e_chunk<S, TH, 32>(sE, tcol, q, half, lane, h0 * S - 1, w0 * S - 1, a.H, a.W);
+          else e_chunk<S, TH, 16>(sE, tcol, q, half, lane, h0 * S - 1, w0 * S - 1, a.H, a.W);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&e_empty[e_r.i]);
+        e_r.next(a.nbuf_e);
+        // the previous tile's output leaves here: its last project MMA had the whole E hand-off above to complete
+        if (c == 0 && have_prev) p_epilogue(pbb, ph0, pw0, tph ^ 1u);
+        named_bar_sync(1, MB_CWARPS * 32);                 // E complete
+        // ---- depthwise 3x3: smem E -> smem D ----
+        mb_wait(&d_empty[d_r.i], d_r.ph ^ 1u, 31);
+        if (!narrow) dw_chunk<S, TH, 3>(sE, sD + d_r.i * 16384, a, c, ct);
+        else if (a.last_nv == 32) dw_chunk<S, TH, 2>(sE, sD + d_r.i * 16384, a, c, ct);
+        else dw_chunk<S, TH, 1>(sE, sD + d_r.i * 16384, a, c, ct);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&d_full[d_r.i]);
+        d_r.next(a.nbuf_d);
+        named_bar_sync(2, MB_CWARPS * 32);                 // every read of E done before the next chunk overwrites it
+      }
+      pbb = bb; ph0 = h0; pw0 = w0; have_prev = true;
     }
+    if (have_prev) p_epilogue(pbb, ph0, pw0, tph ^ 1u);
   }
   tc_fence_before();
   __syncthreads();
