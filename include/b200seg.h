@@ -47,6 +47,16 @@ int b200seg_conv3x3_smallcin(const void* x, int x_dtype, const float* w, const f
                              int y_dtype, int B, int Cin, int H, int W, int Cout, int stride, int act,
                              b200seg_stream_t s);
 
+/* features.0 + features.1 of the MobileNetV2 encoder as one kernel (eval, BatchNorm folded; unet.py:15,34 ->
+ * tv:models/mobilenetv2.py:42-57): stem 3x3 stride 2 (3->32) + ReLU6 -> depthwise 3x3 + ReLU6 -> linear 1x1 (32->16); the two
+ * 32-channel half-resolution maps stay in shared memory.  Replaces three aten::convolution (+BN +hardtanh) calls.
+ *   x NCHW [B,3,H,W] (f32 | bf16); w_stem f32 [3][3][3][32], b_stem f32 [32]; w_dw bf16 [9][32], b_dw f32 [32];
+ *   w_pw bf16 [16][32], b_pw f32 [16]; y NHWC bf16 [B,H/2,W/2,16].  b200seg_stem_mb1_supported: 1 when the shape qualifies. */
+int b200seg_stem_mb1_supported(int x_dtype, int H, int W, int Cstem, int Cout);
+int b200seg_stem_mb1(const void* x, int x_dtype, const float* w_stem, const float* b_stem, const void* w_dw,
+                     const float* b_dw, const void* w_pw, const float* b_pw, void* y, int B, int H, int W,
+                     b200seg_stream_t s);
+
 /* Depthwise 3x3 (+folded BN shift +act), NHWC, pad 1, stride 1|2 (mobilenetv2.py:42-51).
  *   w : f32 [9][C] (tap-major, BN scale folded);  b : f32 [C] or NULL. */
 int b200seg_dwconv3x3(const void* x, const float* w, const float* b, void* y, int dtype, int B, int H,

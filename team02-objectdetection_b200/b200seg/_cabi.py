@@ -23,6 +23,8 @@ _PROTOS = {
     "b200seg_version": [],
     "b200seg_device_info": [C.POINTER(_i), C.POINTER(_i)],
     "b200seg_conv3x3_smallcin": [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "b200seg_stem_mb1_supported": [_i, _i, _i, _i, _i],
+    "b200seg_stem_mb1": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "b200seg_dwconv3x3": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "b200seg_dwconv3x3_bf16w": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "b200seg_conv_tc": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],

@@ -108,6 +108,7 @@ class Engine:
         self.dw_impl: Optional[str] = None          # None = per-layer choice; "tc" / "simt" force one kernel
         self.mbconv_impl: Optional[str] = None      # None = per-block choice; "fused" / "unfused" force (eval bf16 only)
         self.tail_impl: Optional[str] = None        # None = fused outconv + final upsample (+argmax) when it applies; "unfused"
+        self.head_impl: Optional[str] = None        # None = fused features.0 + features.1 (stem_mb1) when it applies; "unfused"
         self.mbconv_flags = 0
         self._eval_sched: Dict[tuple, List[Step]] = {}
         self.tc_flags = 0
@@ -251,13 +252,14 @@ class Engine:
                 out.append((e, d, pj))
         return out
 
-    def _schedule(self, mode: str, dense_impl: str, H: int, W: int) -> List[Step]:
+    def _schedule(self, mode: str, dense_impl: str, H: int, W: int, in_dtype=torch.float32) -> List[Step]:
         """Eval schedule for an input of H x W: self.steps with the inverted-residual triples replaced by one
         fused step (measured faster for every block, tools/kbench_mb.py), and the output tail by its fused kernel."""
+        from ._cabi import lib
         impl = self.mbconv_impl or "auto"
         if mode != "bf16" or dense_impl != "tc":
             return self.steps
-        key = (impl, self.tail_impl, H, W)
+        key = (impl, self.tail_impl, self.head_impl, H, W, in_dtype)
         if key not in self._eval_sched:
             first = {id(e): (e, d, pj) for e, d, pj in self._mb_triples()}
             out, skip = [], set()
@@ -280,6 +282,16 @@ class Engine:
                         skip.update((id(d), id(pj)))
                         continue
                 out.append(st)
+            # head of MobileNetV2UNet: features.0 (stem) -> features.1 (depthwise + linear 1x1) as one kernel
+            if (self.head_impl != "unfused" and len(out) >= 3 and out[0].op == "stem" and out[1].op == "dw"
+                    and out[2].op == "dense" and out[1].src == out[0].dst and out[2].src == out[1].dst
+                    and out[0].stride == 2 and out[1].stride == 1 and out[2].taps == 1 and out[2].res is None
+                    and out[0].act == ACT_RELU6 and out[1].act == ACT_RELU6 and out[2].act == ACT_NONE and not out[2].pad_cout
+                    and in_dtype in (torch.float32, torch.bfloat16)
+                    and not any(t.src in (out[0].dst, out[1].dst) or t.res in (out[0].dst, out[1].dst) for t in out[3:])
+                    and lib.b200seg_stem_mb1_supported(ops.F32 if in_dtype == torch.float32 else ops.BF16, H, W, out[0].conv.weight.shape[0], out[2].conv.weight.shape[0])):
+                st0, dw1, pw1 = out[0], out[1], out[2]
+                out = [Step("stem_mb1", "backbone.features.0+1", st0.src, pw1.dst, parts=(st0, dw1, pw1))] + out[3:]
             # output tail of MobileNetV2UNet: outc.conv.0 -> outc.conv.3 -> final_upsample (+ argmax) as one kernel
             if (self.tail_impl != "unfused" and len(out) >= 3 and out[-1].op == "final" and self.out_ch <= 16
                     and out[-2].op == "dense" and out[-3].op == "dense" and out[-2].taps == 1 and out[-3].taps == 1
@@ -317,11 +329,12 @@ class Engine:
             raise RuntimeError(f"input on {x.device} but model on {p0.device}")
 
     # ------------------------------------------------------------------ forward (eval)
-    def _run_step(self, s: Step, env, pk, mode: str, sdt, dense_impl: str, out_dtype, want_mask: bool):
-        """Launch the kernel of one fused step; inputs/outputs live in ``env`` by schedule name."""
+    def _run_step(self, s: Step, env, pk, mode: str, sdt, dense_impl: str, out_dtype, want_mask: bool, out=None):
+        """Launch the kernel of one fused step; inputs/outputs live in ``env`` by schedule name.  ``out``: existing output
+        buffer (only for the head step, which is launched outside the captured graph into a static buffer)."""
         if s.op == "stem":
             p = pk[s.name]
-            env[s.dst] = ops.conv3x3_smallcin(env[s.src], p["w"], p["b"], s.stride, s.act, sdt)
+            env[s.dst] = ops.conv3x3_smallcin(env[s.src], p["w"], p["b"], s.stride, s.act, sdt, out=out)
         elif s.op == "dw":
             p = pk[s.name]
             if mode == "bf16" and self.dw_impl == "tc":
@@ -339,6 +352,9 @@ class Engine:
                 env[s.dst] = ops.conv_tc(env[s.src], p["w"], p["b"], s.taps, s.act, res, flags=self.tc_flags)
             else:
                 env[s.dst] = ops.conv_simt(env[s.src], p["w"], p["b"], s.taps, s.act, res)
+        elif s.op == "stem_mb1":
+            p0, p1, p2 = (pk[q.name] for q in s.parts)
+            env[s.dst] = ops.stem_mb1(env[s.src], p0["w"], p0["b"], p1["wb"], p1["b"], p2["w"], p2["b"], out=out)
         elif s.op == "mbconv":
             p = pk[s.parts[2].name + "#mb"]
             env[s.dst] = ops.mbconv(env[s.src], p["w_exp"], p["b_exp"], p["w_dw"], p["b_dw"], p["w_proj"], p["b_proj"],
@@ -385,10 +401,10 @@ class Engine:
         x = x.contiguous()
         out_dtype = x.dtype
         args = (pk, mode, sdt, dense_impl, out_dtype, want_mask)
-        steps = self._schedule(mode, dense_impl, x.shape[2], x.shape[3])
+        steps = self._schedule(mode, dense_impl, x.shape[2], x.shape[3], x.dtype)
 
         if keep is None and profile is None and self.use_graphs and not torch.cuda.is_current_stream_capturing():
-            key = (tuple(x.shape), x.dtype, mode, dense_impl, self.dw_impl, self.mbconv_impl, self.tail_impl, self.tc_flags,
+            key = (tuple(x.shape), x.dtype, mode, dense_impl, self.dw_impl, self.mbconv_impl, self.tail_impl, self.head_impl, self.tc_flags,
                    self.mbconv_flags, self._packed_key, x.device)
             ent = self._graphs.get(key)
             if ent is None:
@@ -399,8 +415,8 @@ class Engine:
             if ent["graph"] is None and ent["seen"] > self.graph_after:
                 self._capture(ent, x, args, steps)
             if ent["graph"] is not None:
-                env = {"x": x, ent["head_dst"]: ent["head_out"]}
-                ops.conv3x3_smallcin(x, *ent["head_args"], out=ent["head_out"])
+                env = {"x": x}
+                self._run_step(ent["head"], env, *args, out=ent["head_out"])
                 ent["graph"].replay()
                 env[ent["tail"].src] = ent["body_out"]
                 self._run_step(ent["tail"], env, *args)
@@ -424,10 +440,8 @@ class Engine:
         graph's private pool and stay valid for every replay."""
         pk, mode, sdt, dense_impl, out_dtype, want_mask = args
         head, body, tail = steps[0], steps[1:-1], steps[-1]
-        assert head.op == "stem" and tail.op in ("final", "to_nchw", "tail")
-        p = pk[head.name]
-        ent["head_args"] = (p["w"], p["b"], head.stride, head.act, sdt)
-        ent["head_dst"] = head.dst
+        assert head.op in ("stem", "stem_mb1") and tail.op in ("final", "to_nchw", "tail")
+        ent["head"] = head
         env = {"x": x}
         self._run_step(head, env, *args)
         ent["head_out"] = env[head.dst]
@@ -452,6 +466,12 @@ class Engine:
             npix = env[s.src].numel() // env[s.src].shape[-1]
             nbytes += (c0.conv.weight.numel() + c3.conv.weight.numel()) * 2 + 2 * 16 * 4
             return nbytes, 2 * npix * (c0.conv.weight.numel() + c3.conv.weight.numel())
+        if s.op == "stem_mb1":
+            st0, dw1, pw1 = s.parts
+            cs, co = st0.conv.weight.shape[0], pw1.conv.weight.shape[0]
+            npix = out.numel() // out.shape[-1]
+            nbytes += 27 * cs * 4 + 9 * cs * 2 + co * cs * 2 + (2 * cs + co) * 4
+            return nbytes, 2 * npix * (27 * cs + 9 * cs + cs * co)
         if s.op == "mbconv":
             # algorithmic bytes of the FUSED block: input, output, residual and the three weight sets once
             e, d, pj = s.parts

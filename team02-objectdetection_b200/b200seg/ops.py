@@ -64,6 +64,25 @@ def conv3x3_smallcin(x_nchw, w, b, stride: int, act: int, out_dtype, out=None):
     return out
 
 
+def stem_mb1_supported(x_nchw, cstem: int, cout: int) -> bool:
+    return bool(lib.b200seg_stem_mb1_supported(_dt(x_nchw), x_nchw.shape[2], x_nchw.shape[3], cstem, cout))
+
+
+def stem_mb1(x_nchw, w_stem, b_stem, w_dw, b_dw, w_pw, b_pw, out=None):
+    """features.0 + features.1 in one kernel: NCHW f32 frames -> NHWC bf16 [B,H/2,W/2,16] (csrc/stem_mb1.cu)."""
+    _cuda(x_nchw, w_stem, b_stem, w_dw, b_dw, w_pw, b_pw)
+    B, C, H, W = x_nchw.shape
+    if C != 3 or not x_nchw.is_contiguous():
+        raise ValueError("stem_mb1 expects a contiguous NCHW tensor with 3 channels")
+    if w_dw.dtype != torch.bfloat16 or w_pw.dtype != torch.bfloat16 or w_stem.dtype != torch.float32:
+        raise TypeError("stem_mb1: w_stem f32, w_dw / w_pw bf16")
+    if out is None:
+        out = torch.empty((B, H // 2, W // 2, w_pw.shape[0]), device=x_nchw.device, dtype=torch.bfloat16)
+    check(lib.b200seg_stem_mb1(ptr(x_nchw), _dt(x_nchw), ptr(w_stem), ptr(b_stem), ptr(w_dw), ptr(b_dw), ptr(w_pw), ptr(b_pw),
+                               ptr(out), B, H, W, _stream()), "stem_mb1")
+    return out
+
+
 def dwconv3x3(x, w9c, b, stride: int, act: int, out=None):
     """x NHWC; w9c f32 [9,C]."""
     _cuda(x, w9c, b)

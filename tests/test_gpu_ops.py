@@ -312,3 +312,33 @@ def test_conv_tc_dispatches_small_cout_3x3_to_conv_rs():
     assert lib.b200seg_conv_rs_supported(64, 128, 152, 64) == 0          # 64 output channels: 3 accumulators exceed TMEM
     assert lib.b200seg_conv_rs_supported(32, 64, 32, 32) == 0            # narrow map: conv_tc's 2-D tiles
     assert lib.b200seg_conv_rs_supported(128, 256, 1344, 32) == 0        # weights would not stay resident
+
+
+# ------------------------------------------------------------------------------------------------
+# fused head: features.0 (stem 3x3 s2 + ReLU6) -> features.1 (depthwise 3x3 + ReLU6 -> linear 1x1) (stem_mb1.cu)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("xdt", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("B,H,W", [(2, 64, 128), (1, 16, 64), (3, 34, 136), (1, 2, 8), (2, 256, 512)])
+def test_stem_mb1_matches_the_three_ops_it_replaces(B, H, W, xdt):
+    x = _rand(B, 3, H, W, seed=31).to(xdt)
+    w0 = _rand(32, 3, 3, 3, seed=32, scale=(2.0 / 27) ** 0.5)
+    b0 = _rand(32, seed=33, scale=0.3)
+    wd = _rand(32, 1, 3, 3, seed=34, scale=0.4).bfloat16().float()
+    bd = _rand(32, seed=35, scale=0.3)
+    wp = _rand(16, 32, seed=36, scale=(1.0 / 32) ** 0.5).bfloat16()
+    bp = _rand(16, seed=37, scale=0.2)
+    # float64 reference with the kernel's rounding points: bf16 input and stem weights, both intermediates rounded to bf16
+    e = torch.clamp(F.conv2d(x.bfloat16().double(), w0.bfloat16().double(), b0.double(), 2, 1), 0, 6).bfloat16().double()
+    d = torch.clamp(F.conv2d(e, wd.double(), bd.double(), 1, 1, 1, 32), 0, 6).bfloat16().double()
+    ref = F.conv2d(d, wp.double()[:, :, None, None], bp.double())
+    w0k = w0.permute(2, 3, 1, 0).contiguous()                      # [kh][kw][c][32]
+    wdk = wd.reshape(32, 9).t().contiguous().bfloat16()            # [9][32]
+    got = ops.stem_mb1(x, w0k, b0, wdk, bd, wp, bp)
+    torch.cuda.synchronize()
+    assert got.shape == (B, H // 2, W // 2, 16)
+    assert _err(_nchw(got), ref) < TOL[torch.bfloat16]
+    # and against the three kernels it replaces (same rounding points: equal up to fp32 summation order)
+    s0 = ops.conv3x3_smallcin(x, w0k, b0, 2, 2, torch.bfloat16)
+    s1 = ops.dwconv3x3_bf16w(s0, wdk, bd, 1, 2)
+    s2 = ops.conv_tc(s1, wp, bp, 1, 0)
+    assert _err(got.float(), s2.double()) < 8e-3

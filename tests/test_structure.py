@@ -132,13 +132,18 @@ def test_fused_schedule_replaces_the_inverted_residual_triples():
     assert len(eng._mb_triples()) == 16
     sched = eng._schedule("bf16", "tc", 256, 512)
     fused = [s for s in sched if s.op == "mbconv"]
-    assert len(fused) == 16 and len(sched) == 33
+    assert len(fused) == 16 and len(sched) == 31
+    assert sched[0].op == "stem_mb1" and [p.name for p in sched[0].parts] == [
+        "backbone.features.0", "backbone.features.1.conv.0", "backbone.features.1.conv.1"]
+    assert eng._schedule("bf16", "tc", 256, 512, torch.bfloat16)[0].op == "stem_mb1"  # bf16 frames too (the bench's input)
+    assert eng._schedule("bf16", "tc", 258, 516, torch.bfloat16)[0].op == "stem"      # bf16 rows not 16-byte multiples: layer by layer
     assert all(s.parts[1].stride in (1, 2) and s.parts[0].src == s.src and s.parts[2].dst == s.dst for s in fused)
     assert sched[-1].op == "tail" and [p.name for p in sched[-1].parts] == ["outc.conv.0", "outc.conv.3", "final_upsample"]
-    n_convs = sum(3 if s.op == "mbconv" else 2 if s.op == "tail" else 1 for s in sched if s.op in ("stem", "dw", "dense", "mbconv", "tail"))
+    n_convs = sum(3 if s.op in ("mbconv", "stem_mb1") else 2 if s.op == "tail" else 1 for s in sched
+                  if s.op in ("stem", "dw", "dense", "mbconv", "tail", "stem_mb1"))
     assert n_convs == 62
     assert eng._schedule("fp32", "simt", 256, 512) is eng.steps               # the exact path is never fused
-    eng.mbconv_impl, eng.tail_impl = "unfused", "unfused"
+    eng.mbconv_impl, eng.tail_impl, eng.head_impl = "unfused", "unfused", "unfused"
     assert [s.name for s in eng._schedule("bf16", "tc", 256, 512)] == [s.name for s in eng.steps]
     m17 = b200seg.MobileNetV2UNet(output_channels=17)                          # > 16 classes: the generic tail kernels
     assert m17._get_engine()._schedule("bf16", "tc", 256, 512)[-1].op == "final"
