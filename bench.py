@@ -67,6 +67,7 @@ def peaks():
     return dict(hbm=6650.0, tc_burst=1590.0, tc=1400.0, src="fallback")
 
 
+E2E_TRACE = [] if os.environ.get("B200SEG_E2E_TRACE") else None     # debug: (host time, device event) after every e2e step
 LEAD_IN = 4         # untimed steps queued ahead of the timed window (see the value leg)
 
 
@@ -82,6 +83,7 @@ class ClockSampler:
     def __init__(self, index=0):
         self.rows, self.proc, self.index, self.first = [], None, index, 0
         self.nvml, self.handle, self.stop_flag, self.thread, self.max_mhz = None, None, False, None, None
+        self.poll_log = []
 
     def start(self):
         try:
@@ -109,8 +111,10 @@ class ClockSampler:
                  ("sw_thermal_slowdown", n.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksEventReasonSwPowerCap))
         while not self.stop_flag:
             try:
+                _t = time.perf_counter()
                 mhz = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
                 mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                self.poll_log.append((_t, time.perf_counter()))
                 self.rows.append([str(mhz), str(self.max_mhz)] + [("Active" if mask & bit else "Not Active") for _, bit in names])
             except Exception:                               # noqa: BLE001
                 pass
@@ -267,8 +271,12 @@ def main():
     # ---------------- value leg: inputs resident in HBM ----------------
     settle = 30        # extra untimed steps after the W warm-up steps: the first ~10 replays after capture run 3-5 % slow
     with torch.no_grad():
+        y = None
         for i in range(args.warmup + settle):
-            model(xs[i % nrot])
+            # bound to a name exactly like the timed loop: the loop then needs TWO output blocks alive at a time (the new
+            # result is allocated before the old one is released); a warm-up that drops its result keeps only one in the
+            # caching allocator and the second timed step pays a 168 MB cudaMalloc (20-160 ms, host AND device stalled)
+            y = model(xs[i % nrot])
         barrier()
         clocks.mark()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -277,13 +285,23 @@ def main():
         # clock sampler's NVML query holds a driver lock for milliseconds now and then) otherwise shows up as a 30 %
         # slower "step".  The events still bracket EXACTLY args.steps steps, executed back to back on the device.
         for i in range(LEAD_IN):
-            model(xs[i % nrot])
+            y = model(xs[i % nrot])
         e0.record()
+        vtrace = []
         for i in range(args.steps):
             y = model(xs[(i + LEAD_IN) % nrot])
+            if E2E_TRACE is not None:
+                ev = torch.cuda.Event(enable_timing=True); ev.record()
+                vtrace.append((time.perf_counter(), ev))
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
+        if vtrace and rank == 0:
+            h0 = vtrace[0][0]
+            print("value trace (step: host issue ms, device done ms): " +
+                  " ".join(f"{i}:{(h - h0) * 1e3:.1f}/{e0.elapsed_time(d):.1f}" for i, (h, d) in enumerate(vtrace)), file=sys.stderr)
+            print("sampler polls (start ms, duration ms): " + " ".join(f"{(a - h0) * 1e3:.1f}/{(b - a) * 1e3:.2f}" for a, b in clocks.poll_log[-12:]),
+                  file=sys.stderr)
         clk = clocks.stop() if rank == 0 else None
         # sustained figure: the same loop for >= --sustain-seconds (power/thermals settled), reported beside `value`
         n_sus = max(args.steps, int(args.sustain_seconds * 1e3 / max(ms / args.steps, 1e-3)))
@@ -302,6 +320,10 @@ def main():
     mh = [torch.empty(B, H, W, dtype=torch.uint8).pin_memory() for _ in range(2)]
     xd = [torch.empty(B, H, W, 3, dtype=torch.uint8, device=dev) for _ in range(2)]
     xn = [torch.empty(B, 3, H, W, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+    md = [torch.empty(B, H, W, dtype=torch.uint8, device=dev) for _ in range(2)]      # device masks, double-buffered: no
+    # per-frame allocation (a fresh mask handed to the download stream with record_stream() cannot be recycled until its
+    # event completes; with the host several frames ahead the caching allocator fell back to cudaMalloc/cudaFree -- a
+    # device-wide sync of 20-170 ms in the middle of the timed window)
     copy_s, out_s, comp_s = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.current_stream()
     own_d2h = os.environ.get("B200SEG_E2E_D2H_STREAM", "1") != "0"
 
@@ -312,6 +334,7 @@ def main():
         # inside the window -- n uploads, n forwards and n downloads are timed.
         ev_in = [torch.cuda.Event() for _ in range(2)]
         ev_free = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event() for _ in range(2)]
         for i in range(lead + n):
             k = i & 1
             if i == lead and t_start is not None:
@@ -323,25 +346,37 @@ def main():
                 ev_in[k].record(copy_s)
             comp_s.wait_event(ev_in[k])
             b200seg.preprocess_image(xd[k], target_size=(W, H), dtype=torch.bfloat16, out=xn[k], want_rgb=False)
-            mask = model.predict_mask(xn[k])
+            if i >= 2:
+                comp_s.wait_event(ev_out[k])             # the download of frame i-2 has left md[k]
+            mask = model.predict_mask(xn[k], out=md[k])
             ev_free[k].record(comp_s)
+            if E2E_TRACE is not None:
+                ev = torch.cuda.Event(enable_timing=True); ev.record(comp_s)
+                E2E_TRACE.append((time.perf_counter(), ev))
             if own_d2h:
                 with torch.cuda.stream(out_s):           # the D2H of the mask overlaps the next forward as well (own stream:
                     out_s.wait_event(ev_free[k])         # on the H2D stream it would hold back the next frame upload)
-                    mask.record_stream(out_s)
                     mh[k].copy_(mask, non_blocking=True)
+                    ev_out[k].record(out_s)
             else:
                 mh[k].copy_(mask, non_blocking=True)
+                ev_out[k].record(comp_s)
         torch.cuda.synchronize()
 
     with torch.no_grad():
         e2e_steps(max(12, args.warmup))         # untimed: first touches of the pinned buffers / copy engines on a fresh box
         barrier()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if E2E_TRACE is not None:
+            E2E_TRACE.clear()
         e2e_steps(args.steps, LEAD_IN, t0)
         t1.record()
         barrier()
         ms_e2e = t0.elapsed_time(t1)
+        if E2E_TRACE is not None and rank == 0:
+            h0, d0 = E2E_TRACE[0]
+            print("e2e trace (step: host issue ms, device done ms): " +
+                  " ".join(f"{i}:{(h - h0) * 1e3:.1f}/{d0.elapsed_time(d):.1f}" for i, (h, d) in enumerate(E2E_TRACE)), file=sys.stderr)
 
     # ---------------- per-kernel roofline (live, CUDA events on the launch stream) ----------------
     pk = peaks()

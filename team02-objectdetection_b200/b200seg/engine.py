@@ -123,16 +123,38 @@ class Engine:
         self._train_ws = None             # gradient arena + staging (train_path.TrainWorkspace)
 
     # ------------------------------------------------------------------ weights
+    def _version_items(self):
+        """(owning dict, name, tensor) of every parameter and buffer, built once: walking the module tree through
+        ``model.parameters()`` costs ~1 ms of host time per forward (379 tensors), more than half of what the host spends on a
+        whole 1.9 ms inference step."""
+        items = []
+        for mod in self.model.modules():
+            for d in (mod._parameters, mod._buffers):
+                for name, t in d.items():
+                    if t is not None:
+                        items.append((d, name, t))
+        return items
+
     def _version_key(self, mode: str):
+        items = getattr(self, "_ver_items", None)
+        if items is None:
+            items = self._ver_items = self._version_items()
         v = 0
-        for t in self.model.parameters():
+        for d, name, t in items:
+            if d.get(name) is not t:          # a parameter/buffer object was replaced (load_state_dict(assign=True), p = nn.Parameter(..))
+                items = self._ver_items = self._version_items()
+                v = -1
+                break
             v += t._version
-        for t in self.model.buffers():
-            v += t._version
-        p0 = next(self.model.parameters())
+        if v < 0:
+            v = 0
+            for d, name, t in items:
+                v += t._version
+            # id(items) in the key forces a re-fold: the tensors themselves changed
+        p0 = items[0][2]
         # ops.mutation_epoch: bumped by everything that writes parameters / BN buffers through raw pointers (b200seg.Adam,
         # the training forward and its CUDA-graph replays) -- those writes do not touch tensor._version
-        return (mode, self.dense_impl, v, ops.mutation_epoch(), p0.device, p0.data_ptr())
+        return (mode, self.dense_impl, v, ops.mutation_epoch(), p0.device, p0.data_ptr(), id(items))
 
     def _eval_plan(self, mode: str, dense_impl: str):
         """Persistent eval operand buffers + the device table of the one-launch fold/pack kernel
@@ -228,8 +250,10 @@ class Engine:
         """Folded + packed eval weights for the current parameter values: ONE kernel launch when anything changed."""
         from ._cabi import check, lib, ptr
         dense_impl = self.dense_impl or ("tc" if mode == "bf16" else "simt")
-        plan = self._eval_plan(mode, dense_impl)
         key = self._version_key(mode)
+        if key == self._packed_key:           # nothing written since the last fold (the steady-state inference call): ~0.1 ms of
+            return self._packed               # host time instead of ~1.5 ms for re-deriving the operand plan's identity
+        plan = self._eval_plan(mode, dense_impl)
         if key != self._packed_key:
             if plan["mirror_src"]:
                 with torch.no_grad():
@@ -361,27 +385,27 @@ class Engine:
                                     s.stride, s.res is not None, flags=self.mbconv_flags)
         elif s.op == "tail":
             p0, p3 = pk[s.parts[0].name], pk[s.parts[1].name]
-            env[s.dst] = ops.tail_fused(env[s.src], p0["w"], p0["b64"], p3["w"], p3["b64"], self.out_ch, out_dtype, want_mask)
+            env[s.dst] = ops.tail_fused(env[s.src], p0["w"], p0["b64"], p3["w"], p3["b64"], self.out_ch, out_dtype, want_mask, out=out)
         elif s.op == "upcat":
             env[s.dst] = ops.upsample2x_concat(env[s.res], env[s.src])
         elif s.op == "pool":
             env[s.dst] = ops.maxpool2x2(env[s.src])
         elif s.op == "final":
             if want_mask:
-                env[s.dst] = ops.upsample2x_ac_argmax(env[s.src], self.out_ch)
+                env[s.dst] = ops.upsample2x_ac_argmax(env[s.src], self.out_ch, out=out)
             else:
-                env[s.dst] = ops.upsample2x_ac_nchw(env[s.src], self.out_ch, out_dtype)
+                env[s.dst] = ops.upsample2x_ac_nchw(env[s.src], self.out_ch, out_dtype, out=out)
         elif s.op == "to_nchw":
             if want_mask:
-                env[s.dst] = ops.nhwc_argmax(env[s.src], self.out_ch)
+                env[s.dst] = ops.nhwc_argmax(env[s.src], self.out_ch, out=out)
             else:
-                env[s.dst] = ops.nhwc_to_nchw(env[s.src], self.out_ch, out_dtype)
+                env[s.dst] = ops.nhwc_to_nchw(env[s.src], self.out_ch, out_dtype, out=out)
         else:  # pragma: no cover
             raise AssertionError(s.op)
 
     @torch.no_grad()
     def forward_eval(self, x: torch.Tensor, want_mask: bool = False, keep: Optional[dict] = None,
-                     profile: Optional[list] = None):
+                     profile: Optional[list] = None, out=None):
         """Eval-mode forward.  ``keep`` (dict) receives every intermediate NHWC tensor by schedule name;
         ``profile`` (list) receives (step, start_event, end_event, bytes, flops) per launched kernel.
 
@@ -419,14 +443,14 @@ class Engine:
                 self._run_step(ent["head"], env, *args, out=ent["head_out"])
                 ent["graph"].replay()
                 env[ent["tail"].src] = ent["body_out"]
-                self._run_step(ent["tail"], env, *args)
+                self._run_step(ent["tail"], env, *args, out=out)
                 return env["out"]
 
         env: Dict[str, torch.Tensor] = {"x": x}
         for s in steps:
             if profile is not None:
                 ev0 = torch.cuda.Event(enable_timing=True); ev0.record()
-            self._run_step(s, env, *args)
+            self._run_step(s, env, *args, out=out if s is steps[-1] else None)
             if profile is not None:
                 ev1 = torch.cuda.Event(enable_timing=True); ev1.record()
                 nbytes, flops = self.step_cost(s, env, pk)
@@ -500,7 +524,7 @@ class Engine:
         return nbytes, flops
 
     # ------------------------------------------------------------------ dispatch
-    def forward(self, x: torch.Tensor, want_mask: bool = False):
+    def forward(self, x: torch.Tensor, want_mask: bool = False, out=None):
         # every kernel is launched on the current stream of the CURRENT device: make the input's device current for the
         # whole call (model.to("cuda:1") while cuda:0 is current must work like any nn.Module)
         with torch.cuda.device(x.device):
@@ -509,4 +533,4 @@ class Engine:
                     raise RuntimeError("predict_mask needs model.eval()")
                 from . import train_path
                 return train_path.forward_train(self, x)
-            return self.forward_eval(x, want_mask)
+            return self.forward_eval(x, want_mask, out=out)

@@ -265,7 +265,7 @@ def upsample2x_ac_argmax(logits, C: int, out=None):
     return out
 
 
-def tail_fused(x, w0, b0, w3, b3, C: int, out_dtype=None, want_mask: bool = False):
+def tail_fused(x, w0, b0, w3, b3, C: int, out_dtype=None, want_mask: bool = False, out=None):
     """outconv(32, C) + final_upsample (+ argmax) in one kernel.  x NHWC bf16 [B,h,w,32]; w0 bf16 [16,32], b0 f32 [>=16];
     w3 bf16 [16,16], b3 f32 [>=16].  Returns NCHW [B,C,2h,2w] of out_dtype, or the uint8 mask [B,2h,2w]."""
     _cuda(x, w0, b0, w3, b3)
@@ -273,12 +273,19 @@ def tail_fused(x, w0, b0, w3, b3, C: int, out_dtype=None, want_mask: bool = Fals
     if (x.dtype != torch.bfloat16 or cin != 32 or tuple(w0.shape) != (16, 32) or tuple(w3.shape) != (16, 16)
             or w0.dtype != torch.bfloat16 or w3.dtype != torch.bfloat16 or b0.numel() < 16 or b3.numel() < 16 or not 1 <= C <= 16):
         raise ValueError("tail_fused: expects the MobileNetV2UNet tail (32 -> 16 -> C <= 16 channels, bf16)")
+    if out is not None:
+        want = (B, 2 * h, 2 * w) if want_mask else (B, C, 2 * h, 2 * w)
+        if (tuple(out.shape) != want or out.dtype != (torch.uint8 if want_mask else out_dtype) or not out.is_contiguous()
+                or out.device != x.device):
+            raise ValueError(f"tail_fused: out must be a contiguous {want} tensor of the result dtype on {x.device}")
     if want_mask:
-        out = torch.empty((B, 2 * h, 2 * w), device=x.device, dtype=torch.uint8)
+        if out is None:
+            out = torch.empty((B, 2 * h, 2 * w), device=x.device, dtype=torch.uint8)
         check(lib.b200seg_tail_fused(ptr(x), ptr(w0), ptr(b0), ptr(w3), ptr(b3), None, F32, ptr(out), B, h, w, C, _stream()),
               "tail_fused")
     else:
-        out = torch.empty((B, C, 2 * h, 2 * w), device=x.device, dtype=out_dtype)
+        if out is None:
+            out = torch.empty((B, C, 2 * h, 2 * w), device=x.device, dtype=out_dtype)
         check(lib.b200seg_tail_fused(ptr(x), ptr(w0), ptr(b0), ptr(w3), ptr(b3), ptr(out), _dt(out), None, B, h, w, C, _stream()),
               "tail_fused")
     return out

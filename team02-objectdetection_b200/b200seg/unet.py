@@ -171,10 +171,11 @@ class _EngineModel(nn.Module):
         return self._get_engine().forward(x)
 
     @torch.no_grad()
-    def predict_mask(self, x: torch.Tensor) -> torch.Tensor:
+    def predict_mask(self, x: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
         """Fused final-upsample + argmax -> uint8 class mask [B,H,W] (what inference.py:64-65
-        computes on the host from the logits).  Eval mode only."""
-        return self._get_engine().forward(x, want_mask=True)
+        computes on the host from the logits).  Eval mode only.  ``out``: an existing uint8 [B,H,W] tensor to write
+        (a frame loop that hands the mask to another stream keeps two of them instead of allocating per frame)."""
+        return self._get_engine().forward(x, want_mask=True, out=out)
 
 
 class MobileNetV2UNet(_EngineModel):
