@@ -32,7 +32,7 @@ template <typename TI> struct PatchGeo {
   static constexpr int VL = 16 / (int)sizeof(TI);
   static constexpr int LEAD = VL;
   static constexpr int PC = (LEAD - 3 + 69 + VL - 1) / VL * VL;      // 72 (f32) | 80 (bf16)
-  static constexpr int BYTES = (3 * (2 * (8 + 2) + 1) * PC * 4 + 127) / 128 * 128;
+  static constexpr int BYTES = (3 * (2 * (8 + 2) + 1) * PC * (int)sizeof(TI) + 127) / 128 * 128;   // one raw patch buffer
 };
 constexpr int SM_CS = 32, SM_CO = 16;                // stem / projection output channels
 constexpr int SM_EP = 40;                            // bf16 pitch of E and D rows: 20 words -> conflict-free fragment accesses
@@ -40,7 +40,17 @@ constexpr int SM_OP = 24;                            // bf16 pitch of the staged
 constexpr int SM_E_BYTES = SM_NHALO * SM_EP * 2;               // 27200
 constexpr int SM_D_BYTES = SM_TH * SM_TW * SM_EP * 2;          // 20480
 constexpr int SM_W_BYTES = SM_CS * SM_EP * 2;                   // stem weights as bf16 [32 n][32 k] (k = c*9+kh*3+kw), pitch 40
-template <typename TI> constexpr int sm_smem() { return PatchGeo<TI>::BYTES + SM_E_BYTES + SM_D_BYTES + SM_W_BYTES; }
+template <typename TI> constexpr int sm_smem() { return 2 * PatchGeo<TI>::BYTES + SM_E_BYTES + SM_D_BYTES + SM_W_BYTES; }
+
+// 16-byte asynchronous global -> shared copy; src_bytes = 0 writes zeros (pixels outside the image)
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float patch_f32(const float* p, int i) { return p[i]; }
+__device__ __forceinline__ float patch_f32(const __nv_bfloat16* p, int i) { return __bfloat162float(p[i]); }
 
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -68,10 +78,10 @@ stem_mb1_kernel(const TI* __restrict__ x, const float* __restrict__ w_stem, cons
                 int B, int H, int W, int Ho, int Wo, int tiles_h, int tiles_w) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int SM_PC = PatchGeo<TI>::PC, LEAD = PatchGeo<TI>::LEAD;
-  float* patch = reinterpret_cast<float*>(smem);                           // [3][21][PC] f32; later the staged output
-  uint8_t* sE = smem + PatchGeo<TI>::BYTES;                                // [340][40] bf16
+  // two raw input patches [3][21][PC] in the input type: the patch of the NEXT tile streams in (cp.async) while this tile computes
+  uint8_t* sE = smem + 2 * PatchGeo<TI>::BYTES;                            // [340][40] bf16
   uint8_t* sD = sE + SM_E_BYTES;                                           // [256][40] bf16
-  uint8_t* sO = smem;                                                      // [256][24] bf16 (aliases the dead patch)
+  uint8_t* sO = sE;                                                        // [256][24] bf16 staged output (E is dead by then)
   uint8_t* sW = sD + SM_D_BYTES;                                           // stem weights, bf16 [32][40]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -100,32 +110,40 @@ stem_mb1_kernel(const TI* __restrict__ x, const float* __restrict__ w_stem, cons
   const long long HW = (long long)H * W;
   const int total = B * tiles_h * tiles_w;
 
-  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+  auto issue_patch = [&](const int tile, const int buf) {
     int q = tile;
     const int w0 = (q % tiles_w) * SM_TW; q /= tiles_w;
     const int h0 = (q % tiles_h) * SM_TH;
     const int b = q / tiles_h;
     const TI* xb = x + (long long)b * 3 * HW;
     const int hi0 = 2 * h0 - 3, wi0 = 2 * w0 - LEAD;        // input coordinates of patch[.][0][0]
-    __syncthreads();                                        // previous tile's output has left the staging area
-    // ---- 1. input patch ----
+    TI* dst = reinterpret_cast<TI*>(smem + buf * PatchGeo<TI>::BYTES);
     for (int i = tid; i < 3 * SM_PR * (SM_PC / VL); i += 256) {
       const int rowi = i / (SM_PC / VL), v = i - rowi * (SM_PC / VL);
       const int c = rowi / SM_PR, pr = rowi - c * SM_PR;
       const int hi = hi0 + pr, wi = wi0 + v * VL;
-      float f[VL];
-      if (hi >= 0 && hi < H && wi >= 0 && wi < W) {         // W % VL == 0 and wi % VL == 0: never straddles the border
-        Vec16<TI> tv;
-        tv.load(xb + (long long)c * HW + (long long)hi * W + wi);
-#pragma unroll
-        for (int e = 0; e < VL; ++e) f[e] = tv.v[e];
-      } else {
-#pragma unroll
-        for (int e = 0; e < VL; ++e) f[e] = 0.f;
-      }
-#pragma unroll
-      for (int e = 0; e < VL; e += 4)
-        *reinterpret_cast<float4*>(patch + rowi * SM_PC + v * VL + e) = make_float4(f[e], f[e + 1], f[e + 2], f[e + 3]);
+      const bool ok = hi >= 0 && hi < H && wi >= 0 && wi < W;   // W % VL == 0 and wi % VL == 0: never straddles the border
+      cp_async16(dst + rowi * SM_PC + v * VL, ok ? xb + (long long)c * HW + (long long)hi * W + wi : x, ok ? 16 : 0);
+    }
+    cp_async_commit();
+  };
+
+  int buf = 0;
+  if ((int)blockIdx.x < total) issue_patch(blockIdx.x, 0);
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x, buf ^= 1) {
+    int q = tile;
+    const int w0 = (q % tiles_w) * SM_TW; q /= tiles_w;
+    const int h0 = (q % tiles_h) * SM_TH;
+    const int b = q / tiles_h;
+    const TI* patch = reinterpret_cast<const TI*>(smem + buf * PatchGeo<TI>::BYTES);
+    // ---- 1. input patch: prefetch the next tile's, wait for this tile's ----
+    __syncthreads();                                        // the other buffer's readers (previous tile's stem phase) and the
+                                                            // previous tile's staged output (aliases E) are done
+    if (tile + (int)gridDim.x < total) {
+      issue_patch(tile + gridDim.x, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
     // ---- 2. stem on the halo pixels -> E ----
@@ -160,7 +178,7 @@ stem_mb1_kernel(const TI* __restrict__ x, const float* __restrict__ w_stem, cons
           for (int rr = 0; rr < 2; ++rr) {
             float v[2];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) v[e] = koff[ks][h][e] >= 0 ? patch[koff[ks][h][e] + poff[rr]] : 0.f;
+            for (int e = 0; e < 2; ++e) v[e] = koff[ks][h][e] >= 0 ? patch_f32(patch, koff[ks][h][e] + poff[rr]) : 0.f;
             afr[ks][h * 2 + rr] = pack_bf16x2(v[0], v[1]);
           }
       float acc[4][4];
