@@ -383,38 +383,49 @@ def main():
     acc = {}
     with torch.no_grad():
         for it in range(3 + 5):
-            prof = []
-            eng.forward_eval(xs[it % nrot], profile=prof)
+            prof, penv = [], {}
+            ppk = eng._pack_eval(eng._mode(xs[0]))
+            eng.forward_eval(xs[it % nrot], profile=prof, keep=penv)
             torch.cuda.synchronize()
             if it < 3:
                 continue
             for s, a, b, nbytes, flops in prof:
                 r = acc.setdefault(s.name, dict(op=s.op, taps=s.taps, ms=0.0, bytes=nbytes, flops=flops, n=0,
+                                                lbytes=eng.layer_model_bytes(s, penv, ppk),
                                                 shape=(tuple(s.conv.weight.shape) if s.op == "dense" else None)))
                 r["ms"] += a.elapsed_time(b); r["n"] += 1
+    FUSED = ("mbconv", "stem_mb1", "tail")
     rows = []
     for name, r in acc.items():
         t = r["ms"] / r["n"] * 1e-3
-        gbs, tfs = r["bytes"] / t / 1e9, r["flops"] / t / 1e12
-        bound = "tensor" if (r["flops"] / max(r["bytes"], 1)) > pk["tc"] * 1e3 / pk["hbm"] else "hbm"
-        rows.append(dict(name=name, op=r["op"], us=t * 1e6, gbs=gbs, tfs=tfs, bound=bound, bytes=r["bytes"], flops=r["flops"],
-                         shape=r["shape"], taps=r["taps"],
+        # HBM figure per SURVEY 8(d)'s per-LAYER traffic model (lbytes: a fused kernel is credited with the layers it replaces);
+        # gbs_io = the same on the kernel's own input + output bytes.  Unfused kernels: identical.
+        gbs, gbs_io, tfs = r["lbytes"] / t / 1e9, r["bytes"] / t / 1e9, r["flops"] / t / 1e12
+        bound = "tensor" if (r["flops"] / max(r["lbytes"], 1)) > pk["tc"] * 1e3 / pk["hbm"] else "hbm"
+        rows.append(dict(name=name, op=r["op"], us=t * 1e6, gbs=gbs, gbs_io=gbs_io, tfs=tfs, bound=bound, bytes=r["bytes"],
+                         lbytes=r["lbytes"], flops=r["flops"], shape=r["shape"], taps=r["taps"],
                          frac=(tfs / pk["tc_burst"]) if bound == "tensor" else gbs / pk["hbm"]))
     rows.sort(key=lambda r: -r["us"])
     tot_us = sum(r["us"] for r in rows)
     if args.breakdown and rank == 0:
-        print(f"{'kernel':34s} {'op':6s} {'us':>9s} {'share':>6s} {'GB/s':>8s} {'TF/s':>8s} bound  frac", file=sys.stderr)
+        print(f"{'kernel':34s} {'op':8s} {'us':>9s} {'share':>6s} {'GB/s':>8s} {'io GB/s':>8s} {'TF/s':>8s} bound  frac", file=sys.stderr)
         for r in rows:
-            print(f"{r['name']:34s} {r['op']:6s} {r['us']:9.1f} {r['us'] / tot_us:6.1%} {r['gbs']:8.0f} {r['tfs']:8.1f} "
+            print(f"{r['name']:34s} {r['op']:8s} {r['us']:9.1f} {r['us'] / tot_us:6.1%} {r['gbs']:8.0f} {r['gbs_io']:8.0f} {r['tfs']:8.1f} "
                   f"{r['bound']:6s} {r['frac']:.2f}", file=sys.stderr)
-        print(f"sum of kernels {tot_us:.0f} us; step {ms / args.steps * 1e3:.0f} us", file=sys.stderr)
+        print(f"sum of kernels {tot_us:.0f} us; step {ms / args.steps * 1e3:.0f} us   (GB/s: SURVEY 8d per-layer traffic model -- fused kernels "
+              f"are credited with the layers they replace; io GB/s: the kernel's own input + output bytes)", file=sys.stderr)
     top = rows[0]
     roofline = {"kernel": top["name"], "bound": top["bound"],
                 "achieved": top["tfs"] if top["bound"] == "tensor" else top["gbs"],
                 "peak": pk["tc_burst"] if top["bound"] == "tensor" else pk["hbm"],
                 "unit": "TFLOP/s" if top["bound"] == "tensor" else "GB/s", "frac": top["frac"], "traffic": None,
                 "peak_source": pk["src"], "share_of_step": top["us"] / tot_us,
-                "algorithmic_per_launch": top["flops"] if top["bound"] == "tensor" else top["bytes"]}
+                "algorithmic_per_launch": top["flops"] if top["bound"] == "tensor" else top["lbytes"]}
+    if top["op"] in FUSED:
+        roofline["fused_io_bytes_per_launch"] = top["bytes"]
+        roofline["frac_on_fused_io_bytes"] = top["gbs_io"] / pk["hbm"]
+        roofline["note"] = ("fused kernel: algorithmic bytes = SURVEY 8(d) per-layer model summed over the layers it replaces (their "
+                            "intermediates stay on chip, see traffic); its own bound is CUDA-core issue, DESIGN.md section 4")
     if top.get("shape"):
         # third bound of a small-N implicit GEMM: the tcgen05.mma issue floor measured by tools/mma_probe.py
         # (profiles/r01_mma_probe.txt): cycles per M=128, K=16 instruction as a function of N, per SM
@@ -439,12 +450,14 @@ def main():
     except (OSError, ValueError):
         pass
     tot_bytes = sum(r["bytes"] for r in rows)
-    survey_bytes = 115.7e6 * B if args.workload == "infer" else None      # SURVEY 8d per-image figure of the UNFUSED op list
-    step_roofline = {"bound": "hbm", "algorithmic_bytes_per_step": tot_bytes,
-                     "note": "bytes of the schedule actually run (fused inverted-residual blocks count input+output only)",
-                     "frac_vs_survey_unfused_bytes": (survey_bytes / (ms / args.steps * 1e-3) / 1e9 / pk["hbm"]) if survey_bytes else None,
-                     "achieved": tot_bytes / (ms / args.steps * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-                     "frac": tot_bytes / (ms / args.steps * 1e-3) / 1e9 / pk["hbm"]}
+    tot_lbytes = sum(r["lbytes"] for r in rows)      # = SURVEY 8d's 115.7 MB/img x B for the MobileNetV2UNet inference step
+    step_s = ms / args.steps * 1e-3
+    step_roofline = {"bound": "hbm", "algorithmic_bytes_per_step": tot_lbytes,
+                     "note": "SURVEY 8(d) per-layer traffic model (the 115.7 MB/img figure); fused_io_*: bytes the schedule actually "
+                             "has to move (fused blocks count input + output only)",
+                     "achieved": tot_lbytes / step_s / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                     "frac": tot_lbytes / step_s / 1e9 / pk["hbm"],
+                     "fused_io_bytes_per_step": tot_bytes, "frac_on_fused_io_bytes": tot_bytes / step_s / 1e9 / pk["hbm"]}
 
     # ---------------- max over ranks ----------------
     if dist is not None:

@@ -479,6 +479,32 @@ class Engine:
 
     # ------------------------------------------------------------------ cost model
     @staticmethod
+    def layer_model_bytes(s: Step, env, pk) -> int:
+        """Bytes of the step under SURVEY 8(d)'s per-LAYER traffic model ("each conv(+BN+act[+res]) reads its input once and
+        writes its output once in the storage dtype", i.e. the figure behind its 115.7 MB/img): for a kernel that fuses
+        several layers this is the SUM over the layers it replaces -- the intermediates it keeps on chip are counted, which
+        is why a fused kernel may exceed 1.0 of the HBM roofline on this scale.  Equal to step_cost()[0] for unfused steps."""
+        fused_io, _ = Engine.step_cost(s, env, pk)
+        out = env[s.dst]
+        esz = 2                                            # bf16 storage of every intermediate (fused steps are bf16-only)
+        if s.op == "mbconv":
+            e, d, pj = s.parts
+            ce = e.conv.weight.shape[0]
+            npix_in = env[s.src].numel() // env[s.src].shape[-1]
+            npix_out = out.numel() // out.shape[-1]
+            return fused_io + esz * ce * (2 * npix_in + 2 * npix_out)      # expand out + dw in, dw out + project in
+        if s.op == "stem_mb1":
+            cs = s.parts[0].conv.weight.shape[0]
+            npix = out.numel() // out.shape[-1]
+            return fused_io + esz * cs * 4 * npix                          # stem out + dw in, dw out + 1x1 in
+        if s.op == "tail":
+            c0, c3, _ = s.parts
+            npix = env[s.src].numel() // env[s.src].shape[-1]
+            mid, cls = c0.conv.weight.shape[0], c3.conv.weight.shape[0]
+            return fused_io + esz * npix * (2 * mid + 2 * cls)             # outc.0 out + outc.3 in, logits out + upsample in
+        return fused_io
+
+    @staticmethod
     def step_cost(s: Step, env, pk):
         """Algorithmic HBM bytes and FLOPs of one fused step (SURVEY 8d traffic model): read every
         input once, write the output once, weights once; FLOPs = 2*MAC."""
