@@ -153,6 +153,8 @@ int b200seg_maxpool2x2(const void* x, void* y, int dtype, int B, int H, int W, i
  *              reduction), or NULL: dlogits is scaled by grad_scale alone. */
 int b200seg_softmax_ce(const float* logits, const int64_t* target, float* loss_sum, float* dlogits,
                        float grad_scale, const float* counts, int B, int C, int H, int W, b200seg_stream_t s);
+/* d(logits) *= gout[0] in place (the incoming gradient of the scalar loss, train.py:38); a no-op on the device when it is 1 */
+int b200seg_scale_unless_one(float* x, long long n, const float* s, b200seg_stream_t st);
 /* counts[0] += number of targets in [0,C); counts[1] += number of targets that are neither in range nor ignore_index
  * (torch raises on those; the Python binding turns a non-zero counts[1] into a NaN loss). Caller zeroes counts. */
 int b200seg_ce_count(const int64_t* target, float* counts, long long N, int C, long long ignore_index,

@@ -135,6 +135,13 @@ class Engine:
                         items.append((d, name, t))
         return items
 
+    def _ptr_ident(self) -> int:
+        """Hash of the storage addresses of every parameter and buffer (what a captured graph holds raw pointers to)."""
+        items = getattr(self, "_ver_items", None)
+        if items is None or any(d.get(name) is not t for d, name, t in items):
+            items = self._ver_items = self._version_items()
+        return hash(tuple(t.data_ptr() for _, _, t in items))
+
     def _version_key(self, mode: str):
         items = getattr(self, "_ver_items", None)
         if items is None:

@@ -345,6 +345,15 @@ def softmax_ce(logits, target, want_grad: bool = True, grad_scale: Optional[floa
     return acc[0] / n, dl
 
 
+def scale_unless_one(x, s):
+    """x *= s (device scalar) in place; nothing is read or written when s == 1."""
+    _cuda(x, s)
+    if x.dtype != torch.float32 or s.dtype != torch.float32 or not x.is_contiguous():
+        raise TypeError("scale_unless_one: contiguous f32 tensors")
+    check(lib.b200seg_scale_unless_one(ptr(x), x.numel(), ptr(s), _stream()), "scale_unless_one")
+    return x
+
+
 # ------------------------------------------------------------------------------------------------
 # training-path wrappers (train.py:35-39).  Activations are NHWC [B,H,W,C]; P = B*H*W.
 # ------------------------------------------------------------------------------------------------

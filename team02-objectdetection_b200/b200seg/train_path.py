@@ -486,9 +486,7 @@ def _graph_for(engine, x, mode) -> Optional[_StepGraph]:
     if not engine.use_graphs or TRACE is not None or torch.cuda.is_current_stream_capturing():
         return None
     # the captured graphs hold raw pointers of every parameter and BatchNorm buffer: a graph is only valid for them
-    ident = tuple(t.data_ptr() for s in engine.steps for m in (s.conv, s.bn) if m is not None
-                  for t in list(m.parameters()) + list(m.buffers()))
-    key = ("train", tuple(x.shape), x.dtype, mode, engine.dense_impl, engine.tc_flags, x.device, hash(ident),
+    key = ("train", tuple(x.shape), x.dtype, mode, engine.dense_impl, engine.tc_flags, x.device, engine._ptr_ident(),
            id(getattr(engine, "dp", None)))
     ent = engine._graphs.get(key)
     if ent is None:

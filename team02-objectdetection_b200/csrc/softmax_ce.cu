@@ -65,6 +65,21 @@ softmax_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ 
 int launch_softmax_ce_generic(const float* logits, const int64_t* target, float* loss_sum, float* dlogits, float grad_scale,
                               const float* counts, int B, int C, long long HW, cudaStream_t st);   // generic_ops.cu
 
+
+// x *= s[0] unless s[0] == 1 (the gradient autograd hands to loss.backward() is ones: the whole pass over the 168 MB of
+// d(logits) is then a few hundred CTAs that read one word and exit).
+__global__ void __launch_bounds__(256)
+scale_unless_one_kernel(float* __restrict__ x, long long n4, const float* __restrict__ s) {
+  const float f = __ldg(s);
+  if (f == 1.f) return;
+  float4* x4 = reinterpret_cast<float4*>(x);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = x4[i];
+    v.x *= f; v.y *= f; v.z *= f; v.w *= f;
+    x4[i] = v;
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -85,4 +100,11 @@ extern "C" int b200seg_softmax_ce(const float* logits, const int64_t* target, fl
   else
     return launch_softmax_ce_generic(logits, target, loss_sum, dlogits, grad_scale, counts, B, C, HW, st);
   return check_launch("softmax_ce");
+}
+
+// In-place x[i] *= s[0] for a device scalar s; returns immediately on the device when s[0] == 1.  n % 4 == 0, x 16-byte aligned.
+extern "C" int b200seg_scale_unless_one(float* x, long long n, const float* s, b200seg_stream_t st) {
+  B200_REQUIRE(x && s && n > 0 && n % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "scale_unless_one: bad arguments");
+  b200::scale_unless_one_kernel<<<b200::sm_count() * 4, 256, 0, (cudaStream_t)st>>>(x, n / 4, s);
+  return b200::check_launch("scale_unless_one");
 }
