@@ -520,13 +520,15 @@ def upcat_bwd(dcat, Cs: int, acc_skip=None):
     return dskip, dx
 
 
-def final_bwd(dout_nchw, sdt, ldc: int = 16):
-    """dout NCHW f32 [B,C,2h,2w] -> NHWC [B,h,w,ldc] of dtype sdt."""
+def final_bwd(dout_nchw, sdt, ldc: int = 16, out=None):
+    """dout NCHW f32 [B,C,2h,2w] -> NHWC [B,h,w,ldc] of dtype sdt (``out``: existing result buffer)."""
     _cuda(dout_nchw)
     if dout_nchw.dtype != torch.float32:
         raise TypeError("final_bwd expects f32 upstream gradients")
     B, Cc, H2, W2 = dout_nchw.shape
-    dl = torch.empty(B, H2 // 2, W2 // 2, ldc, device=dout_nchw.device, dtype=sdt)
+    dl = out if out is not None else torch.empty(B, H2 // 2, W2 // 2, ldc, device=dout_nchw.device, dtype=sdt)
+    if tuple(dl.shape) != (B, H2 // 2, W2 // 2, ldc) or dl.dtype != sdt or not dl.is_contiguous():
+        raise ValueError("final_bwd: bad output buffer")
     if ldc != 16:
         check(lib.b200seg_final_bwd_generic(ptr(dout_nchw), ptr(dl), _dt(dl), B, H2 // 2, W2 // 2, Cc, ldc, _stream()),
               "final_bwd_generic")
@@ -535,10 +537,12 @@ def final_bwd(dout_nchw, sdt, ldc: int = 16):
     return dl
 
 
-def nchw_to_nhwc_pad(x_nchw, ldc: int, sdt):
+def nchw_to_nhwc_pad(x_nchw, ldc: int, sdt, out=None):
     _cuda(x_nchw)
     B, Cc, H, W = x_nchw.shape
-    y = torch.empty(B, H, W, ldc, device=x_nchw.device, dtype=sdt)
+    y = out if out is not None else torch.empty(B, H, W, ldc, device=x_nchw.device, dtype=sdt)
+    if tuple(y.shape) != (B, H, W, ldc) or y.dtype != sdt or not y.is_contiguous():
+        raise ValueError("nchw_to_nhwc_pad: bad output buffer")
     check(lib.b200seg_nchw_to_nhwc_pad(ptr(x_nchw), ptr(y), _dt(y), B, Cc, H, W, ldc, _stream()), "nchw_to_nhwc_pad")
     return y
 

@@ -251,7 +251,27 @@ def _workspace(engine) -> TrainWorkspace:
 # ----------------------------------------------------------------------------------------------------
 # the two passes as plain functions over tensors (no autograd): used eagerly and under graph capture
 # ----------------------------------------------------------------------------------------------------
-def run_forward(engine, x: torch.Tensor, mode: str):
+def _out_step(engine):
+    """The last schedule step when it only produces the public output layout (final upsample / NHWC->NCHW), else None."""
+    last = engine.steps[-1]
+    return last if last.op in ("final", "to_nchw") else None
+
+
+def run_out_step(engine, s, env):
+    """Forward of the output-layout step into a FRESH tensor."""
+    if s.op == "final":
+        return ops.upsample2x_ac_nchw(env[s.src], engine.out_ch, torch.float32)
+    return ops.nhwc_to_nchw(env[s.src], engine.out_ch, torch.float32)
+
+
+def run_out_step_bwd(engine, s, env, dout, sdt, out=None):
+    """Backward of the output-layout step: reads the caller's d(out) directly."""
+    if s.op == "final":
+        return ops.final_bwd(dout, sdt, env[s.src].shape[-1], out=out)
+    return ops.nchw_to_nhwc_pad(dout, env[s.src].shape[-1], sdt, out=out)
+
+
+def run_forward(engine, x: torch.Tensor, mode: str, skip_out_step: bool = False):
     sdt = torch.bfloat16 if mode == "bf16" else torch.float32
     tc = mode == "bf16" and (engine.dense_impl or "tc") == "tc"
     env: Dict[str, torch.Tensor] = {"x": x}
@@ -260,9 +280,13 @@ def run_forward(engine, x: torch.Tensor, mode: str):
     ops.zero_pool32.reset()
     packs = _train_packs(engine, tc)       # every layer's operand layouts from the current fp32 weights, one launch
     counters = []                          # BatchNorm.num_batches_tracked, bumped with one fused launch at the end
+    out_step = _out_step(engine) if skip_out_step else None
     for s in engine.steps:
         rec: dict = {}
         _e0 = _tick()
+        if s is out_step:                      # launched by the caller outside the captured graph (fresh output tensor)
+            saved[s.name] = rec
+            continue
         if s.op in ("stem", "dw", "dense"):
             cout = s.conv.weight.shape[0]
             bias = s.conv.bias.detach().float() if s.conv.bias is not None else None
@@ -301,10 +325,8 @@ def run_forward(engine, x: torch.Tensor, mode: str):
             env[s.dst] = ops.upsample2x_concat(env[s.res], env[s.src])
         elif s.op == "pool":
             env[s.dst] = ops.maxpool2x2(env[s.src])
-        elif s.op == "final":
-            env[s.dst] = ops.upsample2x_ac_nchw(env[s.src], engine.out_ch, torch.float32)
-        elif s.op == "to_nchw":
-            env[s.dst] = ops.nhwc_to_nchw(env[s.src], engine.out_ch, torch.float32)
+        elif s.op in ("final", "to_nchw"):
+            env[s.dst] = run_out_step(engine, s, env)
         else:  # pragma: no cover
             raise AssertionError(s.op)
         saved[s.name] = rec
@@ -315,23 +337,25 @@ def run_forward(engine, x: torch.Tensor, mode: str):
     return env, saved
 
 
-def run_backward(engine, env, saved, mode: str, dout: torch.Tensor, ws: TrainWorkspace) -> None:
+def run_backward(engine, env, saved, mode: str, dout, ws: TrainWorkspace, g_src=None) -> None:
     """Walk the schedule in reverse.  Parameter gradients are accumulated in ``ws`` staging; as soon as the last
     parameter of a gradient bucket is staged the bucket is finalized into the arena and (data parallel) its all-reduce
     starts on the side stream while the walk continues."""
     sdt = torch.bfloat16 if mode == "bf16" else torch.float32
     tc = mode == "bf16" and (engine.dense_impl or "tc") == "tc"
-    g: Dict[str, torch.Tensor] = {"out": dout}
+    # g_src: the gradient of the output-layout step's INPUT, already computed by the caller outside the captured graph
+    out_step = _out_step(engine) if g_src is not None else None
+    g: Dict[str, torch.Tensor] = {"out": dout} if out_step is None else {out_step.src: g_src}
     ops.zero_pool.reset()
     ops.zero_pool32.reset()
     ws.begin_backward()
     for s in reversed(engine.steps):
         rec = saved[s.name]
         _e0 = _tick()
-        if s.op == "final":
-            g[s.src] = ops.final_bwd(g.pop(s.dst), sdt, env[s.src].shape[-1])
-        elif s.op == "to_nchw":
-            g[s.src] = ops.nchw_to_nhwc_pad(g.pop(s.dst), env[s.src].shape[-1], sdt)
+        if s is out_step:
+            continue
+        if s.op in ("final", "to_nchw"):
+            g[s.src] = run_out_step_bwd(engine, s, env, g.pop(s.dst), sdt)
         elif s.op == "upcat":
             dcat = g.pop(s.dst)
             cs = env[s.res].shape[-1]
@@ -407,15 +431,25 @@ class _StepGraph:
         from ._cabi import LAUNCHES
         n0 = LAUNCHES[0]
         self.fwd = torch.cuda.CUDAGraph()
+        # The output-layout step (final upsample) and its adjoint stay OUTSIDE the graphs: the forward one writes a fresh
+        # result tensor, the backward one reads the caller's d(out) -- no 168 MB clone / copy_ around the replays.
+        self.out_step = _out_step(engine)
         with torch.no_grad(), torch.cuda.graph(self.fwd):
-            self.env, self.saved = run_forward(engine, self.x, mode)
-        self.out = self.env["out"]
-        self.dout = torch.zeros_like(self.out)
+            self.env, self.saved = run_forward(engine, self.x, mode, skip_out_step=True)
+        sdt = torch.bfloat16 if mode == "bf16" else torch.float32
+        if self.out_step is not None:
+            self.out = None
+            self.dout = None
+            self.g_src = torch.zeros_like(self.env[self.out_step.src], dtype=sdt)
+        else:
+            self.out = self.env["out"]
+            self.dout = torch.zeros_like(self.out)
+            self.g_src = None
         self.bwd = torch.cuda.CUDAGraph()
         # the per-bucket all-reduces (data parallel) are captured on the arena's side stream: fork/join events become
         # graph edges, so every replay overlaps them with the rest of backward
         with torch.no_grad(), torch.cuda.graph(self.bwd, pool=self.fwd.pool()):
-            run_backward(engine, self.env, self.saved, mode, self.dout, ws)
+            run_backward(engine, self.env, self.saved, mode, self.dout, ws, g_src=self.g_src)
         self.n_launches = LAUNCHES[0] - n0     # hand-written kernels inside the two graphs (ATen fills/copies not counted)
         self.pending = False      # a forward has been replayed whose backward has not run yet
 
@@ -451,7 +485,7 @@ class _TrainFn(torch.autograd.Function):
             sg.fwd.replay()
             sg.pending = True
             ctx.graph = sg
-            out = sg.out.clone()
+            out = run_out_step(engine, sg.out_step, sg.env) if sg.out_step is not None else sg.out.clone()
         else:
             with torch.no_grad():
                 ctx.env, ctx.saved = run_forward(engine, x, mode)
@@ -468,7 +502,11 @@ class _TrainFn(torch.autograd.Function):
             _detach_accumulated(params, ws)
             sg = ctx.graph
             if sg is not None:
-                sg.dout.copy_(dout)
+                if sg.out_step is not None:
+                    sdt = torch.bfloat16 if ctx.mode == "bf16" else torch.float32
+                    run_out_step_bwd(engine, sg.out_step, sg.env, dout.float().contiguous(), sdt, out=sg.g_src)
+                else:
+                    sg.dout.copy_(dout)
                 sg.bwd.replay()
                 sg.pending = False
                 ctx.graph = None             # the loss tensor's autograd node must not keep the captured graphs alive
