@@ -280,6 +280,11 @@ int b200seg_preprocess_u8(const uint8_t* frames, int B, int Hs, int Ws, void* ou
                           int W, float mean0, float mean1, float mean2, float std0, float std1, float std2,
                           b200seg_stream_t s);
 
+/* Dataset label remap on the device (the class_map loops of BDD100KDataset.py:23-35,66-69, CarlaDataset.py, SEAMEDataset.py, followed
+ * by `.long()`): out[i] = lut256[in[i]], uint8 labels -> int64 targets.  Unmapped source classes map to whatever the table holds
+ * (0 = background in the reference). */
+int b200seg_remap_labels(const uint8_t* in, int64_t* out, const uint8_t* lut256, long long n, b200seg_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

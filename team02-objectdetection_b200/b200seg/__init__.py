@@ -10,6 +10,9 @@ from .unet import LightUNet, MobileNetV2UNet, UNet  # noqa: F401
 from .loss import CrossEntropyLoss  # noqa: F401
 from .optim import Adam  # noqa: F401
 from .preprocess import preprocess_image  # noqa: F401
+from .feed import DeviceFeeder, class_map_lut, remap_labels  # noqa: F401
+from .export import torch_graph  # noqa: F401
 
-__all__ = ["MobileNetV2UNet", "UNet", "LightUNet", "CrossEntropyLoss", "Adam", "preprocess_image"]
+__all__ = ["MobileNetV2UNet", "UNet", "LightUNet", "CrossEntropyLoss", "Adam", "preprocess_image", "DeviceFeeder",
+           "class_map_lut", "remap_labels", "torch_graph"]
 __version__ = "0.1.0"

@@ -41,6 +41,7 @@ _PROTOS = {
     "b200seg_maxpool2x2": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "b200seg_softmax_ce": [_vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _vp],
     "b200seg_scale_unless_one": [_vp, _ll, _vp, _vp],
+    "b200seg_remap_labels": [_vp, _vp, _vp, _ll, _vp],
     "b200seg_ce_count": [_vp, _vp, _ll, _i, _ll, _vp],
     "b200seg_upsample2x_ac_generic": [_vp, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp],
     "b200seg_final_bwd_generic": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],

@@ -98,6 +98,30 @@ preprocess_u8_same_kernel(const uint8_t* __restrict__ frames, TO* __restrict__ o
   }
 }
 
+
+// dataset label remap on the GPU (BDD100KDataset.py:23-35,66-69 and the other datasets' class_map loops):
+// out[i] = lut[in[i]] as int64 (the dtype nn.CrossEntropyLoss wants, `.long()` at BDD100KDataset.py:75), 16 labels per thread.
+__global__ void __launch_bounds__(256)
+remap_labels_kernel(const uint8_t* __restrict__ in, int64_t* __restrict__ out, const uint8_t* __restrict__ lut, long long n) {
+  __shared__ uint8_t sl[256];
+  sl[threadIdx.x] = lut[threadIdx.x];
+  __syncthreads();
+  const long long i0 = ((long long)blockIdx.x * 256 + threadIdx.x) * 16;
+  if (i0 + 16 <= n && ((reinterpret_cast<uintptr_t>(in) & 15) == 0)) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + i0));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      longlong2 a = make_longlong2(sl[w[q] & 255u], sl[(w[q] >> 8) & 255u]);
+      longlong2 b = make_longlong2(sl[(w[q] >> 16) & 255u], sl[w[q] >> 24]);
+      *reinterpret_cast<longlong2*>(out + i0 + 4 * q) = a;
+      *reinterpret_cast<longlong2*>(out + i0 + 4 * q + 2) = b;
+    }
+  } else {
+    for (long long i = i0; i < n && i < i0 + 16; ++i) out[i] = sl[in[i]];
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -131,4 +155,14 @@ extern "C" int b200seg_preprocess_u8(const uint8_t* frames, int B, int Hs, int W
   else
     return set_error(-1, "preprocess_u8: bad out dtype %d", out_dtype);
   return check_launch("preprocess_u8");
+}
+
+// out[i] = lut[in[i]] (uint8 labels -> int64 targets through a 256-entry table).
+extern "C" int b200seg_remap_labels(const uint8_t* in, int64_t* out, const uint8_t* lut256, long long n, b200seg_stream_t s) {
+  B200_REQUIRE(in && out && lut256 && n > 0, "remap_labels: bad arguments");
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "remap_labels: output must be 16-byte aligned");
+  const long long blocks = (n + 4095) / 4096;
+  B200_REQUIRE(blocks < (1ll << 31), "remap_labels: too many labels");
+  remap_labels_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(in, out, lut256, n);
+  return check_launch("remap_labels");
 }

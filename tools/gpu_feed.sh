@@ -1,0 +1,2 @@
+#!/bin/bash
+timeout 600 python -m pytest tests/test_gpu_feed.py -m gpu -q -x 2>&1 | tail -12
