@@ -86,29 +86,15 @@ def train_leg(args, dev, dist, world, rank, unet=False, batch=0, want_breakdown=
     # read back (a sync) every step as train.py:41-42 does
     xh = [torch.randn(B, 3, H, W, generator=g).pin_memory() for _ in range(2)]
     yh = [torch.randint(0, NCLS, (B, H, W), generator=g).pin_memory() for _ in range(2)]
-    copy_s, comp_s = torch.cuda.Stream(), torch.cuda.current_stream()
-    xd = [torch.empty(B, 3, H, W, device=dev) for _ in range(2)]
-    yd = [torch.empty(B, H, W, dtype=torch.int64, device=dev) for _ in range(2)]
 
-    def upload(i):
-        k = i & 1
-        with torch.cuda.stream(copy_s):
-            copy_s.wait_stream(comp_s)              # buffer k was last read by step i-2, already enqueued on comp_s
-            xd[k].copy_(xh[k], non_blocking=True)
-            yd[k].copy_(yh[k], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy_s)
-        return ev
+    # the library input feed (b200seg.DeviceFeeder) in place of train.py:32-33's blocking copies; one
+    # feeder for the whole leg (its device buffers are allocated on the untimed first pass)
+    feeder = b200seg.DeviceFeeder([], dev)
 
     def e2e_steps(n):
-        ev = upload(0)
-        for i in range(n):
-            comp_s.wait_event(ev)
-            if i + 1 < n:
-                ev_next = upload(i + 1)
-            step(xd[i & 1], yd[i & 1]).item()       # train.py:41-42 reads the loss every step
-            if i + 1 < n:
-                ev = ev_next
+        feeder.loader = [(xh[i & 1], yh[i & 1]) for i in range(n)]
+        for x, y in feeder:
+            step(x, y).item()                       # train.py:41-42 reads the loss every step
 
     e2e_steps(3)
     barrier()
@@ -159,7 +145,7 @@ def train_leg(args, dev, dist, world, rank, unet=False, batch=0, want_breakdown=
                launches_per_step=launches_per_step)
     eng._graphs.clear()
     eng._train_ws = None
-    del model, optimizer, xs, ys, xd, yd, eng
+    del model, optimizer, xs, ys, feeder, eng
     import gc
     gc.collect()
     torch.cuda.empty_cache()

@@ -92,11 +92,14 @@ class DeviceFeeder:
                 self.copy_stream.wait_event(self._consumed[k])       # slot k's previous batch is no longer being read
             for t_i, t in enumerate(batch[:2]):
                 t = t.contiguous()
-                self._pin[k][t_i] = self._fit(self._pin[k][t_i], t, pin_memory=True)
                 self._dev[k][t_i] = self._fit(self._dev[k][t_i], t, device=self.device)
-                h = self._pin[k][t_i][:t.numel()].view(t.shape)
                 d = self._dev[k][t_i][:t.numel()].view(t.shape)
-                h.copy_(t)                                           # pageable -> pinned on the host (what .to() hides inside)
+                if t.is_pinned():                                    # DataLoader(pin_memory=True): upload straight from it
+                    h = t
+                else:
+                    self._pin[k][t_i] = self._fit(self._pin[k][t_i], t, pin_memory=True)
+                    h = self._pin[k][t_i][:t.numel()].view(t.shape)
+                    h.copy_(t)                                       # pageable -> pinned on the host (what .to() hides inside)
                 d.copy_(h, non_blocking=True)
                 out.append(d)
             ev = torch.cuda.Event()
