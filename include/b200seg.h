@@ -200,6 +200,18 @@ int b200seg_bn_bwd_reduce(const void* da, const void* z, const float* scale, con
 int b200seg_bn_bwd_apply(const void* da, const void* z, const float* scale, const float* shift, const float* mean,
                          const float* invstd, const float* sg, const float* sgx, void* dz, int dtype, long long P,
                          int C, int act, b200seg_stream_t s);
+/* Train-mode BatchNorm2d forward / backward of the small and mid-size layers in ONE launch per direction: a thread-block cluster
+ * owns 16 channels, reduces through distributed shared memory and applies in the same kernel (nn.BatchNorm2d in model.train(),
+ * train.py:24,36, and its backward, train.py:38).  bf16, C % 16 == 0, tensors up to ~40 MB (b200seg_bn_cluster_supported);
+ * larger layers use the grid-wide kernels above.  sv: f32 [4][C] = mean, invstd, scale, shift; red: zeroed f64 [nslot][2][C],
+ * slot 0 receives sum g (d beta) and sum g*xhat (d gamma). */
+int b200seg_bn_cluster_supported(int dtype, long long P, int C);
+int b200seg_bn_cluster_bwd_supported(int dtype, long long P, int C);
+int b200seg_bn_cluster_fwd(const void* z, long long P, int C, const float* gamma, const float* beta, float eps, float momentum,
+                           float* running_mean, float* running_var, float* sv, const void* res, void* a, int act,
+                           b200seg_stream_t s);
+int b200seg_bn_cluster_bwd(const void* da, const void* z, const float* sv, long long P, int C, int act, double* red, void* dz,
+                           b200seg_stream_t s);
 /* dz = da * act'(a_out) for a layer without BatchNorm */
 int b200seg_act_bwd(const void* da, const void* a_out, void* dz, int dtype, long long N, int act, b200seg_stream_t s);
 /* out[slot][c] += sum_p x[p][c]  (bias gradients) ; out[i] = scale * sum_slot in[slot*slot_stride + i] as f32 */

@@ -51,6 +51,10 @@ _PROTOS = {
     "b200seg_bn_finalize": [_vp, _i, _vp, _vp, _i, _ll, _ll, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "b200seg_bn_apply": [_vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _vp],
     "b200seg_bn_bwd_reduce": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _vp, _vp, _i, _ll, _vp],
+    "b200seg_bn_cluster_supported": [_i, _ll, _i],
+    "b200seg_bn_cluster_bwd_supported": [_i, _ll, _i],
+    "b200seg_bn_cluster_fwd": [_vp, _ll, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+    "b200seg_bn_cluster_bwd": [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp],
     "b200seg_bn_bwd_apply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _vp],
     "b200seg_act_bwd": [_vp, _vp, _vp, _i, _ll, _i, _vp],
     "b200seg_colsum": [_vp, _i, _ll, _i, _vp, _i, _ll, _vp],

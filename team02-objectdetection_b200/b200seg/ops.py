@@ -392,6 +392,9 @@ def _P(t):
     return t.shape[0] * t.shape[1] * t.shape[2]
 
 
+BN_CLUSTER = True        # small / mid-size bf16 layers: one cluster-synchronised launch per direction (csrc/bn_cluster.cu)
+
+
 def bn_train_forward(z, gamma, beta, running_mean, running_var, eps: float, momentum: float, act: int, res=None):
     """Train-mode BatchNorm over NHWC z (+act, +residual).  Updates the running stats in place.
     Returns (a, saved) where saved = (mean, invstd, scale, shift) for the backward pass.
@@ -400,6 +403,12 @@ def bn_train_forward(z, gamma, beta, running_mean, running_var, eps: float, mome
     5 us launch gap they remove; bn_stats 0.61 + finalize 0.35 ms vs 1.05-1.20 ms fused, per training step.)"""
     _cuda(z, gamma, beta, running_mean, running_var, res)
     C, P = z.shape[-1], _P(z)
+    if BN_CLUSTER and lib.b200seg_bn_cluster_supported(_dt(z), P, C):
+        sv = torch.empty(4, C, device=z.device, dtype=torch.float32)
+        a = torch.empty_like(z)
+        check(lib.b200seg_bn_cluster_fwd(ptr(z), P, C, ptr(gamma), ptr(beta), eps, momentum, ptr(running_mean), ptr(running_var),
+                                         ptr(sv), ptr(res), ptr(a), act, _stream()), "bn_cluster_fwd")
+        return a, sv
     st = zero_pool.take((NSLOT, 2, C), z.device)                              # slot-major: [slot][sum | sumsq][C]
     check(lib.b200seg_bn_stats(ptr(z), _dt(z), P, C, ptr(st[0, 0]), ptr(st[0, 1]), NSLOT, 2 * C, _stream()), "bn_stats")
     sv = torch.empty(4, C, device=z.device, dtype=torch.float32)
@@ -416,8 +425,16 @@ def bn_train_backward(da, z, sv, act: int, red=None):
     (row 0 = d beta, row 1 = d gamma; the gradient-finalize kernel reads them from there)."""
     _cuda(da, z, sv)
     C, P = z.shape[-1], _P(z)
+    own_red = red is None
     if red is None:
         red = zero_pool.take((NSLOT, 2, C), z.device)
+    if BN_CLUSTER and lib.b200seg_bn_cluster_bwd_supported(_dt(z), P, C):
+        dz = torch.empty_like(z)
+        check(lib.b200seg_bn_cluster_bwd(ptr(da), ptr(z), ptr(sv), P, C, act, ptr(red), ptr(dz), _stream()), "bn_cluster_bwd")
+        if not own_red:               # the training step reads the sums from the staging block (gradient finalize)
+            return dz, None, None
+        g32 = red[0].float()
+        return dz, g32[1], g32[0]
     check(lib.b200seg_bn_bwd_reduce(ptr(da), ptr(z), ptr(sv[2]), ptr(sv[3]), ptr(sv[0]), ptr(sv[1]), _dt(z), P, C, act,
                                     ptr(red[0, 0]), ptr(red[0, 1]), NSLOT, 2 * C, _stream()), "bn_bwd_reduce")
     g32 = torch.empty(2, C, device=z.device, dtype=torch.float32)
