@@ -45,8 +45,16 @@ def _rand(*shape, seed=0, scale=1.0):
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("B,H,W,C,act,res", [(2, 16, 24, 32, 2, False), (3, 9, 7, 96, 1, False), (2, 8, 8, 24, 0, True),
-                                             (1, 33, 65, 144, 2, False)])
+                                             (1, 33, 65, 144, 2, False),
+                                             # bf16: the cluster kernels (bn_cluster.cu) -- slice resident in shared memory,
+                                             # cluster sizes 8 / 4, ragged pixel split, residual; streamed forward (128 ch)
+                                             (8, 16, 32, 384, 2, False), (32, 8, 16, 960, 1, True), (5, 17, 31, 640, 0, False),
+                                             (32, 32, 64, 128, 2, False)])
 def test_batchnorm_train_forward_backward(dt, B, H, W, C, act, res):
+    if dt == torch.bfloat16 and C >= 128 and C != 144:
+        from b200seg._cabi import lib, BF16
+        assert lib.b200seg_bn_cluster_supported(BF16, B * H * W, C) == 1        # these shapes must take the cluster path
+        assert lib.b200seg_bn_cluster_bwd_supported(BF16, B * H * W, C) == (0 if C == 128 else 1)
     z = (_rand(B, C, H, W, seed=1) * 2 + 0.5).to(dt)
     gamma, beta = _rand(C, seed=2).abs() + 0.5, _rand(C, seed=3, scale=0.2)
     rm, rv = _rand(C, seed=4, scale=0.1), _rand(C, seed=5).abs() + 0.5
