@@ -282,11 +282,11 @@ struct Vec16;
 template <>
 struct Vec16<float> {
   static constexpr int N = 4;
-  float v[4];
-  __device__ __forceinline__ void load(const float* p) {
-    float4 t = __ldg(reinterpret_cast<const float4*>(p));
-    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-  }
+  typedef float4 Raw;                          // the 16 bytes as loaded: lets a kernel issue a batch of loads first and
+  float v[4];                                  // unpack later (see train_ops.cu, "batched streaming")
+  static __device__ __forceinline__ Raw ldraw(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+  __device__ __forceinline__ void unpack(const Raw& t) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  __device__ __forceinline__ void load(const float* p) { unpack(ldraw(p)); }
   __device__ __forceinline__ void store(float* p) const {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   }
@@ -294,12 +294,19 @@ struct Vec16<float> {
 template <>
 struct Vec16<__nv_bfloat16> {
   static constexpr int N = 8;
+  typedef uint4 Raw;
   float v[8];
-  __device__ __forceinline__ void load(const __nv_bfloat16* p) {
-    uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+  // volatile asm: a batch of these stays a batch (ptxas sank plain __ldg loads back into the arithmetic to save registers)
+  static __device__ __forceinline__ Raw ldraw(const __nv_bfloat16* p) {
+    uint4 t;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(p));
+    return t;
+  }
+  __device__ __forceinline__ void unpack(const Raw& t) {
     v[0] = bf16lo(t.x); v[1] = bf16hi(t.x); v[2] = bf16lo(t.y); v[3] = bf16hi(t.y);
     v[4] = bf16lo(t.z); v[5] = bf16hi(t.z); v[6] = bf16lo(t.w); v[7] = bf16hi(t.w);
   }
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { unpack(ldraw(p)); }
   __device__ __forceinline__ void store(__nv_bfloat16* p) const {
     uint4 t;
     t.x = pack_bf16x2(v[0], v[1]); t.y = pack_bf16x2(v[2], v[3]);

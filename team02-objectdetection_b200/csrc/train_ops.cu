@@ -55,10 +55,14 @@ static inline int red_ppb(long long P, const dim3& block, int cvecs) {
   return (int)ppb;
 }
 
-template <typename T, int NOUT, int UNROLL = 4, typename F>
-__device__ __forceinline__ void channel_reduce(long long P, int C, int ppb, double* const* out, int nslot,
-                                               long long slot_stride, F&& f) {
+// "Batched streaming": the pixel loop first issues U rows of 16-byte loads per input (raw, not yet unpacked), then does
+// the arithmetic.  With the loads written inside the per-pixel body the compiler kept them behind the body's branches,
+// i.e. 32 bytes in flight per thread and ~16 KB per SM: the large-layer BatchNorm passes ran at 2.3-2.9 TB/s, latency-bound.
+template <typename T, int NOUT, int NIN, int U = 4, typename F>
+__device__ __forceinline__ void channel_reduce(const T* const (&in)[NIN], long long P, int C, int ppb, double* const* out,
+                                               int nslot, long long slot_stride, F&& f) {
   using V = Vec16<T>;
+  using Raw = typename V::Raw;
   constexpr int VN = V::N;
   const int TX = blockDim.x, TY = blockDim.y;
   const int cvec = blockIdx.y * TX + threadIdx.x;
@@ -71,8 +75,29 @@ __device__ __forceinline__ void channel_reduce(long long P, int C, int ppb, doub
     for (int j = 0; j < VN; ++j) acc[o][j] = 0.f;
   if (active) {
     const long long p0 = (long long)blockIdx.x * ppb, p1 = min(p0 + ppb, P);
-#pragma unroll UNROLL
-    for (long long p = p0 + threadIdx.y; p < p1; p += TY) f(p, c0, acc);
+    long long p = p0 + threadIdx.y;
+    const long long rowstep = (long long)TY * C;
+    for (; p + (long long)(U - 1) * TY < p1; p += (long long)U * TY) {
+      Raw raw[U][NIN];
+      const long long off = p * C + c0;
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int i = 0; i < NIN; ++i) raw[u][i] = V::ldraw(in[i] + off + u * rowstep);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        V v[NIN];
+#pragma unroll
+        for (int i = 0; i < NIN; ++i) v[i].unpack(raw[u][i]);
+        f(v, acc);
+      }
+    }
+    for (; p < p1; p += TY) {
+      V v[NIN];
+#pragma unroll
+      for (int i = 0; i < NIN; ++i) v[i].load(in[i] + p * C + c0);
+      f(v, acc);
+    }
   }
   __shared__ float red[256][VN + 1];
   const int tid = threadIdx.y * TX + threadIdx.x;
@@ -117,11 +142,10 @@ bn_stats_kernel(const T* __restrict__ z, long long P, int C, int ppb, double* su
     const int c0 = (blockIdx.y * blockDim.x + threadIdx.x) * V::N;
     if (c0 < C) k.load(z + c0);
   }
-  channel_reduce<T, 2>(P, C, ppb, outs, nslot, slot_stride, [&](long long p, int c0, float (&acc)[2][V::N]) {
-    V v;
-    v.load(z + p * C + c0);
+  const T* const ins[1] = {z};
+  channel_reduce<T, 2, 1, 8>(ins, P, C, ppb, outs, nslot, slot_stride, [&](const V (&v)[1], float (&acc)[2][V::N]) {
 #pragma unroll
-    for (int j = 0; j < V::N; ++j) { const float d = v.v[j] - k.v[j]; acc[0][j] += d; acc[1][j] = fmaf(d, d, acc[1][j]); }
+    for (int j = 0; j < V::N; ++j) { const float d = v[0].v[j] - k.v[j]; acc[0][j] += d; acc[1][j] = fmaf(d, d, acc[1][j]); }
   });
 }
 
@@ -160,7 +184,7 @@ __global__ void bn_finalize_kernel(const T* __restrict__ z0, const double* __res
 // each, twice per layer per step) disappear.  `counter` is a zeroed 32-bit word per reduction.
 // a = act(z * scale + shift) (+ residual).  Thread = one channel vector x several pixels (same (tx, ty) layout as the
 // reductions): the per-channel constants are loaded once per thread instead of once per element.
-template <typename T>
+template <typename T, bool HAS_RES>
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const T* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
                 const T* __restrict__ res, T* __restrict__ a, long long P, int C, int ppb, int act) {
@@ -174,21 +198,54 @@ bn_apply_kernel(const T* __restrict__ z, const float* __restrict__ scale, const 
   for (int j = 0; j < VN; ++j) { ksc[j] = __ldg(scale + c0 + j); ksh[j] = __ldg(shift + c0 + j); }
   const float lo = act != B200SEG_ACT_NONE ? 0.f : -INFINITY, hi = act == B200SEG_ACT_RELU6 ? 6.f : INFINITY;
   const long long p0 = (long long)blockIdx.x * ppb, p1 = min(p0 + ppb, P);
-#pragma unroll 4
-  for (long long p = p0 + threadIdx.y; p < p1; p += TY) {
-    const long long off = p * C + c0;
-    V v, r, o;
-    v.load(z + off);
-    if (res) r.load(res + off);
+  auto body = [&](const V& v, const V& r, long long off) {
+    V o;
 #pragma unroll
     for (int j = 0; j < VN; ++j) {
       const float u = fminf(fmaxf(fmaf(v.v[j], ksc[j], ksh[j]), lo), hi);
-      o.v[j] = res ? u + r.v[j] : u;
+      o.v[j] = HAS_RES ? u + r.v[j] : u;
     }
     o.store(a + off);
+  };
+  // batched streaming (see channel_reduce): all loads of U rows first
+  constexpr int U = HAS_RES ? 4 : 8;
+  using Raw = typename V::Raw;
+  long long p = p0 + threadIdx.y;
+  const long long rowstep = (long long)TY * C;
+  for (; p + (long long)(U - 1) * TY < p1; p += (long long)U * TY) {
+    const long long off = p * C + c0;
+    Raw rz[U], rr[HAS_RES ? U : 1];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      rz[u] = V::ldraw(z + off + u * rowstep);
+      if (HAS_RES) rr[u] = V::ldraw(res + off + u * rowstep);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      V v, r;
+      v.unpack(rz[u]);
+      if (HAS_RES) r.unpack(rr[u]);
+      body(v, r, off + u * rowstep);
+    }
+  }
+  for (; p < p1; p += TY) {
+    const long long off = p * C + c0;
+    V v, r;
+    v.load(z + off);
+    if (HAS_RES) r.load(res + off);
+    body(v, r, off);
   }
 }
 
+// Activation gradient with loop-invariant predicates: act'(u) = none || (u > 0 && (nohi || u < 6)); no branch on `act`
+// inside the streaming loops (the branches kept the compiler from hoisting the loads of the next rows).
+struct ActMask {
+  bool none, nohi;
+  __device__ __forceinline__ explicit ActMask(int act) : none(act == B200SEG_ACT_NONE), nohi(act != B200SEG_ACT_RELU6) {}
+  __device__ __forceinline__ float operator()(float u, float g) const {
+    return (none || (u > 0.f && (nohi || u < 6.f))) ? g : 0.f;
+  }
+};
 // gradient of the activation evaluated at u = z*scale + shift
 __device__ __forceinline__ float act_grad(float u, int act) {
   if (act == B200SEG_ACT_RELU) return u > 0.f ? 1.f : 0.f;
@@ -215,23 +272,22 @@ bn_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ z, const fl
       kmu[j] = ok ? __ldg(mean + c0 + j) : 0.f;  kis[j] = ok ? __ldg(invstd + c0 + j) : 0.f;
     }
   }
-  channel_reduce<T, 2>(P, C, ppb, outs, nslot, slot_stride, [&](long long p, int c0, float (&acc)[2][V::N]) {
-    V d, v;
-    d.load(da + p * C + c0);
-    v.load(z + p * C + c0);
+  const ActMask am(act);
+  const T* const ins[2] = {da, z};
+  channel_reduce<T, 2, 2, 4>(ins, P, C, ppb, outs, nslot, slot_stride, [&](const V (&v)[2], float (&acc)[2][V::N]) {
 #pragma unroll
     for (int j = 0; j < V::N; ++j) {
-      const float u = fmaf(v.v[j], ksc[j], ksh[j]);
-      const float g = d.v[j] * act_grad(u, act);
+      const float u = fmaf(v[1].v[j], ksc[j], ksh[j]);
+      const float g = am(u, v[0].v[j]);
       acc[0][j] += g;
-      acc[1][j] = fmaf(g, (v.v[j] - kmu[j]) * kis[j], acc[1][j]);
+      acc[1][j] = fmaf(g, (v[1].v[j] - kmu[j]) * kis[j], acc[1][j]);
     }
   });
 }
 
 // dz = scale * (g - mean(g) - xhat * mean(g*xhat))        (scale = gamma * invstd; sums passed as f32, mean = sum * inv_n)
 template <typename T>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_kernel(const T* __restrict__ da, const T* __restrict__ z, const float* __restrict__ scale,
                     const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
                     const float* __restrict__ sg, const float* __restrict__ sgx, float inv_n, T* __restrict__ dz,
@@ -249,20 +305,40 @@ bn_bwd_apply_kernel(const T* __restrict__ da, const T* __restrict__ z, const flo
     kmg[j] = __ldg(sg + c0 + j) * inv_n; kmx[j] = __ldg(sgx + c0 + j) * inv_n;
   }
   const long long p0 = (long long)blockIdx.x * ppb, p1 = min(p0 + ppb, P);
-#pragma unroll 2
-  for (long long p = p0 + threadIdx.y; p < p1; p += TY) {
-    const long long off = p * C + c0;
-    V d, v, o;
-    d.load(da + off);
-    v.load(z + off);
+  const ActMask am(act);
+  auto body = [&](const V& d, const V& v, long long off) {
+    V o;
 #pragma unroll
     for (int j = 0; j < VN; ++j) {
       const float u = fmaf(v.v[j], ksc[j], ksh[j]);
-      const float g = d.v[j] * act_grad(u, act);
+      const float g = am(u, d.v[j]);
       const float xh = (v.v[j] - kmu[j]) * kis[j];
       o.v[j] = ksc[j] * (g - kmg[j] - xh * kmx[j]);
     }
     o.store(dz + off);
+  };
+  // batched streaming (see channel_reduce): all loads of U rows first
+  constexpr int U = 4;
+  using Raw = typename V::Raw;
+  long long p = p0 + threadIdx.y;
+  const long long rowstep = (long long)TY * C;
+  for (; p + (long long)(U - 1) * TY < p1; p += (long long)U * TY) {
+    const long long off = p * C + c0;
+    Raw rd[U], rz[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { rd[u] = V::ldraw(da + off + u * rowstep); rz[u] = V::ldraw(z + off + u * rowstep); }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      V d, v;
+      d.unpack(rd[u]); v.unpack(rz[u]);
+      body(d, v, off + u * rowstep);
+    }
+  }
+  for (; p < p1; p += TY) {
+    const long long off = p * C + c0;
+    V d, v;
+    d.load(da + off); v.load(z + off);
+    body(d, v, off);
   }
 }
 
@@ -287,11 +363,10 @@ __global__ void __launch_bounds__(256)
 colsum_kernel(const T* __restrict__ x, long long P, int C, int ppb, double* out, int nslot, long long slot_stride) {
   using V = Vec16<T>;
   double* const outs[1] = {out};
-  channel_reduce<T, 1>(P, C, ppb, outs, nslot, slot_stride, [&](long long p, int c0, float (&acc)[1][V::N]) {
-    V v;
-    v.load(x + p * C + c0);
+  const T* const ins[1] = {x};
+  channel_reduce<T, 1, 1, 8>(ins, P, C, ppb, outs, nslot, slot_stride, [&](const V (&v)[1], float (&acc)[1][V::N]) {
 #pragma unroll
-    for (int j = 0; j < V::N; ++j) acc[0][j] += v.v[j];
+    for (int j = 0; j < V::N; ++j) acc[0][j] += v[0].v[j];
   });
 }
 
@@ -1159,8 +1234,9 @@ int b200seg_bn_apply(const void* z, const float* scale, const float* shift, cons
   const int ppb = ew_ppb(block);
   dim3 grid(cdiv(P, ppb), cdiv(C / vn, block.x));
   cudaStream_t st = (cudaStream_t)s;
-  DISPATCH_T(dtype, (bn_apply_kernel<float><<<grid, block, 0, st>>>((const float*)z, scale, shift, (const float*)res, (float*)a, P, C, ppb, act)),
-             (bn_apply_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)z, scale, shift, (const bf16*)res, (bf16*)a, P, C, ppb, act)), "bn_apply")
+#define BN_APPLY(T, R) bn_apply_kernel<T, R><<<grid, block, 0, st>>>((const T*)z, scale, shift, (const T*)res, (T*)a, P, C, ppb, act)
+  DISPATCH_T(dtype, (res ? BN_APPLY(float, true) : BN_APPLY(float, false)), (res ? BN_APPLY(bf16, true) : BN_APPLY(bf16, false)), "bn_apply")
+#undef BN_APPLY
   return check_launch("bn_apply");
 }
 
