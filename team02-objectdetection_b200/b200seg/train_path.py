@@ -140,6 +140,12 @@ class TrainWorkspace:
     ``stage``     {id(param): staging view the backward kernel of that parameter accumulates into}; BatchNorm's two
                   parameters share one f64 [NSLOT, 2, C] block (``stage[id(bn.weight)]``).
     ``finalize``  one ``b200seg_grad_finalize_multi`` launch per bucket: staging -> arena (parameter layout, * 1/world).
+    ``wg_stream`` second CUDA stream for the weight-gradient kernels (``side``).  The data-gradient chain
+                  dz -> dgrad -> BN backward -> dz of the layer before is the critical path of backward; the weight
+                  gradient of a layer only needs dz and the saved input and nothing downstream needs it before the
+                  bucket's finalize launch.  On the small deep layers neither kind of kernel fills 148 SMs (pixel-split
+                  wgrad CTAs, 15-40 us each), so the two streams overlap; the fork/join events become graph edges
+                  under capture.  ``B200SEG_WGRAD_STREAM=0`` keeps everything on one stream.
     """
 
     def __init__(self, engine):
@@ -213,11 +219,33 @@ class TrainWorkspace:
             self.bucket_chunks.append((torch.tensor(ct, dtype=torch.int32, device=dev),
                                        torch.tensor(ci, dtype=torch.int32, device=dev), len(ct)))
         self.pending: List[int] = []
+        import os
+        self.wg_stream = (torch.cuda.Stream(device=dev)
+                          if dev.type == "cuda" and os.environ.get("B200SEG_WGRAD_STREAM", "1") != "0" else None)
+        self._wg_forked = False
+        self._wg_keep: list = []      # tensors the side stream still reads (must outlive the main stream's references)
 
     def begin_backward(self) -> None:
         self.s64.zero_()
         self.s32.zero_()
         self.pending = [len(b["params"]) for b in self.arena.buckets]
+
+    def side(self, fn, *reads) -> None:
+        """Run ``fn`` (weight-gradient launches reading ``reads``) behind everything enqueued so far, off the critical path."""
+        if self.wg_stream is None:
+            fn()
+            return
+        self.wg_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.wg_stream):
+            fn()
+        self._wg_keep.extend(reads)
+        self._wg_forked = True
+
+    def join_side(self) -> None:
+        if self._wg_forked:
+            torch.cuda.current_stream().wait_stream(self.wg_stream)
+            self._wg_forked = False
+        self._wg_keep.clear()
 
     def done(self, *params) -> None:
         """The staging of these parameters is complete (their kernels are enqueued).  When a bucket fills: finalize it into
@@ -227,6 +255,7 @@ class TrainWorkspace:
             bi = self.arena.bucket_of[id(p)]
             self.pending[bi] -= 1
             if self.pending[bi] == 0:
+                self.join_side()                 # the bucket's weight gradients are complete
                 ct, ci, n = self.bucket_chunks[bi]
                 check(lib.b200seg_grad_finalize_multi(ptr(self.table), ptr(ct), ptr(ci), n,
                                                       torch.cuda.current_stream().cuda_stream), "grad_finalize_multi")
@@ -235,6 +264,7 @@ class TrainWorkspace:
     def end_backward(self) -> None:
         if any(self.pending):
             raise RuntimeError("gradient bucket incomplete: a parameter on the path produced no gradient")
+        self.join_side()
         self.arena.join()
 
 
@@ -378,14 +408,14 @@ def run_backward(engine, env, saved, mode: str, dout, ws: TrainWorkspace, g_src=
                 dz = da                                   # conv + bias only (the last 1x1 of outconv)
             w = s.conv.weight
             if s.conv.bias is not None:
-                ops.colsum(dz, acc=ws.stage[id(s.conv.bias)])
+                ws.side(lambda: ops.colsum(dz, acc=ws.stage[id(s.conv.bias)]), dz)
                 ws.done(s.conv.bias)
             src = env[s.src]
             if s.op == "stem":
-                ops.smallcin_wgrad(src, dz, s.stride, dw=ws.stage[id(w)])             # [3,3,Cin,Cout]
+                ws.side(lambda: ops.smallcin_wgrad(src, dz, s.stride, dw=ws.stage[id(w)]), src, dz)   # [3,3,Cin,Cout]
                 ws.done(w)
             elif s.op == "dw":
-                ops.dw_wgrad(src, dz, s.stride, acc=ws.stage[id(w)])                  # f64 slots [NSLOT,9,C]
+                ws.side(lambda: ops.dw_wgrad(src, dz, s.stride, acc=ws.stage[id(w)]), src, dz)        # f64 slots [NSLOT,9,C]
                 ws.done(w)
                 if s.stride == 1 and g.get(s.src) is None:
                     # stride 1: the data gradient IS the forward depthwise conv of dz with the taps flipped -> the
@@ -398,9 +428,9 @@ def run_backward(engine, env, saved, mode: str, dout, ws: TrainWorkspace, g_src=
                     g[s.src] = ops.dw_dgrad(dz, rec["wp"], tuple(src.shape), s.stride, g.get(s.src))
             else:
                 if tc:
-                    ops.conv_wgrad_tc(src, dz, s.taps, dw=ws.stage[id(w)])            # [Cout_pad, taps*Cin]
+                    ws.side(lambda: ops.conv_wgrad_tc(src, dz, s.taps, dw=ws.stage[id(w)]), src, dz)  # [Cout_pad, taps*Cin]
                 else:
-                    ops.conv_wgrad(src, dz, s.taps, dw=ws.stage[id(w)])
+                    ws.side(lambda: ops.conv_wgrad(src, dz, s.taps, dw=ws.stage[id(w)]), src, dz)
                 ws.done(w)
                 # dgrad = the same conv with W transposed (and the 3x3 taps flipped): packed with the forward operand
                 wt = rec["wt"]                                          # [Cin, taps*Cout_pad]
