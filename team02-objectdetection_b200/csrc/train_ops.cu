@@ -676,81 +676,84 @@ dw_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dz, int B, int H,
 // bf16 specialisation: a thread owns PW consecutive output pixels of one row x 8 channels.  The 3 x ((PW-1)S+3) input
 // vectors they touch are loaded once (instead of 9 per pixel) and both operands stay packed bf16: every product goes through
 // the mixed-precision FMA (f32 += bf16 * bf16, exact product), so the loop has no unpack instructions at all.
+// One block per SM (up to 255 registers): with the 72 accumulators capped at 128 registers ptxas serialised the loads two
+// at a time; now all PW + 3*NCOL loads of a pixel group are in flight together.  Index arithmetic is 32-bit (the launcher
+// checks the tensors have < 2^31 elements): the four 64-bit divisions per group cost more instructions than the FMAs.
+// Epilogue: every thread parks its 72 partial sums in shared memory ([pixel lane][tap][channel]), ONE barrier, then each
+// (tap, channel) is summed over the pixel lanes by one thread and leaves as one f64 atomic -- the 9 tree reductions
+// (45 barriers) per block were most of the run time of the small deep layers.
 template <int S, int PW>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 1)
 dw_wgrad_bf16_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dz, int B, int H, int W, int C,
                      int Ho, int Wo, int gpb /* pixel groups per block */, double* dw /* [nslot][9][C] */, int nslot) {
   constexpr int NCOL = (PW - 1) * S + 3;
+  extern __shared__ __align__(16) float dww_red[];         // [TY][9][TX * 8]
   const int TX = blockDim.x, TY = blockDim.y;
   const int c0 = (blockIdx.y * TX + threadIdx.x) * 8;
   const bool active = c0 < C;
-  const int gw = (Wo + PW - 1) / PW;                       // pixel groups per output row
-  const long long G = (long long)B * Ho * gw;
+  const unsigned gw = (Wo + PW - 1) / PW;                  // pixel groups per output row
+  const unsigned G = (unsigned)B * Ho * gw;
   float acc[9][8];
 #pragma unroll
   for (int t = 0; t < 9; ++t)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
-  const long long g0 = (long long)blockIdx.x * gpb, g1 = min(g0 + gpb, G);
+  const unsigned g0 = blockIdx.x * (unsigned)gpb, g1 = min(g0 + (unsigned)gpb, G);
   if (active) {
-    const long long rowC = (long long)W * C;
-    for (long long gi = g0 + threadIdx.y; gi < g1; gi += TY) {
-      const int gx = (int)(gi % gw);
-      const long long t_ = gi / gw;
-      const int ho = (int)(t_ % Ho), b = (int)(t_ / Ho);
+    const unsigned rowC = (unsigned)W * C;
+    for (unsigned gi = g0 + threadIdx.y; gi < g1; gi += TY) {
+      const unsigned row = gi / gw, gx = gi - row * gw;    // row = b * Ho + ho
+      const unsigned b = row / (unsigned)Ho, ho = row - b * Ho;
       const int wo0 = gx * PW;
-      uint4 d[PW];
-      const __nv_bfloat16* dp = dz + (((long long)b * Ho + ho) * Wo + wo0) * C + c0;
+      const int hi0 = (int)ho * S - 1, wi0 = wo0 * S - 1;
+      const __nv_bfloat16* dp = dz + ((size_t)row * Wo + wo0) * C + c0;
+      const __nv_bfloat16* xb = x + (size_t)b * H * rowC + c0;
+      uint4 d[PW], xr[3][NCOL];
 #pragma unroll
       for (int o = 0; o < PW; ++o)
-        d[o] = (wo0 + o < Wo) ? __ldg(reinterpret_cast<const uint4*>(dp + (long long)o * C)) : make_uint4(0, 0, 0, 0);
-      const int hi0 = ho * S - 1, wi0 = wo0 * S - 1;
-      const __nv_bfloat16* xb = x + (((long long)b * H + hi0) * W + wi0) * C + c0;
+        d[o] = (wo0 + o < Wo) ? __ldg(reinterpret_cast<const uint4*>(dp + o * C)) : make_uint4(0, 0, 0, 0);
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
         const bool hok = (unsigned)(hi0 + kh) < (unsigned)H;
-        uint4 xr[NCOL];
+        const unsigned ro = (unsigned)(hi0 + kh) * rowC;
 #pragma unroll
         for (int i = 0; i < NCOL; ++i)
-          xr[i] = (hok && (unsigned)(wi0 + i) < (unsigned)W) ? __ldg(reinterpret_cast<const uint4*>(xb + kh * rowC + (long long)i * C))
-                                                             : make_uint4(0, 0, 0, 0);
+          xr[kh][i] = (hok && (unsigned)(wi0 + i) < (unsigned)W)
+                          ? __ldg(reinterpret_cast<const uint4*>(xb + ro + (unsigned)(wi0 + i) * C))
+                          : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
           float* a = acc[kh * 3 + kw];
 #pragma unroll
           for (int o = 0; o < PW; ++o) {
-            const uint4 xv = xr[o * S + kw], dv = d[o];
+            const uint4 xv = xr[kh][o * S + kw], dv = d[o];
             a[0] = fma_bf16_lo(xv.x, dv.x, a[0]); a[1] = fma_bf16_hi(xv.x, dv.x, a[1]);
             a[2] = fma_bf16_lo(xv.y, dv.y, a[2]); a[3] = fma_bf16_hi(xv.y, dv.y, a[3]);
             a[4] = fma_bf16_lo(xv.z, dv.z, a[4]); a[5] = fma_bf16_hi(xv.z, dv.z, a[5]);
             a[6] = fma_bf16_lo(xv.w, dv.w, a[6]); a[7] = fma_bf16_hi(xv.w, dv.w, a[7]);
           }
         }
-      }
     }
   }
-  __shared__ float red[256][8 + 1];
-  const int tid = threadIdx.y * TX + threadIdx.x;
+  const int CT = TX * 8, nout = 9 * CT;
+  float* mine = dww_red + (size_t)threadIdx.y * nout + threadIdx.x * 8;
 #pragma unroll
-  for (int o = 0; o < 9; ++o) {
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 8; ++j) red[tid][j] = acc[o][j];
-    __syncthreads();
-    int top = 1;
-    while (top < TY) top <<= 1;
-    for (int stride = top >> 1; stride >= 1; stride >>= 1) {
-      if (threadIdx.y < stride && threadIdx.y + stride < TY) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) red[tid][j] += red[tid + stride * TX][j];
-      }
-      __syncthreads();
-    }
-    if (threadIdx.y == 0 && active) {
-      double* dst = dw + ((long long)(blockIdx.x % nslot) * 9 + o) * C + c0;      // one of nslot copies (see channel_reduce)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(dst + j, (double)red[threadIdx.x][j]);
-    }
+  for (int t = 0; t < 9; ++t) {
+    *reinterpret_cast<float4*>(mine + t * CT) = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
+    *reinterpret_cast<float4*>(mine + t * CT + 4) = make_float4(acc[t][4], acc[t][5], acc[t][6], acc[t][7]);
+  }
+  __syncthreads();
+  double* dst = dw + (size_t)(blockIdx.x % nslot) * 9 * C;              // one of nslot copies (see channel_reduce)
+  for (int o = threadIdx.y * TX + threadIdx.x; o < nout; o += TX * TY) {
+    const int t = o / CT, cl = o - t * CT;
+    const int c = blockIdx.y * CT + cl;
+    if (c >= C) continue;
+    float sum = 0.f;
+    for (int l = 0; l < TY; ++l) sum += dww_red[l * nout + o];
+    atomicAdd(dst + t * C + c, (double)sum);
   }
 }
 
@@ -1360,16 +1363,37 @@ int b200seg_dw_wgrad(const void* x, const void* dz, double* dw, int nslot, int d
   const int ppb = red_ppb(P, block, C / vn);
   dim3 grid(cdiv(P, ppb), cdiv(C / vn, block.x));
   cudaStream_t st = (cudaStream_t)s;
-  static int variant = -1;      // B200SEG_DW_WGRAD: 0 = generic kernel, 2 / 4 = pixels per thread of the bf16 kernel (default 2)
-  if (variant < 0) { const char* e = getenv("B200SEG_DW_WGRAD"); variant = e ? atoi(e) : 2; }
-  if (dtype == B200SEG_BF16 && variant > 0) {
+  static int variant = -1;      // B200SEG_DW_WGRAD: 0 = generic kernel, 2 / 4 = pixels per thread of the bf16 kernel (default 4)
+  if (variant < 0) { const char* e = getenv("B200SEG_DW_WGRAD"); variant = e ? atoi(e) : 4; }
+  const bool small_index = (long long)B * H * W * C < (1LL << 31);
+  if (dtype == B200SEG_BF16 && variant > 0 && small_index) {
     const int pw = variant == 4 ? 4 : 2;
     const long long G = (long long)B * Ho * ((Wo + pw - 1) / pw);
-    const int gpb = max(1, (ppb + pw - 1) / pw);
-    dim3 g2(cdiv(G, gpb), cdiv(C / vn, block.x));
-#define DWW(S, PW) dw_wgrad_bf16_kernel<S, PW><<<g2, block, 0, st>>>((const bf16*)x, (const bf16*)dz, B, H, W, C, Ho, Wo, gpb, dw, nslot)
-    if (stride == 1) { if (pw == 4) DWW(1, 4); else DWW(1, 2); }
-    else { if (pw == 4) DWW(2, 4); else DWW(2, 2); }
+    static int bps = -1;          // blocks per SM (one is resident at a time; more = shorter tail, more atomics)
+    if (bps < 0) { const char* e = getenv("B200SEG_DWW_BPS"); bps = e ? max(1, atoi(e)) : 1; }
+    // L2-resident layers (the 13 deep ones): blocks of 2 channel vectors (one 32-byte sector per pixel) x 128 pixel lanes,
+    // the channel axis on grid.y -- a block then emits 9*16 atomics instead of 9*C.  With full-width blocks the f64
+    // atomics (148 blocks x 9 x 384 channels = 511 k, ~20 per ns chip-wide) were 25 of the 33 us of a 384-channel layer.
+    static long long narrow_bytes = -1;
+    if (narrow_bytes < 0) { const char* e = getenv("B200SEG_DWW_NARROW_MB"); narrow_bytes = (e ? atoll(e) : 48) << 20; }
+    dim3 blk = block;
+    if ((long long)B * H * W * C * 2 <= narrow_bytes && (C / vn) % 2 == 0 && C / vn > 2) blk = dim3(2, 128);
+    const long long gy = cdiv(C / vn, blk.x);
+    long long gpb = cdiv(G * gy, (long long)sm_count() * bps);
+    if (gpb < (long long)blk.y) gpb = blk.y;
+    dim3 g2(cdiv(G, gpb), (unsigned)gy);
+    const size_t smem = (size_t)blk.y * 9 * blk.x * 8 * sizeof(float);
+#define DWW(S, PW)                                                                                                     \
+  {                                                                                                                    \
+    static bool attr_set = false;                                                                                      \
+    if (!attr_set) {                                                                                                   \
+      cudaFuncSetAttribute(dw_wgrad_bf16_kernel<S, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 72 * 4);    \
+      attr_set = true;                                                                                                 \
+    }                                                                                                                  \
+    dw_wgrad_bf16_kernel<S, PW><<<g2, blk, smem, st>>>((const bf16*)x, (const bf16*)dz, B, H, W, C, Ho, Wo, (int)gpb, dw, nslot); \
+  }
+    if (stride == 1) { if (pw == 4) DWW(1, 4) else DWW(1, 2) }
+    else { if (pw == 4) DWW(2, 4) else DWW(2, 2) }
 #undef DWW
     return check_launch("dw_wgrad");
   }
