@@ -286,6 +286,7 @@ struct Vec16<float> {
   float v[4];                                  // unpack later (see train_ops.cu, "batched streaming")
   static __device__ __forceinline__ Raw ldraw(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
   __device__ __forceinline__ void unpack(const Raw& t) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  __device__ __forceinline__ void unpack_dep(const Raw& t, uint32_t) { unpack(t); }
   __device__ __forceinline__ void load(const float* p) { unpack(ldraw(p)); }
   __device__ __forceinline__ void store(float* p) const {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
@@ -305,6 +306,15 @@ struct Vec16<__nv_bfloat16> {
   __device__ __forceinline__ void unpack(const Raw& t) {
     v[0] = bf16lo(t.x); v[1] = bf16hi(t.x); v[2] = bf16lo(t.y); v[3] = bf16hi(t.y);
     v[4] = bf16lo(t.z); v[5] = bf16hi(t.z); v[6] = bf16lo(t.w); v[7] = bf16hi(t.w);
+  }
+  // unpack with a run-time-zero word folded into every element ((x << 16) + dep is one LEA, (x & 0xffff0000) | dep one
+  // LOP3: no extra instructions): makes the arithmetic on this vector depend on whatever `dep` was computed from --
+  // see all_loaded() in train_ops.cu
+  __device__ __forceinline__ void unpack_dep(const Raw& t, uint32_t dep) {
+    v[0] = __uint_as_float((t.x << 16) + dep); v[1] = __uint_as_float((t.x & 0xffff0000u) | dep);
+    v[2] = __uint_as_float((t.y << 16) + dep); v[3] = __uint_as_float((t.y & 0xffff0000u) | dep);
+    v[4] = __uint_as_float((t.z << 16) + dep); v[5] = __uint_as_float((t.z & 0xffff0000u) | dep);
+    v[6] = __uint_as_float((t.w << 16) + dep); v[7] = __uint_as_float((t.w & 0xffff0000u) | dep);
   }
   __device__ __forceinline__ void load(const __nv_bfloat16* p) { unpack(ldraw(p)); }
   __device__ __forceinline__ void store(__nv_bfloat16* p) const {

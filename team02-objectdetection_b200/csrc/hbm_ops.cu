@@ -13,6 +13,7 @@
 namespace b200 {
 
 static inline int grid_for(long long items, int threads) {
+  if (items >= (1LL << 31)) return 0;      // the kernels index their threads with 32 bits: a zero grid fails loudly in check_launch
   long long g = (items + threads - 1) / threads;
   return (int)(g < 1 ? 1 : g);
 }
@@ -255,10 +256,10 @@ dwconv3x3_kernel(const T* __restrict__ x, const float* __restrict__ w, const flo
   const int cv = C / VN;
   const int strips = (Wo + TW - 1) / TW;
   const long long total = (long long)B * Ho * strips * cv;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;     // < 2^31 threads (checked by the launcher): 32-bit div/mod
   if (idx >= total) return;
-  const int c0 = (int)(idx % cv) * VN;
-  long long p = idx / cv;
+  const int c0 = (int)(idx % (unsigned)cv) * VN;
+  unsigned p = idx / (unsigned)cv;
   const int st = (int)(p % strips); p /= strips;
   const int ho = (int)(p % Ho);
   const int b = (int)(p / Ho);
@@ -336,10 +337,10 @@ dwconv3x3_bf16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restri
   const int cv = C >> 3;
   const int sw_ = (Wo + TW - 1) / TW, sh_ = (Ho + TH - 1) / TH;
   const long long total = (long long)B * sh_ * sw_ * cv;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;     // < 2^31 threads (checked by the launcher): 32-bit div/mod
   if (idx >= total) return;
-  const int c0 = (int)(idx % cv) << 3;
-  long long p = idx / cv;
+  const int c0 = (int)(idx % (unsigned)cv) << 3;
+  unsigned p = idx / (unsigned)cv;
   const int tw = (int)(p % sw_); p /= sw_;
   const int th = (int)(p % sh_);
   const int b = (int)(p / sh_);
@@ -426,10 +427,10 @@ dwconv3x3_bf16w_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
   const int cv = C >> 3;
   const int sw_ = (Wo + TW - 1) / TW, sh_ = (Ho + TH - 1) / TH;
   const long long total = (long long)B * sh_ * sw_ * cv;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;     // < 2^31 threads (checked by the launcher): 32-bit div/mod
   if (idx >= total) return;
-  const int c0 = (int)(idx % cv) << 3;
-  long long p = idx / cv;
+  const int c0 = (int)(idx % (unsigned)cv) << 3;
+  unsigned p = idx / (unsigned)cv;
   const int tw = (int)(p % sw_); p /= sw_;
   const int th = (int)(p % sh_);
   const int b = (int)(p / sh_);
@@ -519,12 +520,28 @@ upsample2x_concat_kernel(const T* __restrict__ skip, const T* __restrict__ x, T*
   pdl_wait();
   using V = Vec16<T>;
   constexpr int VN = V::N;
-  const int C = Cs + Cu, cv = C / VN, Wo = 2 * w;
-  const long long total = (long long)B * h * w * cv;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int C = Cs + Cu, cvs = Cs / VN, cvu = Cu / VN, Wo = 2 * w;
+  // When the skip slice ends on a 32-byte sector boundary, threads [0, n_skip) copy the skip slice and the rest interpolate:
+  // warps are uniform (with the two kinds interleaved along the channel axis every warp of the 48-channel stage executed
+  // both paths).  Otherwise (24 skip channels: 48 bytes) the two kinds stay interleaved so that the sector shared by the
+  // two slices of a pixel is written by neighbouring lanes at the same time (split, that stage was 30 % slower).
+  const unsigned npix = (unsigned)B * h * w, total = npix * (cvs + cvu);
+  unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;     // < 2^31 threads (checked by the launcher): 32-bit div/mod
   if (idx >= total) return;
-  const int c = (int)(idx % cv) * VN;
-  long long p = idx / cv;
+  int c;
+  unsigned p;
+  if ((Cs * (int)sizeof(T)) % 32 == 0) {
+    const unsigned n_skip = npix * cvs;
+    const bool is_skip = idx < n_skip;
+    if (!is_skip) idx -= n_skip;
+    const unsigned cv = is_skip ? cvs : cvu;
+    c = (int)(idx % cv) * VN + (is_skip ? 0 : Cs);
+    p = idx / cv;
+  } else {
+    const unsigned cv = cvs + cvu;
+    c = (int)(idx % cv) * VN;
+    p = idx / cv;
+  }
   const int j = (int)(p % w); p /= w;
   const int i = (int)(p % h);
   const int b = (int)(p / h);
@@ -623,10 +640,10 @@ upsample2x_ac_kernel(const T* __restrict__ lg, TO* __restrict__ out, uint8_t* __
   const int Ho = 2 * h, Wo = 2 * w;
   const int wq = Wo / PPT;
   const long long total = (long long)B * Ho * wq;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;     // < 2^31 threads (checked by the launcher): 32-bit div/mod
   if (idx >= total) return;
-  const int q = (int)(idx % wq);
-  long long p = idx / wq;
+  const int q = (int)(idx % (unsigned)wq);
+  unsigned p = idx / (unsigned)wq;
   const int ho = (int)(p % Ho);
   const int b = (int)(p / Ho);
   const float sch = (Ho > 1) ? (float)(h - 1) / (float)(Ho - 1) : 0.f;
@@ -704,12 +721,12 @@ nhwc_to_nchw_kernel(const T* __restrict__ x, int ldc, TO* __restrict__ out, int 
   pdl_trigger();
   pdl_wait();
   const long long total = (long long)B * H * W;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;     // < 2^31 threads (checked by the launcher): 32-bit div/mod
   if (idx >= total) return;
-  const long long hw = (long long)H * W;
+  const unsigned hw = (unsigned)H * W;
   const int b = (int)(idx / hw);
   const long long pix = idx % hw;
-  const T* xp = x + idx * ldc;
+  const T* xp = x + (long long)idx * ldc;
   for (int c = 0; c < C; ++c) out[((long long)b * C + c) * hw + pix] = from_f32<TO>(to_f32<T>(xp[c]));
 }
 
@@ -722,10 +739,10 @@ maxpool2x2_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int 
   constexpr int VN = V::N;
   const int Ho = H / 2, Wo = W / 2, cv = C / VN;
   const long long total = (long long)B * Ho * Wo * cv;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;     // < 2^31 threads (checked by the launcher): 32-bit div/mod
   if (idx >= total) return;
-  const int c = (int)(idx % cv) * VN;
-  long long p = idx / cv;
+  const int c = (int)(idx % (unsigned)cv) * VN;
+  unsigned p = idx / (unsigned)cv;
   const int wo = (int)(p % Wo); p /= Wo;
   const int ho = (int)(p % Ho);
   const int b = (int)(p / Ho);

@@ -55,10 +55,23 @@ static inline int red_ppb(long long P, const dim3& block, int cvecs) {
   return (int)ppb;
 }
 
+// ptxas sinks independent loads into the arithmetic that consumes them when that saves registers, whatever order the
+// source (or the PTX) has them in, volatile or not, across warp barriers too.  What does pin a batch is a data dependence:
+// one word of every loaded vector is OR-ed together, masked with a value that is zero at run time but that the compiler
+// cannot prove zero (batch size >> 30), and OR-ed into an operand of the first arithmetic instruction.  Cost: N/2 LOP3.
+__device__ __forceinline__ uint32_t opaque_zero(int positive_below_2_30) { return (uint32_t)positive_below_2_30 >> 30; }
+template <int N>
+__device__ __forceinline__ uint32_t all_loaded(const uint4 (&r)[N], uint32_t zmask) {
+  uint32_t t = 0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) t |= r[i].x;
+  return t & zmask;
+}
+
 // "Batched streaming": the pixel loop first issues U rows of 16-byte loads per input (raw, not yet unpacked), then does
 // the arithmetic.  With the loads written inside the per-pixel body the compiler kept them behind the body's branches,
 // i.e. 32 bytes in flight per thread and ~16 KB per SM: the large-layer BatchNorm passes ran at 2.3-2.9 TB/s, latency-bound.
-template <typename T, int NOUT, int NIN, int U = 4, typename F>
+template <typename T, int NOUT, int NIN, int U = 4, bool PIN = false, typename F>
 __device__ __forceinline__ void channel_reduce(const T* const (&in)[NIN], long long P, int C, int ppb, double* const* out,
                                                int nslot, long long slot_stride, F&& f) {
   using V = Vec16<T>;
@@ -84,11 +97,18 @@ __device__ __forceinline__ void channel_reduce(const T* const (&in)[NIN], long l
       for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int i = 0; i < NIN; ++i) raw[u][i] = V::ldraw(in[i] + off + u * rowstep);
+      uint32_t dep = 0;
+      if constexpr (PIN && sizeof(T) == 2) {          // pin the batch (see all_loaded); measured slower on bn_stats
+                                                      // (94 registers, half the resident blocks), so opt-in
+        const uint32_t zm = opaque_zero(ppb);
+#pragma unroll
+        for (int u = 0; u < U; ++u) dep |= all_loaded(raw[u], zm);
+      }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         V v[NIN];
 #pragma unroll
-        for (int i = 0; i < NIN; ++i) v[i].unpack(raw[u][i]);
+        for (int i = 0; i < NIN; ++i) v[i].unpack_dep(raw[u][i], dep);
         f(v, acc);
       }
     }
@@ -944,82 +964,103 @@ __device__ __forceinline__ float bil_weight_ac_true(int r, int i, int n_in, floa
   return (i0 == i ? 1.f - l : 0.f) + (i1 == i ? l : 0.f);
 }
 
-// dcat [B,2h,2w,Cs+Cu] -> dskip [B,2h,2w,Cs] (+= acc_skip) and dx [B,h,w,Cu]
+// dcat [B,2h,2w,Cs+Cu] -> dskip [B,2h,2w,Cs] (+= acc_skip) and dx [B,h,w,Cu].
+// Threads [0, n_skip) copy the skip slice, the rest gather the upsampled slice: warps are uniform (one thread per
+// low-resolution pixel x channel vector of ITS slice), and both paths issue all their loads before any arithmetic --
+// the 4 x 4 gather reads clamped coordinates with zero weights outside the image instead of skipping taps (the
+// `continue`s kept one load in flight per thread; skipped and zero-weight terms give the same sum for finite gradients).
 template <typename T>
 __global__ void __launch_bounds__(256)
 upcat_bwd_kernel(const T* __restrict__ dcat, const T* __restrict__ acc_skip, T* __restrict__ dskip, T* __restrict__ dx,
                  int B, int h, int w, int Cs, int Cu) {
   using V = Vec16<T>;
+  using Raw = typename V::Raw;
   constexpr int VN = V::N;
-  const int C = Cs + Cu, cv = C / VN, Ho = 2 * h, Wo = 2 * w;
-  const long long total = (long long)B * h * w * cv;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int C = Cs + Cu, cvs = Cs / VN, cvu = Cu / VN, Ho = 2 * h, Wo = 2 * w;
+  const unsigned npix = (unsigned)B * h * w;               // < 2^31 threads (checked by the launcher): 32-bit div/mod
+  const unsigned n_skip = npix * cvs, total = n_skip + npix * cvu;
+  unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
+  const bool skip = idx < n_skip;
+  if (!skip) idx -= n_skip;
+  const unsigned cv = skip ? cvs : cvu;
   const int c = (int)(idx % cv) * VN;
-  long long p = idx / cv;
+  unsigned p = idx / cv;
   const int j = (int)(p % w); p /= w;
   const int i = (int)(p % h);
   const int b = (int)(p / h);
-  if (c < Cs) {          // the skip half: plain slice (+ accumulation of the skip tensor's other gradient)
+  if (skip) {            // plain slice (+ accumulation of the skip tensor's other gradient)
+    Raw rv[4], ru[4];
+    long long pix[4];
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+    for (int a = 0; a < 4; ++a) {
+      pix[a] = ((long long)b * Ho + 2 * i + (a >> 1)) * Wo + 2 * j + (a & 1);
+      rv[a] = V::ldraw(dcat + pix[a] * C + c);
+      if (acc_skip) ru[a] = V::ldraw(acc_skip + pix[a] * Cs + c);
+    }
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const long long pix = ((long long)b * Ho + 2 * i + a) * Wo + 2 * j + q;
-        V v, u;
-        v.load(dcat + pix * C + c);
-        if (acc_skip) {
-          u.load(acc_skip + pix * Cs + c);
+    for (int a = 0; a < 4; ++a) {
+      V v, u;
+      v.unpack(rv[a]);
+      if (acc_skip) {
+        u.unpack(ru[a]);
 #pragma unroll
-          for (int k = 0; k < VN; ++k) v.v[k] += u.v[k];
-        }
-        v.store(dskip + pix * Cs + c);
+        for (int k = 0; k < VN; ++k) v.v[k] += u.v[k];
       }
+      v.store(dskip + pix[a] * Cs + c);
+    }
     return;
   }
-  const int cu = c - Cs;
-  // the 4 + 4 separable weights of this low-resolution pixel, computed once (they were re-derived inside the 4 x 4 gather);
-  // every product wy*wx is a multiple of 1/16 <= 1, i.e. exact in bf16, so bf16 storage takes the mixed-precision FMA
-  // (f32 += bf16 * bf16) on the packed vectors as loaded -- no unpack instructions.  Same terms, same order as before.
+  // the 4 + 4 separable weights of this low-resolution pixel; every product wy*wx is a multiple of 1/16 <= 1, i.e. exact
+  // in bf16, so bf16 storage takes the mixed-precision FMA (f32 += bf16 * bf16) on the packed vectors as loaded.
   float wy[4], wx[4];
+  int rr[4], qq[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int r = 2 * i - 1 + k, q = 2 * j - 1 + k;
     wy[k] = (r >= 0 && r < Ho) ? bil_weight_ac_false(r, i, h) : 0.f;
     wx[k] = (q >= 0 && q < Wo) ? bil_weight_ac_false(q, j, w) : 0.f;
+    rr[k] = min(max(r, 0), Ho - 1);
+    qq[k] = min(max(q, 0), Wo - 1);
+  }
+  const T* base = dcat + (long long)b * Ho * Wo * C + Cs + c;
+  Raw raw[4][4];
+#pragma unroll
+  for (int kr = 0; kr < 4; ++kr)
+#pragma unroll
+    for (int kq = 0; kq < 4; ++kq) raw[kr][kq] = V::ldraw(base + ((long long)rr[kr] * Wo + qq[kq]) * C);
+  uint32_t dep = 0;
+  if constexpr (sizeof(T) == 2) {
+    const uint32_t zm = opaque_zero(B);
+#pragma unroll
+    for (int kr = 0; kr < 4; ++kr) dep |= all_loaded(raw[kr], zm);
   }
   float acc[VN];
 #pragma unroll
   for (int k = 0; k < VN; ++k) acc[k] = 0.f;
 #pragma unroll
-  for (int kr = 0; kr < 4; ++kr) {
-    if (wy[kr] == 0.f) continue;
-    const int r = 2 * i - 1 + kr;
+  for (int kr = 0; kr < 4; ++kr)
 #pragma unroll
     for (int kq = 0; kq < 4; ++kq) {
       const float ww = wy[kr] * wx[kq];
-      if (ww == 0.f) continue;
-      const int q = 2 * j - 1 + kq;
-      const T* src = dcat + (((long long)b * Ho + r) * Wo + q) * C + c;
       if constexpr (sizeof(T) == 2) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src));
-        const uint32_t wp = pack_bf16x2(ww, ww);
+        const uint4 u = raw[kr][kq];
+        const uint32_t wp = pack_bf16x2(ww, ww) | dep;
         acc[0] = fma_bf16_lo(u.x, wp, acc[0]); acc[1] = fma_bf16_hi(u.x, wp, acc[1]);
         acc[2] = fma_bf16_lo(u.y, wp, acc[2]); acc[3] = fma_bf16_hi(u.y, wp, acc[3]);
         acc[4] = fma_bf16_lo(u.z, wp, acc[4]); acc[5] = fma_bf16_hi(u.z, wp, acc[5]);
         acc[6] = fma_bf16_lo(u.w, wp, acc[6]); acc[7] = fma_bf16_hi(u.w, wp, acc[7]);
       } else {
         V v;
-        v.load(src);
+        v.unpack(raw[kr][kq]);
 #pragma unroll
         for (int k = 0; k < VN; ++k) acc[k] = fmaf(ww, v.v[k], acc[k]);
       }
     }
-  }
   V o;
 #pragma unroll
   for (int k = 0; k < VN; ++k) o.v[k] = acc[k];
-  o.store(dx + (((long long)b * h + i) * w + j) * Cu + cu);
+  o.store(dx + (((long long)b * h + i) * w + j) * Cu + c);
 }
 
 // dout NCHW f32 [B,C,2h,2w] -> dlogits NHWC T [B,h,w,16] (channels >= C zero), align_corners=True
@@ -1452,6 +1493,7 @@ int b200seg_upcat_bwd(const void* dcat, const void* acc_skip, void* dskip, void*
   const int vn = dtype == B200SEG_BF16 ? 8 : 4;
   B200_REQUIRE(Cs % vn == 0 && Cu % vn == 0 && Cu > 0 && Cs >= 0, "upcat_bwd: Cs=%d Cu=%d", Cs, Cu);
   B200_REQUIRE(B > 0 && h > 0 && w > 0, "upcat_bwd: empty tensor");
+  B200_REQUIRE((long long)B * h * w * ((Cs + Cu) / vn) < (1LL << 31), "upcat_bwd: tensor too large for 32-bit thread indices");
   const unsigned g = cdiv((long long)B * h * w * ((Cs + Cu) / vn), 256);
   cudaStream_t st = (cudaStream_t)s;
   DISPATCH_T(dtype, (upcat_bwd_kernel<float><<<g, 256, 0, st>>>((const float*)dcat, (const float*)acc_skip, (float*)dskip, (float*)dx, B, h, w, Cs, Cu)),

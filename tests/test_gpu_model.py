@@ -255,6 +255,31 @@ def test_plain_unet_fp32_and_bf16():
     assert e16 < 3e-2
 
 
+def test_plain_unet_reference_width_matches_oracle():
+    """BASELINE config[3]'s architecture (UNet, base 64 = the reference default, unet.py:124-171) at a frame the CPU oracle
+    finishes in seconds: every dense conv then has >= 64 channels and takes the tensor-core / wide-channel kernels
+    that the base-16 fixture above never reaches."""
+    sd = O.synth_state_dict(O.unet_param_shapes(10, 64), seed=5)
+    m = b200seg.UNet(output_channels=10, base_filters=64)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).eval()
+    x = O.synth_input(2, 64, 128, seed=5)
+    with torch.no_grad():
+        ref = O.unet_forward(sd, x)
+        y = m(x.to(DEV)).cpu()
+    e = rel_err(y, ref)
+    eng = m._get_engine()
+    eng.precision = "bf16"
+    with torch.no_grad():
+        y16 = m(x.to(DEV)).float().cpu()
+    eng.precision = None
+    e16 = rel_err(y16, ref)
+    agree = float((y16.argmax(1) == ref.argmax(1)).float().mean())
+    _note("unet64_eval", err=e, err_bf16=e16, mask_agreement_bf16=agree)
+    assert e < 1e-4
+    assert e16 < 3e-2
+
+
 def test_full_size_batch_properties_bf16():
     """BASELINE config[1] at full size (batch 64, 3x256x512, bf16): size-independent properties instead of an oracle
     run -- (1) deterministic: two passes are bit-identical; (2) frames are independent: image b of the batch equals
