@@ -30,6 +30,8 @@ struct WgradArgs {
                            // feed the three horizontal taps (B descriptor start advanced by one 128-byte pixel row)
   long long pix_tiles, tiles_per_split;
   int tmem_cols;
+  int exact_n;
+  int m64;                 // Cout <= 64: M = 64 MMAs (one dz box; accumulator rows on TMEM lanes 32*(r/16) + r%16)
 };
 
 constexpr int WG_THREADS = 192;
@@ -73,8 +75,11 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_const
   const int co0 = m_tile * 128, ci0 = n_tile * a.n_boxes * 64;
   int boxes = a.n_boxes;                       // cin boxes that really exist in this N tile
   while (boxes > 1 && ci0 + (boxes - 1) * 64 >= a.Cin) --boxes;
-  const int a_boxes = (co0 + 64 < a.Cout) ? 2 : 1;
-  const int umma_n = boxes * 64;
+  const int a_boxes = (!a.m64 && co0 + 64 < a.Cout) ? 2 : 1;
+  // MMA N: the cin that really exist in this tile, rounded to the instruction granularity (16 at M = 128) -- not the
+  // 64-channel box count: a 32-channel layer issued N = 64 MMAs whose upper half multiplied zeros
+  int umma_n = boxes * 64;
+  if (a.exact_n) { const int real = (a.Cin - ci0 + 15) & ~15; if (real < umma_n) umma_n = real; }
   int dh = 0, dwv = 0;
   if (a.rowmode) { dh = tap - 1; dwv = -1; }
   else if (a.taps == 9) { dh = tap / 3 - 1; dwv = tap % 3 - 1; }
@@ -127,7 +132,10 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_const
   } else if (warp == 1) {
     // ================= MMA issuer =================
     // instruction descriptor: bf16 x bf16 -> f32, A and B both MN-major (bits 15, 16), M = 128, N = umma_n
-    const uint32_t idesc = umma_idesc_bf16(128, umma_n) | (1u << 15) | (1u << 16);
+    // With <= 64 output channels M = 64: the MN-major A operand is read from shared memory by every MMA, and at M = 128 three
+    // quarters of those reads (and of the tensor-pipe rows) were the zero half / zero box of the dz tile -- the kernel ran at
+    // ~82 cycles per N = 64 MMA against a 32-cycle issue floor (profiles/r02_wgrad_kbench.txt).
+    const uint32_t idesc = umma_idesc_bf16(a.m64 ? 64 : 128, umma_n) | (1u << 15) | (1u << 16);
     const uint32_t desc_hi = (uint32_t)(umma_desc_mn128(0, WG_BOX) >> 32);
     const uint32_t lbo_bits = (uint32_t)((WG_BOX >> 4) & 0x3FFF) << 16;
     const uint32_t lbo_bits_x = (uint32_t)((xbox >> 4) & 0x3FFF) << 16;
@@ -157,7 +165,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_const
   } else if (t_begin < t_end) {
     // ================= epilogue: TMEM -> red.global.add =================
     const int q = warp & 3;
-    const int co = co0 + q * 32 + lane;
+    // M = 128: accumulator row r on TMEM lane r.  M = 64: rows 16q .. 16q+15 on the first 16 lanes of warp q's partition.
+    const int co = a.m64 ? (lane < 16 ? co0 + q * 16 + lane : a.Cout) : co0 + q * 32 + lane;
     mbar_wait(acc_full, 0, 13);
     tc_fence_after();
     const int n_acc = a.rowmode ? 3 : 1;
@@ -229,6 +238,11 @@ extern "C" int b200seg_conv_wgrad_tc(const void* x, const void* dz, float* dw, i
     a.rowmode = (taps == 9 && W >= 128 && row_ok) ? 1 : 0;
   }
   if (a.rowmode) { a.BW = 128; a.BH = 1; }
+  {
+    static int exact = -1;
+    if (exact < 0) { const char* e = getenv("B200SEG_WGRAD_EXACT_N"); exact = (e && e[0] == '0') ? 0 : 1; }
+    a.exact_n = exact;
+  }
   a.tiles_w = (a.W + a.BW - 1) / a.BW;
   a.tiles_h = (a.H + a.BH - 1) / a.BH;
   a.pix_tiles = (long long)a.tiles_w * a.tiles_h * a.B;
@@ -237,6 +251,11 @@ extern "C" int b200seg_conv_wgrad_tc(const void* x, const void* dz, float* dw, i
   a.n_boxes = cin_boxes < max_boxes ? cin_boxes : max_boxes;
   a.n_tiles = (cin_boxes + a.n_boxes - 1) / a.n_boxes;
   a.m_tiles = (Cout + 127) / 128;
+  {
+    static int m64 = -1;
+    if (m64 < 0) { const char* e = getenv("B200SEG_WGRAD_M64"); m64 = (e && e[0] == '0') ? 0 : 1; }
+    a.m64 = (m64 && Cout <= 64) ? 1 : 0;
+  }
   a.tmem_cols = 32;
   while (a.tmem_cols < (a.rowmode ? 3 : 1) * a.n_boxes * 64) a.tmem_cols <<= 1;
   const int stage_bytes = 2 * WG_BOX + a.n_boxes * (a.rowmode ? WG_XBOX : WG_BOX);

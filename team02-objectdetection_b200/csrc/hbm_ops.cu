@@ -561,17 +561,27 @@ upsample2x_concat_kernel(const T* __restrict__ skip, const T* __restrict__ x, T*
   const int qj[3] = {max(j - 1, 0), j, min(j + 1, w - 1)};
   const T* xb = x + (long long)b * h * w * Cu + cu;
   float te[3][VN], to[3][VN];     // vertically blended columns for the even / odd output row
+  if constexpr (sizeof(T) == 2) {
+    // bf16: the same arithmetic on the packed vectors as loaded, through the mixed-precision FMA (f32 = bf16 * bf16 + f32;
+    // 0.25 and 0.75 are bf16 numbers, the products are exact): no unpack instructions.  All nine loads are issued before
+    // the first FMA: a run-time-zero word derived from every loaded vector is OR-ed into the two weight constants (ptxas
+    // otherwise sinks the loads into the arithmetic, three in flight per thread).
+    uint4 a[3], m[3], d[3];
 #pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    if constexpr (sizeof(T) == 2) {
-      // bf16: the same arithmetic on the packed vectors as loaded, through the mixed-precision FMA (f32 = bf16 * bf16 + f32;
-      // 0.25 and 0.75 are bf16 numbers, the products are exact): no unpack instructions -- the kernel is bound by
-      // instruction issue (66 % of the slots at 0.55 of HBM, profiles/r02_ncu_forward_summary.txt), not by bytes
-      const uint4 a = __ldg(reinterpret_cast<const uint4*>(xb + ((long long)ri[0] * w + qj[q]) * Cu));
-      const uint4 m = __ldg(reinterpret_cast<const uint4*>(xb + ((long long)ri[1] * w + qj[q]) * Cu));
-      const uint4 d = __ldg(reinterpret_cast<const uint4*>(xb + ((long long)ri[2] * w + qj[q]) * Cu));
-      constexpr uint32_t Q25 = 0x3E803E80u, Q75 = 0x3F403F40u;       // bf16x2 {0.25, 0.25}, {0.75, 0.75}
-      const uint32_t av[4] = {a.x, a.y, a.z, a.w}, mv[4] = {m.x, m.y, m.z, m.w}, dv[4] = {d.x, d.y, d.z, d.w};
+    for (int q = 0; q < 3; ++q) {
+      a[q] = __ldg(reinterpret_cast<const uint4*>(xb + ((long long)ri[0] * w + qj[q]) * Cu));
+      m[q] = __ldg(reinterpret_cast<const uint4*>(xb + ((long long)ri[1] * w + qj[q]) * Cu));
+      d[q] = __ldg(reinterpret_cast<const uint4*>(xb + ((long long)ri[2] * w + qj[q]) * Cu));
+    }
+    uint32_t dep = 0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) dep |= a[q].x | m[q].x | d[q].x;
+    dep &= (uint32_t)B >> 30;                                        // B < 2^30: zero, but not provably so
+    const uint32_t Q25 = 0x3E803E80u | dep, Q75 = 0x3F403F40u | dep;   // bf16x2 {0.25, 0.25}, {0.75, 0.75}
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const uint32_t av[4] = {a[q].x, a[q].y, a[q].z, a[q].w}, mv[4] = {m[q].x, m[q].y, m[q].z, m[q].w},
+                     dv[4] = {d[q].x, d[q].y, d[q].z, d[q].w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         te[q][2 * k] = fma_bf16_lo(mv[k], Q75, fma_bf16_lo(av[k], Q25, 0.f));
@@ -579,7 +589,10 @@ upsample2x_concat_kernel(const T* __restrict__ skip, const T* __restrict__ x, T*
         to[q][2 * k] = fma_bf16_lo(mv[k], Q75, fma_bf16_lo(dv[k], Q25, 0.f));
         to[q][2 * k + 1] = fma_bf16_hi(mv[k], Q75, fma_bf16_hi(dv[k], Q25, 0.f));
       }
-    } else {
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
       V a, m, d;
       a.load(xb + ((long long)ri[0] * w + qj[q]) * Cu);
       m.load(xb + ((long long)ri[1] * w + qj[q]) * Cu);
