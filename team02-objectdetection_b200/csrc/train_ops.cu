@@ -943,6 +943,144 @@ smallcin3_wgrad_tile_kernel(const TI* __restrict__ x, const T* __restrict__ dz, 
     atomicAdd(dw + i, red[i] + red[stride_q + i] + red[2 * stride_q + i] + red[3 * stride_q + i]);
 }
 
+// Stem weight gradient for bf16 dz (the training precision of the path), Cin = 3, Cout = 32 / 64.  Same job as the row-tile
+// kernel above (one 128-pixel output row segment, its 9 input rows and its dz staged in shared memory), rebuilt around what
+// the profile of that kernel showed (252 us for 117 MB: 25 scalar global loads per thread between two barriers, every job):
+//   * the NEXT job's global loads (<= 10 x values, 2-4 16-byte dz vectors per thread) are issued before the current job's
+//     arithmetic and parked in registers, so their latency is hidden by ~1000 cycles of FMAs instead of being exposed
+//     between two barriers; dz is read with 16-byte loads; the per-thread staging coordinates are computed once;
+//   * warp = 16 pixels of the segment, lane = (4 consecutive k = (tap, c)) x (8 consecutive output channels): per pixel
+//     two 16-byte dz reads + 4 patch reads feed 32 FMAs (was 1 + 4 for 16);
+//   * partial sums stay in registers across all jobs of the block; one shared-memory reduction over the 8 warps and
+//     27 * Cout atomics per block at the end.
+template <typename TI, int S, int COUT>
+__global__ void __launch_bounds__(256, 2)
+stem_wgrad_bf16_kernel(const TI* __restrict__ x, const __nv_bfloat16* __restrict__ dz, float* __restrict__ dw, int B, int H,
+                       int W, int Ho, int Wo) {
+  constexpr int NCOL = 127 * S + 3, PITCH = NCOL + 3;
+  constexpr int NX = (9 * NCOL + 255) / 256;            // x values staged per thread and job
+  constexpr int C8N = COUT / 8;
+  constexpr int ND = 128 * C8N / 256;                   // 16-byte dz vectors per thread and job
+  constexpr int NITEMS = 7 * C8N, NIT = (NITEMS + 31) / 32;
+  extern __shared__ __align__(16) float sm[];
+  float* tile = sm;                                     // [9][PITCH]   row = c*3 + kh, column j <-> input column wo0*S - 1 + j
+  float* sd = sm + ((9 * PITCH + 3) & ~3);              // [128][COUT] f32
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int HW = H * W;
+  // staging coordinates of this thread (the same for every job), packed: tile row (c*3 + kh) << 16 | column; -1 = none
+  int rc[NX];
+#pragma unroll
+  for (int k = 0; k < NX; ++k) {
+    const int e = tid + 256 * k;
+    const int rowi = e / NCOL, col = e - rowi * NCOL;
+    rc[k] = e < 9 * NCOL ? (rowi << 16) | col : -1;
+  }
+  // arithmetic coordinates
+  int toff[NIT][4], c8v[NIT];
+  bool act[NIT];
+  float acc[NIT][4][8];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int item = lane + 32 * it;
+    act[it] = item < NITEMS;
+    const int kq = act[it] ? item / C8N : 0;
+    c8v[it] = (item - (item / C8N) * C8N) * 8;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = kq * 4 + j;                         // k = tap*3 + c  (dw layout [kh][kw][c][co]); k = 27 is padding
+      const int tap = k / 3, c = k - tap * 3, kh = tap / 3, kw = tap - kh * 3;
+      toff[it][j] = (k < 27) ? (c * 3 + kh) * PITCH + kw : 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[it][j][q] = 0.f;
+    }
+  }
+  const int segs = (Wo + 127) / 128;
+  const int total = B * Ho * segs;                      // jobs (launcher: < 2^31)
+  float xr[NX];
+  uint4 dr[ND];
+  auto fetch = [&](int job) {
+    const int sg = job % segs, rowj = job / segs;       // rowj = b * Ho + ho
+    const int ho = rowj % Ho, b = rowj / Ho;
+    const int wo0 = sg * 128, wi0 = wo0 * S - 1, hi0 = ho * S - 1;
+    const TI* xb = x + (long long)b * 3 * HW + (long long)hi0 * W + wi0;
+#pragma unroll
+    for (int k = 0; k < NX; ++k) {
+      const int rowi = rc[k] >> 16, col = rc[k] & 0xffff;
+      const int c = (rowi * 11) >> 5, kh = rowi - c * 3;          // rowi / 3 for rowi < 9
+      const int hi = hi0 + kh, wi = wi0 + col;
+      const bool ok = rc[k] >= 0 && (unsigned)hi < (unsigned)H && (unsigned)wi < (unsigned)W;
+      xr[k] = ok ? to_f32<TI>(__ldg(xb + (c * HW + kh * W + col))) : 0.f;
+    }
+    const __nv_bfloat16* dzr = dz + ((long long)rowj * Wo + wo0) * COUT;
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+      const int q = tid + 256 * k, px = q / C8N;
+      dr[k] = (wo0 + px < Wo) ? __ldg(reinterpret_cast<const uint4*>(dzr) + q) : make_uint4(0, 0, 0, 0);
+    }
+  };
+  int job = blockIdx.x;
+  if (job < total) fetch(job);
+  for (; job < total; job += gridDim.x) {
+    __syncthreads();                                    // the previous job's reads of tile / sd are done
+#pragma unroll
+    for (int k = 0; k < NX; ++k)
+      if (rc[k] >= 0) tile[(rc[k] >> 16) * PITCH + (rc[k] & 0xffff)] = xr[k];
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+      const int q = tid + 256 * k;
+      const uint4 u = dr[k];
+      *reinterpret_cast<float4*>(sd + q * 8) = make_float4(bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y));
+      *reinterpret_cast<float4*>(sd + q * 8 + 4) = make_float4(bf16lo(u.z), bf16hi(u.z), bf16lo(u.w), bf16hi(u.w));
+    }
+    __syncthreads();
+    if (job + (int)gridDim.x < total) fetch(job + gridDim.x);      // in flight during the arithmetic below
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      if (!act[it]) continue;
+      const float* sdp = sd + c8v[it];
+      const float* t0 = tile + toff[it][0];
+      const float* t1 = tile + toff[it][1];
+      const float* t2 = tile + toff[it][2];
+      const float* t3 = tile + toff[it][3];
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int px = warp * 16 + i;
+        const float4 d0 = *reinterpret_cast<const float4*>(sdp + px * COUT);
+        const float4 d1 = *reinterpret_cast<const float4*>(sdp + px * COUT + 4);
+        const float a[4] = {t0[px * S], t1[px * S], t2[px * S], t3[px * S]};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float* r = acc[it][j];
+          r[0] = fmaf(a[j], d0.x, r[0]); r[1] = fmaf(a[j], d0.y, r[1]); r[2] = fmaf(a[j], d0.z, r[2]); r[3] = fmaf(a[j], d0.w, r[3]);
+          r[4] = fmaf(a[j], d1.x, r[4]); r[5] = fmaf(a[j], d1.y, r[5]); r[6] = fmaf(a[j], d1.z, r[6]); r[7] = fmaf(a[j], d1.w, r[7]);
+        }
+      }
+    }
+  }
+  // reduce the eight pixel groups (warps) through shared memory, then one atomic per (k, co) per block
+  __syncthreads();
+  float* red = sm;                                      // [8][28 * COUT]
+  constexpr int STRIDE_W = 28 * COUT;
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    if (!act[it]) continue;
+    const int item = lane + 32 * it, kq = item / C8N;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float* dst = red + warp * STRIDE_W + (kq * 4 + j) * COUT + c8v[it];
+      *reinterpret_cast<float4*>(dst) = make_float4(acc[it][j][0], acc[it][j][1], acc[it][j][2], acc[it][j][3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[it][j][4], acc[it][j][5], acc[it][j][6], acc[it][j][7]);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 27 * COUT; i += 256) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[w * STRIDE_W + i];
+    atomicAdd(dw + i, sum);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // adjoints of the bilinear upsamplings.  Gather form: every source pixel enumerates the few output
 // pixels that read it and re-evaluates PyTorch's forward index/weight formula for each, so clamped
@@ -1451,7 +1589,38 @@ int b200seg_smallcin_wgrad(const void* x, int x_dtype, const void* dz, int dtype
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   const long long P = (long long)B * Ho * Wo;
   cudaStream_t st0 = (cudaStream_t)s;
-  if (Cin == 3 && Cout <= 64) {                  // the two stems of the path: row-tile kernel
+  if (Cin == 3 && (Cout == 32 || Cout == 64) && dtype == B200SEG_BF16 && (long long)3 * H * W < (1LL << 30)) {
+    // the stems of the two models in the training precision of the path: software-pipelined kernel
+    const long long jobs = (long long)B * Ho * ((Wo + 127) / 128);
+    B200_REQUIRE(jobs < (1LL << 31), "smallcin_wgrad: too many row segments");
+    long long gb = (long long)sm_count() * 2;
+    if (gb > jobs) gb = jobs;
+    const int ncol = 127 * stride + 3;
+    size_t smem_t = (size_t)(((9 * (ncol + 3) + 3) & ~3) + 128 * Cout) * sizeof(float);
+    const size_t red_b = (size_t)8 * 28 * Cout * sizeof(float);
+    if (smem_t < red_b) smem_t = red_b;
+#define LAUNCH_S(TI, SS, CO)                                                                                             \
+  {                                                                                                                     \
+    static bool attr_set = false;                                                                                       \
+    if (!attr_set) {                                                                                                    \
+      cudaFuncSetAttribute(stem_wgrad_bf16_kernel<TI, SS, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); \
+      attr_set = true;                                                                                                  \
+    }                                                                                                                   \
+    stem_wgrad_bf16_kernel<TI, SS, CO><<<(unsigned)gb, 256, smem_t, st0>>>((const TI*)x, (const bf16*)dz, dw, B, H, W, Ho, Wo); \
+  }
+#define LAUNCH_SC(TI)                                                                                                    \
+  {                                                                                                                     \
+    if (stride == 2) { if (Cout == 32) LAUNCH_S(TI, 2, 32) else LAUNCH_S(TI, 2, 64) }                                   \
+    else { if (Cout == 32) LAUNCH_S(TI, 1, 32) else LAUNCH_S(TI, 1, 64) }                                               \
+  }
+    if (x_dtype == B200SEG_F32) LAUNCH_SC(float)
+    else if (x_dtype == B200SEG_BF16) LAUNCH_SC(bf16)
+    else return set_error(-1, "smallcin_wgrad: bad dtypes");
+#undef LAUNCH_SC
+#undef LAUNCH_S
+    return check_launch("smallcin_wgrad");
+  }
+  if (Cin == 3 && Cout <= 64) {                  // other stems / fp32 training: row-tile kernel
     const long long jobs = (long long)B * Ho * ((Wo + 127) / 128);
     long long gb = (long long)sm_count() * 4;
     if (gb > jobs) gb = jobs;

@@ -145,8 +145,9 @@ def test_depthwise_backward(dt, B, H, W, C, stride):
     assert _err(dw9.t().reshape(C, 1, 3, 3), ww.grad) < (1e-4 if dt == torch.float32 else 1e-3)
 
 
-@pytest.mark.parametrize("xdt,dt", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16)])
-@pytest.mark.parametrize("B,H,W,Cout,stride", [(2, 32, 48, 32, 2), (1, 17, 19, 16, 1), (1, 16, 16, 64, 1)])
+@pytest.mark.parametrize("xdt,dt", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16), (torch.float32, torch.bfloat16)])
+@pytest.mark.parametrize("B,H,W,Cout,stride", [(2, 32, 48, 32, 2), (1, 17, 19, 16, 1), (1, 16, 16, 64, 1),
+                                               (3, 40, 300, 32, 1), (2, 37, 517, 32, 2), (2, 21, 260, 64, 1), (5, 96, 512, 32, 2)])
 def test_smallcin_wgrad(xdt, dt, B, H, W, Cout, stride):
     x = _rand(B, 3, H, W, seed=16).to(xdt)
     w = _rand(Cout, 3, 3, 3, seed=17, scale=0.3)
