@@ -62,6 +62,75 @@ softmax_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ 
   }
 }
 
+// Four consecutive pixels per thread (HW % 4 == 0): the class planes are read and the gradient planes written with 16-byte
+// accesses, all C plane loads of the thread issued before the first use -- a quarter of the memory instructions of the
+// one-pixel kernel above, which ran at 3.4 TB/s on the 370 MB of the B = 32 step.
+template <int CMAX>
+__global__ void __launch_bounds__(256)
+softmax_ce_x4_kernel(const float* __restrict__ logits, const int64_t* __restrict__ target, float* __restrict__ loss_sum,
+                     float* __restrict__ dlogits, float grad_scale, const float* __restrict__ counts, int B, int C,
+                     unsigned HW4) {
+  const unsigned total = (unsigned)B * HW4;             // groups of 4 pixels (launcher: < 2^31)
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  float loss = 0.f;
+  if (idx < total) {
+    const unsigned b = idx / HW4, g = idx - b * HW4;
+    const float4* lp = reinterpret_cast<const float4*>(logits) + (size_t)b * C * HW4 + g;
+    float4 v[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      v[c] = (c < C) ? __ldg(lp + (size_t)c * HW4) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    const longlong2 t01 = __ldg(reinterpret_cast<const longlong2*>(target) + (size_t)idx * 2);
+    const longlong2 t23 = __ldg(reinterpret_cast<const longlong2*>(target) + (size_t)idx * 2 + 1);
+    const long long tt[4] = {t01.x, t01.y, t23.x, t23.y};
+    const float gs = (dlogits && counts) ? grad_scale / fmaxf(__ldg(counts), 1.f) : grad_scale;
+    float inv[4];
+    bool valid[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      float m = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) m = fmaxf(m, (&v[c].x)[p]);
+      float sum = 0.f, zt = 0.f;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) {
+        const float z = (&v[c].x)[p] - m;
+        if (c == (int)tt[p]) zt = z;
+        const float e = (c < C) ? expf(z) : 0.f;
+        (&v[c].x)[p] = e;
+        sum += e;
+      }
+      valid[p] = tt[p] >= 0 && tt[p] < C;
+      inv[p] = 1.f / sum;
+      if (valid[p]) loss += logf(sum) - zt;
+    }
+    if (dlogits) {
+      float4* gp = reinterpret_cast<float4*>(dlogits) + (size_t)b * C * HW4 + g;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) {
+        if (c < C) {
+          float4 o;
+#pragma unroll
+          for (int p = 0; p < 4; ++p)
+            (&o.x)[p] = valid[p] ? ((&v[c].x)[p] * inv[p] - (c == (int)tt[p] ? 1.f : 0.f)) * gs : 0.f;
+          gp[(size_t)c * HW4] = o;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+  __shared__ float wsum[8];
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = loss;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t = wsum[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffu, t, o);
+    if (threadIdx.x == 0) atomicAdd(loss_sum, t);
+  }
+}
+
 int launch_softmax_ce_generic(const float* logits, const int64_t* target, float* loss_sum, float* dlogits, float grad_scale,
                               const float* counts, int B, int C, long long HW, cudaStream_t st);   // generic_ops.cu
 
@@ -93,6 +162,16 @@ extern "C" int b200seg_softmax_ce(const float* logits, const int64_t* target, fl
   const long long total = (long long)B * HW;
   const unsigned grid = (unsigned)((total + 255) / 256);
   cudaStream_t st = (cudaStream_t)s;
+  const bool aligned = HW % 4 == 0 && total / 4 < (1LL << 31) && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(target) & 15) == 0 && (!dlogits || (reinterpret_cast<uintptr_t>(dlogits) & 15) == 0);
+  if (C <= 16 && aligned) {
+    const unsigned g4 = (unsigned)((total / 4 + 255) / 256);
+    if (C <= 10)          // the path's 10 classes: no dead class slots in registers
+      softmax_ce_x4_kernel<10><<<g4, 256, 0, st>>>(logits, target, loss_sum, dlogits, grad_scale, counts, B, C, (unsigned)(HW / 4));
+    else
+      softmax_ce_x4_kernel<16><<<g4, 256, 0, st>>>(logits, target, loss_sum, dlogits, grad_scale, counts, B, C, (unsigned)(HW / 4));
+    return check_launch("softmax_ce");
+  }
   if (C <= 16)
     softmax_ce_kernel<16><<<grid, 256, 0, st>>>(logits, target, loss_sum, dlogits, grad_scale, counts, B, C, HW);
   else if (C <= 32)

@@ -222,7 +222,7 @@ def test_maxpool_and_nhwc_to_nchw():
         assert torch.equal(y, x[:, :10].float())
 
 
-@pytest.mark.parametrize("B,C,H,W", [(2, 10, 64, 128), (1, 10, 7, 9), (3, 19, 8, 8), (1, 1, 4, 4)])
+@pytest.mark.parametrize("B,C,H,W", [(2, 10, 64, 128), (1, 10, 7, 9), (3, 19, 8, 8), (1, 1, 4, 4), (2, 13, 16, 24), (3, 16, 4, 4)])
 def test_softmax_ce_fused_forward_and_gradient(B, C, H, W):
     lg = _rand(B, C, H, W, seed=19, scale=3.0).requires_grad_(True)
     tg = torch.randint(0, C, (B, H, W), generator=torch.Generator().manual_seed(20)).to(DEV)
