@@ -276,7 +276,9 @@ using namespace b200;
 extern "C" int b200seg_conv_rs_supported(int H, int W, int Cin, int Cout) {
   const int cn = (Cout + 15) & ~15;
   const int k_chunks = (Cin + 63) / 64;
-  return (cn == 16 || cn == 32) && W >= 96 && H >= 3 && Cin % 8 == 0 && Cout % 8 == 0 &&
+  // cn = 80: the data gradient of up4.conv.0 (32 -> 80 channels): N = 240, two accumulators = 480 TMEM columns, the
+  // epilogue's two running rows take 160 registers (one CTA per SM, 255 registers per thread)
+  return (cn == 16 || cn == 32 || cn == 80) && W >= 96 && H >= 3 && Cin % 8 == 0 && Cout % 8 == 0 &&
          k_chunks * 3 * (3 * cn * 128) <= 120 * 1024;
 }
 
@@ -312,5 +314,6 @@ extern "C" int b200seg_conv_rs(const void* x, const void* w, const float* bias, 
     if (rc) return rc;
   }
   if (cn == 16) return launch_conv_rs<16>(tmA, tmB, a, flags, (cudaStream_t)s);
+  if (cn == 80) return launch_conv_rs<80>(tmA, tmB, a, flags, (cudaStream_t)s);
   return launch_conv_rs<32>(tmA, tmB, a, flags, (cudaStream_t)s);
 }

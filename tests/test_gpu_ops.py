@@ -284,6 +284,8 @@ RS_CASES = [  # B, H, W, Cin, Cout, act, res
     (5, 7, 130, 24, 16, 1, True),        # 16-column variant, many short strips (ranges span images)
     (1, 128, 256, 32, 8, 0, False),      # Cout = 8
     (2, 33, 257, 136, 32, 1, False),     # odd sizes, 3 K chunks
+    (2, 128, 256, 32, 80, 0, True),      # data gradient of up4.conv.0 (32 -> 80): N = 240, accumulate into res
+    (1, 9, 150, 16, 72, 1, False),       # 72 -> 80 columns, ragged tile
 ]
 
 
