@@ -261,6 +261,11 @@ extern "C" int b200seg_conv_wgrad_tc(const void* x, const void* dz, float* dw, i
   const int stage_bytes = 2 * WG_BOX + a.n_boxes * (a.rowmode ? WG_XBOX : WG_BOX);
   int stages = (227 * 1024 - 2048) / stage_bytes;
   if (stages > 4) stages = 4;
+  {
+    static int cap = -1;          // B200SEG_WGRAD_STAGES: cap of the load ring (a smaller footprint lets main-stream CTAs co-reside)
+    if (cap < 0) { const char* e = getenv("B200SEG_WGRAD_STAGES"); cap = e ? atoi(e) : 0; }
+    if (cap > 0 && stages > cap) stages = cap;
+  }
   B200_REQUIRE(stages >= 1, "conv_wgrad_tc: stage does not fit");
   a.stages = stages;
   const int smem = stages * stage_bytes + 1024 + 256;
