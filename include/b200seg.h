@@ -190,6 +190,12 @@ int b200seg_bn_finalize(const void* z, int dtype, const double* sum, const doubl
 /* a = act(z*scale + shift) (+ res)   -- BN apply + ReLU/ReLU6 (+ inverted-residual shortcut) */
 int b200seg_bn_apply(const void* z, const float* scale, const float* shift, const void* res, void* a, int dtype,
                      long long P, int C, int act, b200seg_stream_t s);
+/* b200seg_bn_finalize + b200seg_bn_apply in one launch: every block derives the per-channel constants from the slot sums
+ * of b200seg_bn_stats (st_sums: f64 [nslot][2][C] = sum | sum of squares, shifted by z at pixel 0) and the first row of
+ * blocks publishes sv = f32 [4][C] (mean, invstd, scale, shift) and updates the running statistics (train.py:24,36). */
+int b200seg_bn_finalize_apply(const void* z, const double* st_sums, int nslot, const float* gamma, const float* beta, float eps,
+                              float momentum, float* running_mean, float* running_var, float* sv, const void* res, void* a,
+                              int dtype, long long P, int C, int act, b200seg_stream_t s);
 /* native_batch_norm_backward + hardtanh/threshold_backward, pass 1: sg[c] += sum g, sgx[c] += sum g*xhat,
  * g = da * act'(z*scale+shift), xhat = (z-mean)*invstd.   (d beta = sg, d gamma = sgx) */
 int b200seg_bn_bwd_reduce(const void* da, const void* z, const float* scale, const float* shift, const float* mean,
@@ -200,6 +206,10 @@ int b200seg_bn_bwd_reduce(const void* da, const void* z, const float* scale, con
 int b200seg_bn_bwd_apply(const void* da, const void* z, const float* scale, const float* shift, const float* mean,
                          const float* invstd, const float* sg, const float* sgx, void* dz, int dtype, long long P,
                          int C, int act, b200seg_stream_t s);
+/* pass 2 reading the f64 slot sums of pass 1 directly (red: [nslot][2][C] = sum g | sum g*xhat; sv as above): no f64 -> f32
+ * launch between the two passes. */
+int b200seg_bn_bwd_apply_slots(const void* da, const void* z, const float* sv, const double* red, int nslot, void* dz,
+                               int dtype, long long P, int C, int act, b200seg_stream_t s);
 /* Train-mode BatchNorm2d forward / backward of the small and mid-size layers in ONE launch per direction: a thread-block cluster
  * owns 16 channels, reduces through distributed shared memory and applies in the same kernel (nn.BatchNorm2d in model.train(),
  * train.py:24,36, and its backward, train.py:38).  bf16, C % 16 == 0, tensors up to ~40 MB (b200seg_bn_cluster_supported);

@@ -56,6 +56,8 @@ _PROTOS = {
     "b200seg_bn_cluster_fwd": [_vp, _ll, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "b200seg_bn_cluster_bwd": [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp],
     "b200seg_bn_bwd_apply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _vp],
+    "b200seg_bn_bwd_apply_slots": [_vp, _vp, _vp, _vp, _i, _vp, _i, _ll, _i, _i, _vp],
+    "b200seg_bn_finalize_apply": [_vp, _vp, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _vp],
     "b200seg_act_bwd": [_vp, _vp, _vp, _i, _ll, _i, _vp],
     "b200seg_colsum": [_vp, _i, _ll, _i, _vp, _i, _ll, _vp],
     "b200seg_f64_to_f32": [_vp, _vp, _i, _i, _ll, _f, _vp],

@@ -7,6 +7,8 @@ from __future__ import annotations
 
 from typing import Optional
 
+import os
+
 import torch
 
 from . import _cabi
@@ -398,6 +400,10 @@ def _P(t):
 BN_CLUSTER = True        # small / mid-size bf16 layers: one cluster-synchronised launch per direction (csrc/bn_cluster.cu)
 
 
+# large-layer BatchNorm: per-channel constants derived inside the apply kernels (no bn_finalize / f64->f32 launches)
+BN_FUSED_CONST = os.environ.get("B200SEG_BN_FUSED_CONST", "1") != "0"
+
+
 def bn_train_forward(z, gamma, beta, running_mean, running_var, eps: float, momentum: float, act: int, res=None):
     """Train-mode BatchNorm over NHWC z (+act, +residual).  Updates the running stats in place.
     Returns (a, saved) where saved = (mean, invstd, scale, shift) for the backward pass.
@@ -415,6 +421,12 @@ def bn_train_forward(z, gamma, beta, running_mean, running_var, eps: float, mome
     st = zero_pool.take((NSLOT, 2, C), z.device)                              # slot-major: [slot][sum | sumsq][C]
     check(lib.b200seg_bn_stats(ptr(z), _dt(z), P, C, ptr(st[0, 0]), ptr(st[0, 1]), NSLOT, 2 * C, _stream()), "bn_stats")
     sv = torch.empty(4, C, device=z.device, dtype=torch.float32)
+    if BN_FUSED_CONST:        # finalize inside the apply launch (every block repeats the per-channel arithmetic)
+        a = torch.empty_like(z)
+        check(lib.b200seg_bn_finalize_apply(ptr(z), ptr(st), NSLOT, ptr(gamma), ptr(beta), eps, momentum, ptr(running_mean),
+                                            ptr(running_var), ptr(sv), ptr(res), ptr(a), _dt(z), P, C, act, _stream()),
+              "bn_finalize_apply")
+        return a, sv
     check(lib.b200seg_bn_finalize(ptr(z), _dt(z), ptr(st[0, 0]), ptr(st[0, 1]), NSLOT, 2 * C, P, ptr(gamma), ptr(beta), eps, momentum, ptr(running_mean),
                                   ptr(running_var), ptr(sv[0]), ptr(sv[1]), ptr(sv[2]), ptr(sv[3]), C, _stream()),
           "bn_finalize")
@@ -440,6 +452,11 @@ def bn_train_backward(da, z, sv, act: int, red=None):
         return dz, g32[1], g32[0]
     check(lib.b200seg_bn_bwd_reduce(ptr(da), ptr(z), ptr(sv[2]), ptr(sv[3]), ptr(sv[0]), ptr(sv[1]), _dt(z), P, C, act,
                                     ptr(red[0, 0]), ptr(red[0, 1]), NSLOT, 2 * C, _stream()), "bn_bwd_reduce")
+    if BN_FUSED_CONST and not own_red:      # the training step: the apply pass sums the f64 slots itself
+        dz = torch.empty_like(z)
+        check(lib.b200seg_bn_bwd_apply_slots(ptr(da), ptr(z), ptr(sv), ptr(red), NSLOT, ptr(dz), _dt(z), P, C, act, _stream()),
+              "bn_bwd_apply_slots")
+        return dz, None, None
     g32 = torch.empty(2, C, device=z.device, dtype=torch.float32)
     check(lib.b200seg_f64_to_f32(ptr(red), ptr(g32), 2 * C, NSLOT, 2 * C, 1.0, _stream()), "f64_to_f32")
     dz = torch.empty_like(z)

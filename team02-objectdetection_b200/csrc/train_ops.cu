@@ -204,18 +204,61 @@ __global__ void bn_finalize_kernel(const T* __restrict__ z0, const double* __res
 // each, twice per layer per step) disappear.  `counter` is a zeroed 32-bit word per reduction.
 // a = act(z * scale + shift) (+ residual).  Thread = one channel vector x several pixels (same (tx, ty) layout as the
 // reductions): the per-channel constants are loaded once per thread instead of once per element.
-template <typename T, bool HAS_RES>
+// FIN: the per-channel constants are not read from `scale` / `shift` but derived by every block from the slot sums of
+// bn_stats (bn_finalize_kernel's arithmetic, redundantly per block; the blocks with blockIdx.x == 0 also publish mean /
+// invstd / scale / shift for the backward pass and update the running statistics).  With ~4 blocks per SM that is a few
+// hundred f64 loads per block from L2 -- and one launch plus one dependency edge less per layer in the step graph
+// (the 25 one-block finalize launches cost 5 us each on the critical path).
+struct BnFin {
+  const double* sum; const double* sumsq; int nslot; long long slot_stride; long long n;
+  const float* gamma; const float* beta; float eps, momentum;
+  float* running_mean; float* running_var; float* mean_out; float* invstd_out; float* scale_out; float* shift_out;
+};
+
+template <typename T, bool HAS_RES, bool FIN>
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const T* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
-                const T* __restrict__ res, T* __restrict__ a, long long P, int C, int ppb, int act) {
+                const T* __restrict__ res, T* __restrict__ a, long long P, int C, int ppb, int act, const BnFin f) {
   using V = Vec16<T>;
   constexpr int VN = V::N;
   const int TY = blockDim.y;
   const int c0 = (blockIdx.y * blockDim.x + threadIdx.x) * VN;
-  if (c0 >= C) return;
   float ksc[VN], ksh[VN];
+  if constexpr (FIN) {
+    __shared__ float s_sc[256 * VN], s_sh[256 * VN];
+    const int cb = blockIdx.y * blockDim.x * VN;
+    const int nch = min((int)blockDim.x * VN, C - cb);
+    for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < nch; i += blockDim.x * blockDim.y) {
+      const int c = cb + i;
+      double s1 = 0.0, s2 = 0.0;
+      for (int sl = 0; sl < f.nslot; ++sl) { s1 += f.sum[sl * f.slot_stride + c]; s2 += f.sumsq[sl * f.slot_stride + c]; }
+      const double ms = s1 / (double)f.n;                     // mean of (z - k), k = z at pixel 0
+      double var = s2 / (double)f.n - ms * ms;
+      if (var < 0.0) var = 0.0;
+      const double m = ms + (double)to_f32<T>(z[c]);
+      const float invstd = (float)(1.0 / sqrt(var + (double)f.eps));
+      const float sc = f.gamma[c] * invstd;
+      const float sh = f.beta[c] - (float)m * sc;
+      s_sc[i] = sc;
+      s_sh[i] = sh;
+      if (blockIdx.x == 0) {
+        f.mean_out[c] = (float)m; f.invstd_out[c] = invstd; f.scale_out[c] = sc; f.shift_out[c] = sh;
+        if (f.running_mean) {
+          const double unbiased = f.n > 1 ? var * ((double)f.n / (double)(f.n - 1)) : var;
+          f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * (float)m;
+          f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * (float)unbiased;
+        }
+      }
+    }
+    __syncthreads();
+    if (c0 >= C) return;
 #pragma unroll
-  for (int j = 0; j < VN; ++j) { ksc[j] = __ldg(scale + c0 + j); ksh[j] = __ldg(shift + c0 + j); }
+    for (int j = 0; j < VN; ++j) { ksc[j] = s_sc[threadIdx.x * VN + j]; ksh[j] = s_sh[threadIdx.x * VN + j]; }
+  } else {
+    if (c0 >= C) return;
+#pragma unroll
+    for (int j = 0; j < VN; ++j) { ksc[j] = __ldg(scale + c0 + j); ksh[j] = __ldg(shift + c0 + j); }
+  }
   const float lo = act != B200SEG_ACT_NONE ? 0.f : -INFINITY, hi = act == B200SEG_ACT_RELU6 ? 6.f : INFINITY;
   const long long p0 = (long long)blockIdx.x * ppb, p1 = min(p0 + ppb, P);
   auto body = [&](const V& v, const V& r, long long off) {
@@ -306,23 +349,45 @@ bn_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ z, const fl
 }
 
 // dz = scale * (g - mean(g) - xhat * mean(g*xhat))        (scale = gamma * invstd; sums passed as f32, mean = sum * inv_n)
-template <typename T>
+// SLOTS: sum(g) / sum(g*xhat) are not read as f32 vectors but summed by every block from the f64 slot copies bn_bwd_reduce
+// left in the gradient staging (sg64 / sgx64, `nslot` copies `slot_stride` apart): the f64 -> f32 launch between the two
+// BatchNorm-backward kernels disappears from the step graph.
+template <typename T, bool SLOTS>
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_kernel(const T* __restrict__ da, const T* __restrict__ z, const float* __restrict__ scale,
                     const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
                     const float* __restrict__ sg, const float* __restrict__ sgx, float inv_n, T* __restrict__ dz,
-                    long long P, int C, int ppb, int act) {
+                    long long P, int C, int ppb, int act, const double* __restrict__ sg64, const double* __restrict__ sgx64,
+                    int nslot, long long slot_stride) {
   using V = Vec16<T>;
   constexpr int VN = V::N;
   const int TY = blockDim.y;
   const int c0 = (blockIdx.y * blockDim.x + threadIdx.x) * VN;
-  if (c0 >= C) return;
   float ksc[VN], ksh[VN], kmu[VN], kis[VN], kmg[VN], kmx[VN];
+  if constexpr (SLOTS) {
+    __shared__ float s_mg[256 * VN], s_mx[256 * VN];
+    const int cb = blockIdx.y * blockDim.x * VN;
+    const int nch = min((int)blockDim.x * VN, C - cb);
+    for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 2 * nch; i += blockDim.x * blockDim.y) {
+      const int which = i >= nch, ci = i - which * nch;
+      const double* src = (which ? sgx64 : sg64) + cb + ci;
+      double t = 0.0;
+      for (int sl = 0; sl < nslot; ++sl) t += src[sl * slot_stride];
+      (which ? s_mx : s_mg)[ci] = (float)t * inv_n;            // same rounding as f64_to_f32 followed by * inv_n
+    }
+    __syncthreads();
+    if (c0 >= C) return;
+#pragma unroll
+    for (int j = 0; j < VN; ++j) { kmg[j] = s_mg[threadIdx.x * VN + j]; kmx[j] = s_mx[threadIdx.x * VN + j]; }
+  } else {
+    if (c0 >= C) return;
+#pragma unroll
+    for (int j = 0; j < VN; ++j) { kmg[j] = __ldg(sg + c0 + j) * inv_n; kmx[j] = __ldg(sgx + c0 + j) * inv_n; }
+  }
 #pragma unroll
   for (int j = 0; j < VN; ++j) {
     ksc[j] = __ldg(scale + c0 + j); ksh[j] = __ldg(shift + c0 + j);
     kmu[j] = __ldg(mean + c0 + j);  kis[j] = __ldg(invstd + c0 + j);
-    kmg[j] = __ldg(sg + c0 + j) * inv_n; kmx[j] = __ldg(sgx + c0 + j) * inv_n;
   }
   const long long p0 = (long long)blockIdx.x * ppb, p1 = min(p0 + ppb, P);
   const ActMask am(act);
@@ -1416,10 +1481,31 @@ int b200seg_bn_apply(const void* z, const float* scale, const float* shift, cons
   const int ppb = ew_ppb(block);
   dim3 grid(cdiv(P, ppb), cdiv(C / vn, block.x));
   cudaStream_t st = (cudaStream_t)s;
-#define BN_APPLY(T, R) bn_apply_kernel<T, R><<<grid, block, 0, st>>>((const T*)z, scale, shift, (const T*)res, (T*)a, P, C, ppb, act)
+  const BnFin nofin = {};
+#define BN_APPLY(T, R) bn_apply_kernel<T, R, false><<<grid, block, 0, st>>>((const T*)z, scale, shift, (const T*)res, (T*)a, P, C, ppb, act, nofin)
   DISPATCH_T(dtype, (res ? BN_APPLY(float, true) : BN_APPLY(float, false)), (res ? BN_APPLY(bf16, true) : BN_APPLY(bf16, false)), "bn_apply")
 #undef BN_APPLY
   return check_launch("bn_apply");
+}
+
+// bn_finalize + bn_apply in one launch (see BnFin): st = slot sums of b200seg_bn_stats ([nslot][2][C]: sum | sumsq),
+// sv = [4][C] out (mean, invstd, scale, shift) for the backward pass; running statistics updated in place (may be NULL).
+int b200seg_bn_finalize_apply(const void* z, const double* st_sums, int nslot, const float* gamma, const float* beta, float eps,
+                              float momentum, float* running_mean, float* running_var, float* sv, const void* res, void* a,
+                              int dtype, long long P, int C, int act, b200seg_stream_t s) {
+  const int vn = dtype == B200SEG_BF16 ? 8 : 4;
+  B200_REQUIRE(P > 0 && C > 0 && C % vn == 0 && nslot >= 1, "bn_finalize_apply: P=%lld C=%d nslot=%d", P, C, nslot);
+  B200_REQUIRE(z && st_sums && gamma && beta && sv && a, "bn_finalize_apply: null pointer");
+  const dim3 block = red_block(C / vn);
+  const int ppb = red_ppb(P, block, C / vn);          // few fat blocks: each one repeats the finalize arithmetic
+  dim3 grid(cdiv(P, ppb), cdiv(C / vn, block.x));
+  cudaStream_t st = (cudaStream_t)s;
+  const BnFin f = {st_sums, st_sums + C, nslot, 2LL * C, P, gamma, beta, eps, momentum, running_mean, running_var,
+                   sv, sv + C, sv + 2 * C, sv + 3 * C};
+#define BN_APPLY(T, R) bn_apply_kernel<T, R, true><<<grid, block, 0, st>>>((const T*)z, nullptr, nullptr, (const T*)res, (T*)a, P, C, ppb, act, f)
+  DISPATCH_T(dtype, (res ? BN_APPLY(float, true) : BN_APPLY(float, false)), (res ? BN_APPLY(bf16, true) : BN_APPLY(bf16, false)), "bn_finalize_apply")
+#undef BN_APPLY
+  return check_launch("bn_finalize_apply");
 }
 
 int b200seg_bn_bwd_reduce(const void* da, const void* z, const float* scale, const float* shift, const float* mean,
@@ -1447,9 +1533,27 @@ int b200seg_bn_bwd_apply(const void* da, const void* z, const float* scale, cons
   dim3 grid(cdiv(P, ppb), cdiv(C / vn, block.x));
   const float inv_n = 1.f / (float)P;
   cudaStream_t st = (cudaStream_t)s;
-  DISPATCH_T(dtype, (bn_bwd_apply_kernel<float><<<grid, block, 0, st>>>((const float*)da, (const float*)z, scale, shift, mean, invstd, sg, sgx, inv_n, (float*)dz, P, C, ppb, act)),
-             (bn_bwd_apply_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)da, (const bf16*)z, scale, shift, mean, invstd, sg, sgx, inv_n, (bf16*)dz, P, C, ppb, act)), "bn_bwd_apply")
+  DISPATCH_T(dtype, (bn_bwd_apply_kernel<float, false><<<grid, block, 0, st>>>((const float*)da, (const float*)z, scale, shift, mean, invstd, sg, sgx, inv_n, (float*)dz, P, C, ppb, act, nullptr, nullptr, 0, 0)),
+             (bn_bwd_apply_kernel<bf16, false><<<grid, block, 0, st>>>((const bf16*)da, (const bf16*)z, scale, shift, mean, invstd, sg, sgx, inv_n, (bf16*)dz, P, C, ppb, act, nullptr, nullptr, 0, 0)), "bn_bwd_apply")
   return check_launch("bn_bwd_apply");
+}
+
+// bn_bwd_apply reading the f64 slot sums of b200seg_bn_bwd_reduce directly (red = [nslot][2][C]: sum g | sum g*xhat);
+// sv = [4][C] (mean, invstd, scale, shift) as written by the forward pass.
+int b200seg_bn_bwd_apply_slots(const void* da, const void* z, const float* sv, const double* red, int nslot, void* dz,
+                               int dtype, long long P, int C, int act, b200seg_stream_t s) {
+  const int vn = dtype == B200SEG_BF16 ? 8 : 4;
+  B200_REQUIRE(P > 0 && C > 0 && C % vn == 0 && nslot >= 1, "bn_bwd_apply_slots: P=%lld C=%d nslot=%d", P, C, nslot);
+  B200_REQUIRE(da && z && sv && red && dz, "bn_bwd_apply_slots: null pointer");
+  const dim3 block = red_block(C / vn);
+  const int ppb = red_ppb(P, block, C / vn);
+  dim3 grid(cdiv(P, ppb), cdiv(C / vn, block.x));
+  const float inv_n = 1.f / (float)P;
+  cudaStream_t st = (cudaStream_t)s;
+  const float *mean = sv, *invstd = sv + C, *scale = sv + 2 * C, *shift = sv + 3 * C;
+  DISPATCH_T(dtype, (bn_bwd_apply_kernel<float, true><<<grid, block, 0, st>>>((const float*)da, (const float*)z, scale, shift, mean, invstd, nullptr, nullptr, inv_n, (float*)dz, P, C, ppb, act, red, red + C, nslot, 2LL * C)),
+             (bn_bwd_apply_kernel<bf16, true><<<grid, block, 0, st>>>((const bf16*)da, (const bf16*)z, scale, shift, mean, invstd, nullptr, nullptr, inv_n, (bf16*)dz, P, C, ppb, act, red, red + C, nslot, 2LL * C)), "bn_bwd_apply_slots")
+  return check_launch("bn_bwd_apply_slots");
 }
 
 int b200seg_act_bwd(const void* da, const void* a_out, void* dz, int dtype, long long N, int act, b200seg_stream_t s) {

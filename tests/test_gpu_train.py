@@ -81,6 +81,37 @@ def test_batchnorm_train_forward_backward(dt, B, H, W, C, act, res):
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,H,W,C,act,res", [(2, 24, 40, 96, 2, False), (3, 17, 23, 24, 1, True), (2, 64, 128, 32, 2, False),
+                                             (1, 9, 11, 2056, 0, False)])
+def test_batchnorm_constants_fused_into_the_apply_kernels(dt, B, H, W, C, act, res, monkeypatch):
+    """The streamed BatchNorm path of the training step derives the per-channel constants inside the apply kernels
+    (b200seg_bn_finalize_apply, b200seg_bn_bwd_apply_slots).  Same arithmetic as the bn_finalize / f64->f32 launches they
+    replace, so the results agree to rounding -- not bit for bit: the f64 slot sums themselves depend on the order in which
+    the reduction blocks' atomics land (C = 2056: two channel blocks)."""
+    monkeypatch.setattr(ops, "BN_CLUSTER", False)
+    z = _nhwc((_rand(B, C, H, W, seed=31) * 2 + 0.5).to(dt))
+    gamma, beta = _rand(C, seed=32).abs() + 0.5, _rand(C, seed=33, scale=0.2)
+    r = _nhwc(_rand(B, C, H, W, seed=34).to(dt)) if res else None
+    da = _nhwc(_rand(B, C, H, W, seed=35).to(dt))
+    out = {}
+    for fused in (False, True):
+        monkeypatch.setattr(ops, "BN_FUSED_CONST", fused)
+        rm, rv = _rand(C, seed=36, scale=0.1), _rand(C, seed=37).abs() + 0.5
+        a, sv = ops.bn_train_forward(z, gamma, beta, rm, rv, 1e-5, 0.1, act, r)
+        red = torch.zeros(ops.NSLOT, 2, C, device=DEV, dtype=torch.float64)
+        dz, _, _ = ops.bn_train_backward(da, z, sv, act, red=red)
+        out[fused] = (a, sv, rm, rv, dz, red)
+    (a0, sv0, rm0, rv0, dz0, red0), (a1, sv1, rm1, rv1, dz1, red1) = out[False], out[True]
+    for x0, x1 in ((sv0, sv1), (rm0, rm1), (rv0, rv1), (red0, red1)):
+        assert torch.allclose(x0.double(), x1.double(), rtol=1e-5, atol=1e-6)
+    for x0, x1 in ((a0, a1), (dz0, dz1)):
+        d = (x0.float() - x1.float()).abs()
+        scale = x0.float().abs().max()
+        assert float(d.max()) <= (1e-5 if dt == torch.float32 else 8e-3) * float(scale)        # at most one ulp of the storage type
+        assert float((d > 0).float().mean()) < (1e-2 if dt == torch.float32 else 1e-3)          # and only where a sum sat on a rounding edge
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("B,H,W,Cin,Cout,taps", [(2, 16, 32, 64, 64, 1), (2, 9, 13, 24, 144, 1), (1, 16, 16, 16, 16, 1),
                                                  (2, 16, 32, 32, 32, 9), (1, 11, 7, 152, 64, 9), (3, 8, 16, 80, 40, 9)])
 def test_conv_wgrad_and_dgrad(dt, B, H, W, Cin, Cout, taps):
