@@ -71,6 +71,20 @@ __device__ __forceinline__ uint32_t all_loaded(const uint4 (&r)[N], uint32_t zma
 // "Batched streaming": the pixel loop first issues U rows of 16-byte loads per input (raw, not yet unpacked), then does
 // the arithmetic.  With the loads written inside the per-pixel body the compiler kept them behind the body's branches,
 // i.e. 32 bytes in flight per thread and ~16 KB per SM: the large-layer BatchNorm passes ran at 2.3-2.9 TB/s, latency-bound.
+// pixels per block of the apply kernels that derive their per-channel constants themselves (BnFin / SLOTS): enough blocks to
+// stream at full rate, few enough that the repeated prologue (<= 32 f64 loads per channel and block) stays negligible
+static inline int fat_ppb(long long P, const dim3& block, int cvecs) {
+  static int bps = 0;
+  if (bps == 0) { const char* e = getenv("B200SEG_BN_FAT_BPS"); bps = e ? atoi(e) : 4; if (bps < 1) bps = 1; }     // measured: 4 -> 8.20 ms, 8 / 16 / 32 -> 8.42 / 8.42 / 8.47
+  const long long gy = (cvecs + block.x - 1) / block.x;
+  const long long nb = (long long)sm_count() * bps;
+  long long ppb = (P * gy + nb - 1) / nb;
+  const long long lo = 8LL * block.y;
+  if (ppb < lo) ppb = lo;
+  if (ppb > 8192) ppb = 8192;
+  return (int)ppb;
+}
+
 template <typename T, int NOUT, int NIN, int U = 4, bool PIN = false, typename F>
 __device__ __forceinline__ void channel_reduce(const T* const (&in)[NIN], long long P, int C, int ppb, double* const* out,
                                                int nslot, long long slot_stride, F&& f) {
@@ -1497,7 +1511,7 @@ int b200seg_bn_finalize_apply(const void* z, const double* st_sums, int nslot, c
   B200_REQUIRE(P > 0 && C > 0 && C % vn == 0 && nslot >= 1, "bn_finalize_apply: P=%lld C=%d nslot=%d", P, C, nslot);
   B200_REQUIRE(z && st_sums && gamma && beta && sv && a, "bn_finalize_apply: null pointer");
   const dim3 block = red_block(C / vn);
-  const int ppb = red_ppb(P, block, C / vn);          // few fat blocks: each one repeats the finalize arithmetic
+  const int ppb = fat_ppb(P, block, C / vn);          // fat blocks: each one repeats the finalize arithmetic
   dim3 grid(cdiv(P, ppb), cdiv(C / vn, block.x));
   cudaStream_t st = (cudaStream_t)s;
   const BnFin f = {st_sums, st_sums + C, nslot, 2LL * C, P, gamma, beta, eps, momentum, running_mean, running_var,
@@ -1546,7 +1560,7 @@ int b200seg_bn_bwd_apply_slots(const void* da, const void* z, const float* sv, c
   B200_REQUIRE(P > 0 && C > 0 && C % vn == 0 && nslot >= 1, "bn_bwd_apply_slots: P=%lld C=%d nslot=%d", P, C, nslot);
   B200_REQUIRE(da && z && sv && red && dz, "bn_bwd_apply_slots: null pointer");
   const dim3 block = red_block(C / vn);
-  const int ppb = red_ppb(P, block, C / vn);
+  const int ppb = fat_ppb(P, block, C / vn);
   dim3 grid(cdiv(P, ppb), cdiv(C / vn, block.x));
   const float inv_n = 1.f / (float)P;
   cudaStream_t st = (cudaStream_t)s;
