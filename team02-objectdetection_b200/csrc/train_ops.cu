@@ -331,8 +331,8 @@ __device__ __forceinline__ float act_grad(float u, int act) {
 }
 
 // sum(g) and sum(g * xhat) with g = da * act'(u), xhat = (z - mean) * invstd
-template <typename T>
-__global__ void __launch_bounds__(256)
+template <typename T, int U = 4, int MINB = 2>
+__global__ void __launch_bounds__(256, MINB)
 bn_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ z, const float* __restrict__ scale,
                      const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
                      long long P, int C, int ppb, int act, double* sg, double* sgx, int nslot, long long slot_stride) {
@@ -351,7 +351,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ z, const fl
   }
   const ActMask am(act);
   const T* const ins[2] = {da, z};
-  channel_reduce<T, 2, 2, 4>(ins, P, C, ppb, outs, nslot, slot_stride, [&](const V (&v)[2], float (&acc)[2][V::N]) {
+  channel_reduce<T, 2, 2, U>(ins, P, C, ppb, outs, nslot, slot_stride, [&](const V (&v)[2], float (&acc)[2][V::N]) {
 #pragma unroll
     for (int j = 0; j < V::N; ++j) {
       const float u = fmaf(v[1].v[j], ksc[j], ksh[j]);
@@ -1532,6 +1532,18 @@ int b200seg_bn_bwd_reduce(const void* da, const void* z, const float* scale, con
   const int ppb = red_ppb(P, block, C / vn);
   dim3 grid(cdiv(P, ppb), cdiv(C / vn, block.x));
   cudaStream_t st = (cudaStream_t)s;
+  // B200SEG_BNR_VARIANT (tools only): 1 = 3 blocks/SM (80 registers, spills), 2 = 2 rows in flight at 4 blocks/SM.  Measured on
+  // the B = 32 step: default 8.33 ms, variant 1 8.62, variant 2 8.43 -- four rows in flight at 2 blocks/SM stays.
+  static int variant = -1;
+  if (variant < 0) { const char* e = getenv("B200SEG_BNR_VARIANT"); variant = e ? atoi(e) : 0; }
+  if (dtype == B200SEG_BF16 && variant == 1) {
+    bn_bwd_reduce_kernel<bf16, 4, 3><<<grid, block, 0, st>>>((const bf16*)da, (const bf16*)z, scale, shift, mean, invstd, P, C, ppb, act, sg, sgx, nslot, slot_stride);
+    return check_launch("bn_bwd_reduce");
+  }
+  if (dtype == B200SEG_BF16 && variant == 2) {
+    bn_bwd_reduce_kernel<bf16, 2, 4><<<grid, block, 0, st>>>((const bf16*)da, (const bf16*)z, scale, shift, mean, invstd, P, C, ppb, act, sg, sgx, nslot, slot_stride);
+    return check_launch("bn_bwd_reduce");
+  }
   DISPATCH_T(dtype, (bn_bwd_reduce_kernel<float><<<grid, block, 0, st>>>((const float*)da, (const float*)z, scale, shift, mean, invstd, P, C, ppb, act, sg, sgx, nslot, slot_stride)),
              (bn_bwd_reduce_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)da, (const bf16*)z, scale, shift, mean, invstd, P, C, ppb, act, sg, sgx, nslot, slot_stride)), "bn_bwd_reduce")
   return check_launch("bn_bwd_reduce");
