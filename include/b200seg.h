@@ -81,7 +81,8 @@ int b200seg_dwconv3x3_bf16w(const void* x, const void* w, const float* b, void* 
 int b200seg_conv_tc(const void* x, const void* w, const float* b, const void* res, void* y, int B, int H,
                     int W, int Cin, int Cout, int taps, int act, int flags, b200seg_stream_t s);
 
-/* 3x3 convolution (pad 1, stride 1) with few output channels (Cout <= 32) on wide maps as a ROW-STACKED implicit GEMM: the
+/* 3x3 convolution (pad 1, stride 1) with few output channels (Cout <= 32, or 65..80 for the data gradient of up4.conv.0:
+ * N = 240, two accumulators = 480 TMEM columns) on wide maps as a ROW-STACKED implicit GEMM: the
  * three vertical taps are stacked along the MMA N axis (one accumulator of 3*Cout columns per input row), the epilogue sums
  * the three accumulators that meet in an output row.  2.1x fewer tensor-pipe cycles and 3x fewer operand reads than
  * b200seg_conv_tc for the same operands and results (unet.py:58,61 -- up4's double_conv -- and their data gradients).
