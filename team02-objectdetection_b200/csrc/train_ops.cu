@@ -297,10 +297,13 @@ bn_apply_kernel(const T* __restrict__ z, const float* __restrict__ scale, const 
       rz[u] = V::ldraw(z + off + u * rowstep);
       if (HAS_RES) rr[u] = V::ldraw(res + off + u * rowstep);
     }
+    uint32_t dep = 0;
+    if constexpr (FIN && sizeof(T) == 2) dep = all_loaded(rz, opaque_zero(ppb));   // pin the batch (the finalize prologue's
+                                                                                 // registers made ptxas split it 4 + 4)
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       V v, r;
-      v.unpack(rz[u]);
+      v.unpack_dep(rz[u], dep);
       if (HAS_RES) r.unpack(rr[u]);
       body(v, r, off + u * rowstep);
     }

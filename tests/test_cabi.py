@@ -61,10 +61,12 @@ def test_streaming_kernels_keep_a_batch_of_loads_in_flight():
     spec = importlib.util.spec_from_file_location("sass_ldg_clusters", tool)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    got = mod.ldg_clusters(_cabi.LIB_PATH, "bn_bwd_reduce|bn_bwd_apply|upcat_bwd|upsample2x_concat_kernel|dw_wgrad_bf16", wide_only=True)
+    got = mod.ldg_clusters(_cabi.LIB_PATH, "bn_bwd_reduce|bn_bwd_apply|bn_apply_kernel|upcat_bwd|upsample2x_concat_kernel|dw_wgrad_bf16",
+                           wide_only=True)
     want = {
         "bn_bwd_reduce_kernel<__nv_bfloat16, 4, 2>": 8,       # 4 pixel rows x (da, z)
         "bn_bwd_apply_kernel<__nv_bfloat16, true>": 8,
+        "bn_apply_kernel<__nv_bfloat16, false, true>": 8,     # 8 rows of z; pinned (the finalize prologue made ptxas split it 4 + 4)
         "upcat_bwd_kernel<__nv_bfloat16>": 12,                # the 4 x 4 gather (16 loads, pinned by a data dependence)
         "upsample2x_concat_kernel<__nv_bfloat16>": 8,         # the 3 x 3 source neighbourhood (9 loads)
         "dw_wgrad_bf16_kernel<1, 4>": 12,                     # 4 dz + 3 x 6 x vectors of a 4-pixel group
